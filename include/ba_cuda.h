@@ -1,0 +1,239 @@
+/*
+ * ba_cuda.h -- C ABI of the B200-native bundle-adjustment hot path.
+ *
+ * This is the drop-in boundary that replaces the reference's use of the Ceres
+ * public API on its one hot path (all citations relative to the reference tree):
+ *
+ *   ceres::Problem problem;                       Main_Calibration/bundle_adjustment_manager.cpp:19
+ *   problem.AddResidualBlock(cost, NULL, ...)     bundle_adjustment_manager.cpp:37,50,67,81
+ *                                                 Test1_BundleAdjustment/main.cpp:76-79
+ *                                                 Test2_BundleAdjustment/main.cpp:75-78,90-94
+ *   Solver::Options{DENSE_SCHUR, progress}        bundle_adjustment_manager.cpp:90-92
+ *   ceres::Solve(options, &problem, &summary)     bundle_adjustment_manager.cpp:94
+ *   summary.FullReport()                          bundle_adjustment_manager.cpp:95
+ *   cv::projectPoints + error sum                 Main_Calibration/reprojection_check.cpp:69,81,100-101
+ *
+ * Conventions: every function returns 0 (BA_OK) or a negative ba_status; no
+ * exceptions and no exit() cross this boundary.  All host pointers are borrowed
+ * only for the duration of the call (the library copies / re-lays-out into HBM),
+ * unlike Ceres which optimises caller memory in place: the host calls
+ * ba_cuda_get_parameters() after ba_cuda_solve() to see the "in place" result.
+ * Indices are int32, counts int64, arithmetic fp64.  One host thread drives one
+ * ba_cuda_problem; one ba_cuda_problem is bound to one GPU.  There is NO CPU
+ * fallback in this library: without a CUDA device ba_cuda_create() fails.
+ *
+ * Multi-GPU: one process (rank) per GPU.  Every rank holds ALL f-blocks
+ * (cameras / markers) and a SHARD of the eliminated blocks (Model A: points with
+ * all their observations; Model B: frames with all their marker observations).
+ * ba_cuda_comm_init() joins the ranks through NCCL; ba_cuda_solve() is then a
+ * collective call (partial reduced camera systems are summed with one
+ * ncclAllReduce per linear solve, scalars with a second small one).
+ */
+#ifndef BA_CUDA_H_
+#define BA_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ba_cuda_problem ba_cuda_problem; /* opaque */
+
+typedef enum ba_status {
+  BA_OK = 0,
+  BA_ERR_INVALID_ARGUMENT = -1,
+  BA_ERR_CUDA = -2,          /* CUDA runtime error, see ba_cuda_last_error() */
+  BA_ERR_STATE = -3,         /* call order (e.g. solve before set_model_*) */
+  BA_ERR_NCCL = -4,
+  BA_ERR_OUT_OF_MEMORY = -5,
+  BA_ERR_NO_DEVICE = -6,
+  BA_ERR_UNSUPPORTED = -7
+} ba_status;
+
+/* How the reduced camera system (RCS) is solved; replaces
+ * options.linear_solver_type = DENSE_SCHUR (bundle_adjustment_manager.cpp:91). */
+typedef enum ba_rcs_solver {
+  BA_RCS_AUTO = 0,            /* dense Cholesky while the RCS is rig sized, PCG above */
+  BA_RCS_DENSE_CHOLESKY = 1,  /* == Ceres DENSE_SCHUR */
+  BA_RCS_PCG = 2              /* block-Jacobi PCG on the explicit block-sparse RCS
+                                 (Ceres ITERATIVE_SCHUR / SCHUR_JACOBI stopping rule) */
+} ba_rcs_solver;
+
+/* Mirrors ceres::TerminationType as far as this path can produce it. */
+typedef enum ba_termination {
+  BA_CONVERGENCE = 0,
+  BA_NO_CONVERGENCE = 1,
+  BA_FAILURE = 2
+} ba_termination;
+
+typedef enum ba_termination_reason {
+  BA_REASON_NONE = 0,
+  BA_REASON_GRADIENT_TOLERANCE = 1,
+  BA_REASON_PARAMETER_TOLERANCE = 2,
+  BA_REASON_FUNCTION_TOLERANCE = 3,
+  BA_REASON_MIN_TRUST_REGION_RADIUS = 4,
+  BA_REASON_MAX_ITERATIONS = 5,
+  BA_REASON_TOO_MANY_INVALID_STEPS = 6,
+  BA_REASON_INITIAL_EVALUATION_FAILED = 7
+} ba_termination_reason;
+
+/* The Ceres 1.14 Solver::Options fields the trust-region LM path reads; the
+ * defaults written by ba_cuda_options_init() are Ceres 1.14's. */
+typedef struct ba_cuda_options {
+  int32_t max_num_iterations;                /* 50 */
+  int32_t max_num_consecutive_invalid_steps; /* 5 */
+  int32_t jacobi_scaling;                    /* 1 */
+  int32_t rcs_solver;                        /* ba_rcs_solver, BA_RCS_AUTO */
+  int32_t pcg_max_iterations;                /* 500  (max_linear_solver_iterations) */
+  int32_t pcg_min_iterations;                /* 0 */
+  int32_t pcg_residual_reset_period;         /* 10 */
+  int32_t minimizer_progress_to_stdout;      /* 0 */
+  double initial_trust_region_radius;        /* 1e4 */
+  double max_trust_region_radius;            /* 1e16 */
+  double min_trust_region_radius;            /* 1e-32 */
+  double min_relative_decrease;              /* 1e-3 */
+  double min_lm_diagonal;                    /* 1e-6 */
+  double max_lm_diagonal;                    /* 1e32 */
+  double function_tolerance;                 /* 1e-6 */
+  double gradient_tolerance;                 /* 1e-10 */
+  double parameter_tolerance;                /* 1e-8 */
+  double pcg_eta;                            /* 1e-1 (q_tolerance) */
+  double pcg_r_tolerance;                    /* -1 (disabled, as LevenbergMarquardtStrategy does) */
+} ba_cuda_options;
+
+/* One row of Ceres' minimizer_progress_to_stdout table (IterationSummary). */
+typedef struct ba_cuda_iteration {
+  int32_t iteration;
+  int32_t step_is_valid;
+  int32_t step_is_successful;
+  int32_t linear_solver_iterations;
+  double cost;
+  double cost_change;
+  double gradient_max_norm;
+  double gradient_norm;
+  double step_norm;
+  double relative_decrease;   /* tr_ratio */
+  double trust_region_radius;
+  double iteration_time_s;
+} ba_cuda_iteration;
+
+typedef struct ba_cuda_summary {
+  int32_t termination_type;    /* ba_termination */
+  int32_t termination_reason;  /* ba_termination_reason */
+  int32_t num_iterations;      /* rows recorded, including row 0 */
+  int32_t num_successful_steps;
+  int32_t num_unsuccessful_steps;
+  int32_t rcs_solver_used;     /* ba_rcs_solver actually run */
+  int32_t rcs_dim;             /* scalar dimension of the reduced camera system */
+  int32_t num_jacobian_evaluations;
+  int32_t num_cost_evaluations;
+  int32_t num_linear_solves;
+  int64_t num_residuals;
+  int64_t num_free_parameters;
+  double initial_cost;
+  double final_cost;
+  double total_time_s;         /* host wall clock of ba_cuda_solve */
+  /* device time per kernel family, CUDA events on the solve stream, milliseconds */
+  double ms_jacobian;          /* K1 residual + Jacobian */
+  double ms_schur;             /* K2 elimination + RCS assembly */
+  double ms_rcs_solve;         /* K3 */
+  double ms_update;            /* K4 back-substitution / model cost / candidate */
+  double ms_cost;              /* K5-style cost-only evaluation */
+  double ms_collective;        /* NCCL */
+} ba_cuda_summary;
+
+void ba_cuda_options_init(ba_cuda_options* options);
+
+/* ---- lifetime -------------------------------------------------------------- */
+int ba_cuda_create(ba_cuda_problem** out, int device_id);
+void ba_cuda_destroy(ba_cuda_problem* p);
+const char* ba_cuda_last_error(void); /* thread-local message of the last failure */
+int ba_cuda_device_count(void);
+
+/* ---- multi-GPU plumbing (NCCL; rendezvous bytes travel by the caller's own
+ *      channel, e.g. torch.distributed broadcast) ------------------------------ */
+#define BA_CUDA_UNIQUE_ID_BYTES 128
+int ba_cuda_comm_unique_id(uint8_t id[BA_CUDA_UNIQUE_ID_BYTES]);
+int ba_cuda_comm_init(ba_cuda_problem* p, int rank, int world_size,
+                      const uint8_t id[BA_CUDA_UNIQUE_ID_BYTES]);
+/* Deterministic shard map used by every host (C++ and Python): splits eliminated
+ * blocks [0,n_blocks) into world_size contiguous ranges balanced by `weight`
+ * (observations per block).  range_begin has world_size+1 entries. */
+int ba_cuda_shard_blocks(int64_t n_blocks, const int64_t* weight, int world_size,
+                         int64_t* range_begin);
+
+/* ---- Model A: (camera 6-DoF angle-axis pose, free 3-D point), 2 residuals.
+ *      Replaces ReprojectionError / AutoDiffCostFunction<...,2,6,3> and the
+ *      AddResidualBlock loop, Test1_BundleAdjustment/bundle_adjustmenter.cpp:106-148,
+ *      Test1_BundleAdjustment/main.cpp:67-80.
+ *      cam_idx/pt_idx/obs_xy are exactly BALProblem::camera_index_/point_index_/
+ *      observations_ (bundle_adjustmenter.cpp:66-77).  intr = fx,fy,ppx,ppy per
+ *      camera; intr_stride = 4 for per-camera intrinsics or 0 when one set is
+ *      shared by every observation (Test1 uses serial_numbers[1] for all,
+ *      main.cpp:73-74).  Parameter layout == BALProblem::parameters_:
+ *      [n_cam x 6 | n_pt x 3] (bundle_adjustmenter.cpp:33-41).  Blocks that no
+ *      observation references are not part of the problem (as in Ceres). -------- */
+int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t n_obs,
+                        const int32_t* cam_idx, const int32_t* pt_idx,
+                        const double* obs_xy, const double* intr, int32_t intr_stride);
+
+/* ---- Model B: 8-residual marker factor over (camera, per-frame base-marker
+ *      pose, marker-in-rig pose).  Replaces the four functors of
+ *      Main_Calibration/bundle_adjustment.h:56-343 and the dispatch of
+ *      bundle_adjustment_manager.cpp:21-88 (fix_marker0 = 1), or the two functors
+ *      and dispatch of Test2_BundleAdjustment/main.cpp:64-97 (fix_marker0 = 0).
+ *      Camera 0 is never a parameter block (fix_cam0 must be 1, as in every
+ *      reference program).  obs8 = BALProblem::observations_ (8 per marker
+ *      observation, corner order TL,TR,BR,BL).  intr4_per_cam = fx,fy,ppx,ppy x
+ *      n_cam.  Parameter layout == BALProblem::parameters_:
+ *      [n_cam x 6 | n_time x 6 | n_marker x 6] (bundle_adjustment.cpp:155). ----- */
+int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32_t n_marker,
+                        int64_t n_mobs, const int32_t* time_idx, const int32_t* cam_idx,
+                        const int32_t* marker_idx, const double* obs8,
+                        const double* intr4_per_cam, double marker_side,
+                        int32_t fix_cam0, int32_t fix_marker0);
+
+int ba_cuda_set_parameters(ba_cuda_problem* p, const double* params, int64_t n);
+int ba_cuda_get_parameters(ba_cuda_problem* p, double* params, int64_t n);
+int64_t ba_cuda_num_parameters(const ba_cuda_problem* p);
+
+/* ---- the hot path: replaces ceres::Solve (bundle_adjustment_manager.cpp:94) -- */
+int ba_cuda_solve(ba_cuda_problem* p, const ba_cuda_options* options, ba_cuda_summary* summary);
+/* rows of the progress table; returns the number of rows available (>= 0) */
+int ba_cuda_get_iterations(ba_cuda_problem* p, ba_cuda_iteration* rows, int cap);
+
+/* One residual + Jacobian evaluation at the current parameters (test hook and
+ * the "residual+Jacobian Mobs/s" measurement).  Outputs may be NULL.  Layouts,
+ * in the caller's observation order:
+ *   Model A: residuals 2/obs; jac 18/obs = [d r/d cam (2x6 row-major) | d r/d point (2x3)]
+ *   Model B: residuals 8/mobs; jac 144/mobs = [d r/d cam (8x6) | d r/d frame (8x6) | d r/d marker (8x6)],
+ *            blocks the functor does not take are zero. */
+int ba_cuda_eval(ba_cuda_problem* p, double* cost, double* residuals, double* jac);
+/* device time (ms, CUDA events) of the last ba_cuda_eval / ba_cuda_reprojection_error kernel */
+double ba_cuda_last_kernel_ms(const ba_cuda_problem* p);
+
+/* Reprojection check, the numeric part of ReprojectionCheck::Reproject
+ * (reprojection_check.cpp:69,81,100-101): sum over corners of
+ * ((x^ - x)^2 + (y^ - y)^2) / 2 and sqrt(err*2 / (n_points*2)). */
+int ba_cuda_reprojection_error(ba_cuda_problem* p, double* sum_half_sq, double* rms_per_coord);
+/* Stand-alone form working on explicit 3-D points as Reproject does: points are
+ * projected with (rvec,tvec,intr4) of camera cam_of_point[i] and compared with
+ * image_xy (float pixels widened to double, reprojection_check.cpp:78-81). */
+int ba_cuda_project_points_error(ba_cuda_problem* p, int64_t n_points, const double* xyz,
+                                 const int32_t* cam_of_point, int32_t n_cam,
+                                 const double* rvec_tvec6, const double* intr4,
+                                 const float* image_xy, double* sum_half_sq,
+                                 double* rms_per_coord, double* reprojected_xy /* opt */);
+
+/* Post-BA outputs of BAManager::Write (bundle_adjustment_manager.cpp:121,135-149)
+ * and BALProblem::getPoint3dCoordinates (bundle_adjustment.cpp:89-130), Model B:
+ *   rot9    n_cam x 9  Rodrigues(rvec) row-major
+ *   inv12   n_cam x 12 rows of [R^T | -R^T t]
+ *   corners n_mobs x 4 x 3 composed marker corners in the base-camera frame. */
+int ba_cuda_model_b_outputs(ba_cuda_problem* p, double* rot9, double* inv12, double* corners);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BA_CUDA_H_ */
