@@ -1,0 +1,949 @@
+// ba_cuda.cu -- the ba_cuda_* C ABI (include/ba_cuda.h) and the Levenberg-Marquardt driver.
+//
+// The driver restates Ceres 1.14's TrustRegionMinimizer + LevenbergMarquardtStrategy (the code
+// behind ceres::Solve at Main_Calibration/bundle_adjustment_manager.cpp:94,
+// Test1_BundleAdjustment/main.cpp:86, Test2_BundleAdjustment/main.cpp:103; spec in SURVEY.md 5.9)
+// with every numeric step running as CUDA kernels on one B200; the host only reads back a
+// handful of scalars per iteration to take the accept / reject / terminate decision.
+// There is no CPU fallback: without a CUDA device ba_cuda_create() fails.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <string>
+
+#include "ba_dense.cuh"
+#include "ba_kernels.cuh"
+#include "ba_structure.cuh"
+
+using namespace ba;
+
+// ---- minimal NCCL surface, bound at run time (the process usually has torch's libnccl loaded) ----
+namespace {
+typedef struct ncclComm* ncclComm_t;
+struct NcclUniqueId { char internal[128]; };
+struct Nccl {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok() const { return handle != nullptr; }
+};
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+Nccl& nccl() {
+  static Nccl n;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      n.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (n.handle) break;
+    }
+    if (n.handle) {
+      n.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(n.handle, "ncclGetUniqueId");
+      n.CommInitRank = (int (*)(ncclComm_t*, int, NcclUniqueId, int))dlsym(n.handle, "ncclCommInitRank");
+      n.CommDestroy = (int (*)(ncclComm_t))dlsym(n.handle, "ncclCommDestroy");
+      n.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclAllReduce");
+      n.GetErrorString = (const char* (*)(int))dlsym(n.handle, "ncclGetErrorString");
+      if (!n.GetUniqueId || !n.CommInitRank || !n.CommDestroy || !n.AllReduce) n.handle = nullptr;
+    }
+  }
+  return n;
+}
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+enum Scal { S_COST = 0, S_G2E, S_GMAXE, S_CAND, S_MCC, S_XE2, S_DE2, S_XF2, S_DF2, S_GMAXF, S_G2F, S_RADIUS, S_COUNT = 16 };
+enum Family { F_JAC = 0, F_SCHUR, F_SOLVE, F_UPDATE, F_COST, F_COLL, F_COUNT };
+}  // namespace
+
+struct ba_cuda_problem {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  int model = -1;  // 0 = A, 1 = B
+  int32_t n_cam = 0, n_time = 0, n_marker = 0;
+  int64_t n_pt = 0, n_params = 0;
+  double half_side = 0.0;
+  Structure S;
+  std::vector<int32_t> h_perm;
+  // model data in sorted observation order
+  DVec<double2> uv;
+  DVec<double> obs8, intr_f;
+  DVec<int32_t> ob_cam, ob_marker;
+  // parameters (x), candidate (xc), Jacobi scaling, block tables
+  DVec<double> xf, xe, xf_c, xe_c, sf, se, tab_f, tab_e, tabc_f, tabc_e;
+  // Jacobian and Schur workspace
+  DVec<double> RES, JE, JF0, JF1, ME, HG, Wt, Lb, zb, Yt, vb, Pacc, Qacc, Sd, rhs, yf, ye;
+  DVec<double> part_fobs, part_finc, part_pairs, part_dobs, bp0, bp1, scal;
+  DVec<int> status;
+  double* h_scal = nullptr;  // pinned
+  int* h_status = nullptr;   // pinned
+  bool params_set = false;
+  std::vector<ba_cuda_iteration> rows;
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  // timing
+  cudaEvent_t ev[F_COUNT][2] = {};
+  double fam_ms[F_COUNT] = {};
+  bool fam_open[F_COUNT] = {};
+  cudaEvent_t k0 = nullptr, k1 = nullptr;
+  float last_kernel_ms = 0.f;
+  int64_t n_rcs() const { return 6 * S.nf; }
+  double* vsum() { return Sd.p + n_rcs() * n_rcs(); }  // tail of the dense RCS buffer: one collective covers both
+};
+
+namespace {
+
+int use_device(ba_cuda_problem* p) {
+  BA_CUDA_TRY(cudaSetDevice(p->device));
+  return BA_OK;
+}
+
+// ---- family timers: one event pair per family, accumulated at the iteration's host sync ----
+void fam_begin(ba_cuda_problem* p, int f) { cudaEventRecord(p->ev[f][0], p->st); p->fam_open[f] = true; }
+void fam_end(ba_cuda_problem* p, int f) { cudaEventRecord(p->ev[f][1], p->st); }
+void fam_collect(ba_cuda_problem* p) {  // call after a stream synchronize
+  for (int f = 0; f < F_COUNT; ++f)
+    if (p->fam_open[f]) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, p->ev[f][0], p->ev[f][1]) == cudaSuccess) p->fam_ms[f] += ms;
+      p->fam_open[f] = false;
+    }
+}
+
+int fold(ba_cuda_problem* p, const double* partial, int n, int slot, bool is_max = false) {
+  k_fold_partials<<<1, 1024, 0, p->st>>>(partial, n, p->scal.p, slot, is_max ? 1 : 0);
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
+int allreduce(ba_cuda_problem* p, double* buf, size_t count, int op) {
+  if (p->world <= 1) return BA_OK;
+  const int rc = nccl().AllReduce(buf, buf, count, kNcclFloat64, op, p->comm, p->st);
+  if (rc != 0) return fail(BA_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
+  return BA_OK;
+}
+
+int build_tables(ba_cuda_problem* p, bool candidate) {
+  const Structure& S = p->S;
+  const double* xf = candidate ? p->xf_c.p : p->xf.p;
+  double* tf = candidate ? p->tabc_f.p : p->tab_f.p;
+  k_tables<<<grid_for(S.nf, 128), 128, 0, p->st>>>(xf, p->intr_f.p, p->sf.p, S.nf, tf);
+  if (p->model == 1) {
+    const double* xe = candidate ? p->xe_c.p : p->xe.p;
+    double* te = candidate ? p->tabc_e.p : p->tab_e.p;
+    k_tables<<<grid_for(S.ne, 128), 128, 0, p->st>>>(xe, nullptr, p->se.p, S.ne, te);
+  }
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
+// K1 at the current parameters: residuals, scaled Jacobian, sum of squares -> scal[S_COST]
+int run_jacobian(ba_cuda_problem* p) {
+  const Structure& S = p->S;
+  BA_TRY(build_tables(p, false));
+  int grid;
+  if (p->model == 0) {
+    grid = (int)grid_for(S.nb, 256);
+    k_jac_a<<<grid, 256, 0, p->st>>>(S.nb, S.ob_e.p, S.ob_f0.p, p->uv.p, p->tab_f.p, p->xe.p, p->se.p, p->RES.p, p->JE.p,
+                                     p->JF0.p, p->bp0.p);
+  } else {
+    grid = (int)grid_for(S.nb * 4, 128);
+    k_jac_b<<<grid, 128, 0, p->st>>>(S.nb, S.ob_e.p, S.ob_f0.p, S.ob_f1.p, p->ob_cam.p, p->obs8.p, p->tab_f.p, p->tab_e.p,
+                                     p->half_side, p->RES.p, p->JE.p, p->JF0.p, p->JF1.p, p->bp0.p);
+  }
+  BA_CUDA_TRY(cudaGetLastError());
+  return fold(p, p->bp0.p, grid, S_COST);
+}
+
+// cost-only evaluation at the candidate -> scal[S_CAND]
+int run_cost_candidate(ba_cuda_problem* p) {
+  const Structure& S = p->S;
+  BA_TRY(build_tables(p, true));
+  int grid;
+  if (p->model == 0) {
+    grid = (int)grid_for(S.nb, 256);
+    k_cost_a<<<grid, 256, 0, p->st>>>(S.nb, S.ob_e.p, S.ob_f0.p, p->uv.p, p->tabc_f.p, p->xe_c.p, p->bp0.p);
+  } else {
+    grid = (int)grid_for(S.nb * 4, 128);
+    k_cost_b<<<grid, 128, 0, p->st>>>(S.nb, S.ob_e.p, S.ob_f0.p, S.ob_f1.p, p->ob_cam.p, p->obs8.p, p->tabc_f.p, p->tabc_e.p,
+                                      p->half_side, p->bp0.p);
+  }
+  BA_CUDA_TRY(cudaGetLastError());
+  return fold(p, p->bp0.p, grid, S_CAND);
+}
+
+// Everything of the normal equations that depends only on J: F^T F / F^T r per f-block, E^T E / E^T r per
+// e-block, Model B: W_i per incidence and the off-diagonal F^T F blocks.
+template <int RD, int DE, int GE>
+int run_normal_parts(ba_cuda_problem* p) {
+  const Structure& S = p->S;
+  constexpr int NVE = DE * (DE + 1) / 2 + DE;
+  if (S.ch_fobs.n > 0)
+    k_fobs_partial<RD><<<grid_for(S.ch_fobs.n, 4), 128, 0, p->st>>>(S.ch_fobs.n, S.ch_fobs.ch, S.ch_fobs.seg.p, S.ch_fobs.begin.p,
+                                                                    S.fobs_ptr.p, S.fobs.p, p->RES.p, p->JF0.p, p->JF1.p, p->part_fobs.p);
+  k_seg_final<NV_F><<<grid_for(S.nf, 4), 128, 0, p->st>>>((int)S.nf, S.ch_fobs.seg_first.p, p->part_fobs.p, p->HG.p);
+  k_e_M<RD, DE, GE><<<grid_for(S.ne * GE, 128), 128, 0, p->st>>>(S.ne, S.e_ptr.p, p->RES.p, p->JE.p, p->ME.p);
+  if (p->model == 1) {
+    k_inc_W<RD><<<grid_for(S.ninc * 8, 128), 128, 0, p->st>>>(S.ninc, S.incobs_ptr.p, S.incobs.p, p->JE.p, p->JF0.p, p->JF1.p, p->Wt.p);
+    if (S.ch_dobs.n > 0)
+      k_dobs_partial<RD><<<grid_for(S.ch_dobs.n, 4), 128, 0, p->st>>>(S.ch_dobs.n, S.ch_dobs.ch, S.ch_dobs.seg.p, S.ch_dobs.begin.p,
+                                                                      S.dobs_ptr.p, S.dobs.p, p->JF0.p, p->JF1.p, p->part_dobs.p);
+    k_seg_final<36><<<grid_for(S.ndest, 4), 128, 0, p->st>>>(S.ndest, S.ch_dobs.seg_first.p, p->part_dobs.p, p->Qacc.p);
+  }
+  BA_CUDA_TRY(cudaGetLastError());
+  (void)NVE;
+  return BA_OK;
+}
+
+template <int DE>
+int run_gradient_norms(ba_cuda_problem* p) {
+  const Structure& S = p->S;
+  constexpr int NU = DE * (DE + 1) / 2;
+  const int ge = (int)grid_for(S.ne * DE, 256), gf = (int)grid_for(S.nf * 6, 256);
+  k_gradient_norm<DE, NU + DE, NU><<<ge, 256, 0, p->st>>>(S.ne, S.e_ptr.p, p->xe.p, p->se.p, p->ME.p, p->bp0.p, p->bp1.p);
+  BA_TRY(fold(p, p->bp0.p, ge, S_GMAXE, true));
+  BA_TRY(fold(p, p->bp1.p, ge, S_G2E));
+  k_gradient_norm<6, NV_F, 21><<<gf, 256, 0, p->st>>>(S.nf, S.fobs_ptr.p, p->xf.p, p->sf.p, p->HG.p, p->bp0.p, p->bp1.p);
+  BA_TRY(fold(p, p->bp0.p, gf, S_GMAXF, true));
+  BA_TRY(fold(p, p->bp1.p, gf, S_G2F));
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
+// TrustRegionMinimizer::EvaluateGradientAndJacobian: r, J, cost, gradient norms at x; on the first call also
+// the Jacobi scaling (computed once, from the unscaled J).
+template <int RD, int DE, int GE>
+int eval_gradient_and_jacobian(ba_cuda_problem* p, bool first, bool jacobi_scaling) {
+  const Structure& S = p->S;
+  fam_begin(p, F_JAC);
+  if (first) {
+    k_fill<<<grid_for(S.ne * DE, 256), 256, 0, p->st>>>(p->se.p, S.ne * DE, 1.0);
+    k_fill<<<grid_for(S.nf * 6, 256), 256, 0, p->st>>>(p->sf.p, S.nf * 6, 1.0);
+  }
+  BA_TRY(run_jacobian(p));
+  fam_end(p, F_JAC);
+  fam_begin(p, F_SCHUR);
+  BA_TRY((run_normal_parts<RD, DE, GE>(p)));
+  if (first && jacobi_scaling) {
+    BA_TRY(allreduce(p, p->HG.p, S.nf * NV_F, kNcclSum));  // column norms of the kept blocks are global sums
+    constexpr int NU = DE * (DE + 1) / 2;
+    k_jacobi_scale<DE, NU + DE><<<grid_for(S.ne * DE, 256), 256, 0, p->st>>>(S.ne, p->ME.p, p->se.p);
+    k_jacobi_scale<6, NV_F><<<grid_for(S.nf * 6, 256), 256, 0, p->st>>>(S.nf, p->HG.p, p->sf.p);
+    BA_TRY(run_jacobian(p));  // same residuals, Jacobian now column scaled
+    BA_TRY((run_normal_parts<RD, DE, GE>(p)));
+  }
+  fam_end(p, F_SCHUR);
+  if (p->world > 1) {
+    fam_begin(p, F_COLL);
+    BA_TRY(allreduce(p, p->HG.p, S.nf * NV_F, kNcclSum));
+    fam_end(p, F_COLL);
+  }
+  BA_TRY(run_gradient_norms<DE>(p));
+  if (p->world > 1) {
+    BA_TRY(allreduce(p, p->scal.p + S_COST, 2, kNcclSum));  // S_COST, S_G2E
+    BA_TRY(allreduce(p, p->scal.p + S_GMAXE, 1, kNcclMax));
+  }
+  return BA_OK;
+}
+
+// LevenbergMarquardtStrategy::ComputeStep + SchurEliminator + dense Cholesky + BackSubstitute + the model cost
+// change and the candidate point.  scal[S_RADIUS] must hold the trust-region radius.
+template <int RD, int DE, int GE, int NSLOT>
+int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
+  const Structure& S = p->S;
+  const int64_t n = p->n_rcs();
+  const double* radius = p->scal.p + S_RADIUS;
+  fam_begin(p, F_SCHUR);
+  BA_CUDA_TRY(cudaMemsetAsync(p->status.p, 0, sizeof(int), p->st));
+  k_e_chol<DE><<<grid_for(S.ne, 256), 256, 0, p->st>>>(S.ne, p->ME.p, radius, opt.min_lm_diagonal, opt.max_lm_diagonal, p->Lb.p, p->zb.p, p->status.p);
+  if (p->model == 0)
+    k_inc_Y<RD, DE, true><<<grid_for(S.ninc, 128), 128, 0, p->st>>>(S.ninc, S.inc_e, p->JE.p, p->JF0.p, nullptr, p->Lb.p, p->zb.p, p->Yt.p, p->vb.p);
+  else
+    k_inc_Y<RD, DE, false><<<grid_for(S.ninc, 128), 128, 0, p->st>>>(S.ninc, S.inc_e, nullptr, nullptr, p->Wt.p, p->Lb.p, p->zb.p, p->Yt.p, p->vb.p);
+  BA_CUDA_TRY(cudaMemsetAsync(p->Sd.p, 0, sizeof(double) * (n * n + n), p->st));
+  if (S.ch_finc.n > 0)
+    k_finc_partial<<<grid_for(S.ch_finc.n, 4), 128, 0, p->st>>>(S.ch_finc.n, S.ch_finc.ch, S.ch_finc.seg.p, S.ch_finc.begin.p, S.finc_ptr.p,
+                                                                S.finc.p, p->vb.p, p->part_finc.p);
+  k_seg_final<6><<<grid_for(S.nf, 4), 128, 0, p->st>>>((int)S.nf, S.ch_finc.seg_first.p, p->part_finc.p, p->vsum());
+  k_pairs_partial<DE><<<grid_for(S.ch_pairs.n, 4), 128, 0, p->st>>>(S.ch_pairs.n, S.ch_pairs.ch, S.ch_pairs.seg.p, S.ch_pairs.begin.p,
+                                                                    S.dpair_ptr.p, S.pairs.p, p->Yt.p, p->part_pairs.p);
+  k_seg_final<36><<<grid_for(S.ndest, 4), 128, 0, p->st>>>(S.ndest, S.ch_pairs.seg_first.p, p->part_pairs.p, p->Pacc.p);
+  k_assemble_dense<<<grid_for((int64_t)S.ndest * 36, 256), 256, 0, p->st>>>(S.ndest, S.dest_fa.p, S.dest_fb.p, p->Pacc.p,
+                                                                            p->model == 1 ? p->Qacc.p : nullptr, n, p->Sd.p);
+  BA_CUDA_TRY(cudaGetLastError());
+  fam_end(p, F_SCHUR);
+  if (p->world > 1) {
+    fam_begin(p, F_COLL);
+    BA_TRY(allreduce(p, p->Sd.p, n * n + n, kNcclSum));  // partial RCS and the partial rhs correction in one call
+    fam_end(p, F_COLL);
+  }
+  fam_begin(p, F_SOLVE);
+  k_diag_rhs_dense<<<grid_for(S.nf * 6, 128), 128, 0, p->st>>>(S.nf, p->HG.p, p->vsum(), radius, opt.min_lm_diagonal, opt.max_lm_diagonal, n,
+                                                               p->Sd.p, p->rhs.p);
+  BA_TRY(launch_chol_solve((int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p, p->st));
+  fam_end(p, F_SOLVE);
+  fam_begin(p, F_UPDATE);
+  k_e_backsub<DE, GE><<<grid_for(S.ne * GE, 128), 128, 0, p->st>>>(S.ne, S.einc_ptr, S.inc_f, p->Yt.p, p->Lb.p, p->zb.p, p->yf.p, p->ye.p);
+  const int gm = (int)grid_for(S.nb, 256);
+  k_model_cost<RD, DE, NSLOT><<<gm, 256, 0, p->st>>>(S.nb, S.ob_e.p, S.ob_f0.p, S.ob_f1.p, p->RES.p, p->JE.p, p->JF0.p, p->JF1.p, p->ye.p,
+                                                     p->yf.p, p->bp0.p);
+  BA_TRY(fold(p, p->bp0.p, gm, S_MCC));
+  const int gce = (int)grid_for(S.ne * DE, 256), gcf = (int)grid_for(S.nf * 6, 256);
+  k_candidate<DE><<<gce, 256, 0, p->st>>>(S.ne, S.e_ptr.p, p->xe.p, p->se.p, p->ye.p, p->xe_c.p, p->bp0.p, p->bp1.p);
+  BA_TRY(fold(p, p->bp0.p, gce, S_XE2));
+  BA_TRY(fold(p, p->bp1.p, gce, S_DE2));
+  k_candidate<6><<<gcf, 256, 0, p->st>>>(S.nf, S.fobs_ptr.p, p->xf.p, p->sf.p, p->yf.p, p->xf_c.p, p->bp0.p, p->bp1.p);
+  BA_TRY(fold(p, p->bp0.p, gcf, S_XF2));
+  BA_TRY(fold(p, p->bp1.p, gcf, S_DF2));
+  BA_CUDA_TRY(cudaGetLastError());
+  fam_end(p, F_UPDATE);
+  fam_begin(p, F_COST);
+  BA_TRY(run_cost_candidate(p));
+  fam_end(p, F_COST);
+  if (p->world > 1) BA_TRY(allreduce(p, p->scal.p + S_CAND, 4, kNcclSum));  // S_CAND, S_MCC, S_XE2, S_DE2
+  return BA_OK;
+}
+
+int fetch_scalars(ba_cuda_problem* p) {
+  BA_CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal.p, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, p->st));
+  BA_CUDA_TRY(cudaMemcpyAsync(p->h_status, p->status.p, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  fam_collect(p);
+  return BA_OK;
+}
+
+template <int RD, int DE, int GE, int NSLOT>
+int minimize(ba_cuda_problem* p, const ba_cuda_options& opt, ba_cuda_summary* sum) {
+  const Structure& S = p->S;
+  const double t_start = now_s();
+  ba_cuda_summary Z;
+  std::memset(&Z, 0, sizeof(Z));
+  p->rows.clear();
+  for (int f = 0; f < F_COUNT; ++f) { p->fam_ms[f] = 0.0; p->fam_open[f] = false; }
+  Z.num_residuals = S.nb * RD;
+  Z.rcs_solver_used = BA_RCS_DENSE_CHOLESKY;
+
+  double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
+  int num_invalid = 0;
+  double iter_t0 = now_s();
+  double x_cost = 0.0, gmax = 0.0, gnorm = 0.0;
+
+  auto finalize = [&](ba_cuda_iteration row) -> bool {  // FinalizeIterationAndCheckIfMinimizerCanContinue
+    if (row.step_is_successful) Z.num_successful_steps++; else Z.num_unsuccessful_steps++;
+    row.trust_region_radius = radius;
+    row.iteration_time_s = now_s() - iter_t0;
+    p->rows.push_back(row);
+    if (opt.minimizer_progress_to_stdout && p->rank == 0) {
+      if (row.iteration == 0) std::printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius\n");
+      std::printf("%4d % 14.6e % 10.2e % 10.2e % 10.2e % 10.2e % 10.2e\n", row.iteration, row.cost, row.cost_change,
+                  row.gradient_max_norm, row.step_norm, row.relative_decrease, row.trust_region_radius);
+    }
+    if (row.iteration >= opt.max_num_iterations) { Z.termination_type = BA_NO_CONVERGENCE; Z.termination_reason = BA_REASON_MAX_ITERATIONS; return false; }
+    if (row.step_is_successful && row.gradient_max_norm <= opt.gradient_tolerance) { Z.termination_type = BA_CONVERGENCE; Z.termination_reason = BA_REASON_GRADIENT_TOLERANCE; return false; }
+    if (row.trust_region_radius <= opt.min_trust_region_radius) { Z.termination_type = BA_CONVERGENCE; Z.termination_reason = BA_REASON_MIN_TRUST_REGION_RADIUS; return false; }
+    return true;
+  };
+  auto read_gradient = [&]() {
+    x_cost = 0.5 * p->h_scal[S_COST];
+    gmax = std::max(p->h_scal[S_GMAXE], p->h_scal[S_GMAXF]);
+    gnorm = std::sqrt(p->h_scal[S_G2E] + p->h_scal[S_G2F]);
+  };
+
+  // IterationZero
+  BA_TRY((eval_gradient_and_jacobian<RD, DE, GE>(p, true, opt.jacobi_scaling != 0)));
+  Z.num_jacobian_evaluations++;
+  BA_TRY(fetch_scalars(p));
+  read_gradient();
+  ba_cuda_iteration row;
+  std::memset(&row, 0, sizeof(row));
+  if (!std::isfinite(x_cost)) {
+    Z.termination_type = BA_FAILURE; Z.termination_reason = BA_REASON_INITIAL_EVALUATION_FAILED;
+    Z.initial_cost = Z.final_cost = x_cost;
+    if (sum) *sum = Z;
+    return BA_OK;
+  }
+  Z.initial_cost = x_cost;
+  row.iteration = 0; row.step_is_valid = 1; row.step_is_successful = 1; row.cost = x_cost;
+  row.gradient_max_norm = gmax; row.gradient_norm = gnorm;
+  bool go = finalize(row);
+
+  while (go) {
+    iter_t0 = now_s();
+    std::memset(&row, 0, sizeof(row));
+    row.iteration = p->rows.back().iteration + 1;
+    BA_CUDA_TRY(cudaMemcpyAsync(p->scal.p + S_RADIUS, &radius, sizeof(double), cudaMemcpyHostToDevice, p->st));
+    BA_TRY((compute_step<RD, DE, GE, NSLOT>(p, opt)));
+    Z.num_linear_solves++;
+    Z.num_cost_evaluations++;
+    BA_TRY(fetch_scalars(p));
+    int status = *p->h_status;
+    if (p->world > 1) {  // a failed block factorisation on any rank invalidates the step everywhere
+      double flag = status ? 1.0 : 0.0, *d = p->scal.p + S_COUNT - 1;
+      BA_CUDA_TRY(cudaMemcpyAsync(d, &flag, sizeof(double), cudaMemcpyHostToDevice, p->st));
+      BA_TRY(allreduce(p, d, 1, kNcclMax));
+      BA_CUDA_TRY(cudaMemcpyAsync(&flag, d, sizeof(double), cudaMemcpyDeviceToHost, p->st));
+      BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+      status = flag != 0.0 ? 1 : 0;
+    }
+    const double model_cost_change = -p->h_scal[S_MCC];
+    const bool solve_ok = status == 0 && std::isfinite(model_cost_change);
+    row.step_is_valid = solve_ok && model_cost_change > 0.0;
+    if (!row.step_is_valid) {  // HandleInvalidStep
+      if (++num_invalid >= opt.max_num_consecutive_invalid_steps) {
+        Z.termination_type = BA_FAILURE; Z.termination_reason = BA_REASON_TOO_MANY_INVALID_STEPS;
+        break;
+      }
+      radius = radius / decrease_factor; decrease_factor *= 2.0;
+      row.cost = x_cost; row.cost_change = 0.0;
+      row.gradient_max_norm = p->rows.back().gradient_max_norm; row.gradient_norm = p->rows.back().gradient_norm;
+      go = finalize(row);
+      continue;
+    }
+    num_invalid = 0;
+    const double cand_cost = 0.5 * p->h_scal[S_CAND];
+    // ParameterToleranceReached
+    const double x_norm = std::sqrt(p->h_scal[S_XE2] + p->h_scal[S_XF2]);
+    row.step_norm = std::sqrt(p->h_scal[S_DE2] + p->h_scal[S_DF2]);
+    if (row.step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
+      Z.termination_type = BA_CONVERGENCE; Z.termination_reason = BA_REASON_PARAMETER_TOLERANCE;
+      break;
+    }
+    // FunctionToleranceReached
+    row.cost_change = x_cost - cand_cost;
+    if (std::fabs(row.cost_change) <= opt.function_tolerance * x_cost) {
+      Z.termination_type = BA_CONVERGENCE; Z.termination_reason = BA_REASON_FUNCTION_TOLERANCE;
+      break;
+    }
+    row.relative_decrease = row.cost_change / model_cost_change;
+    if (row.relative_decrease > opt.min_relative_decrease) {  // HandleSuccessfulStep
+      p->xe.swap(p->xe_c);
+      p->xf.swap(p->xf_c);
+      BA_TRY((eval_gradient_and_jacobian<RD, DE, GE>(p, false, opt.jacobi_scaling != 0)));
+      Z.num_jacobian_evaluations++;
+      BA_TRY(fetch_scalars(p));
+      read_gradient();
+      row.step_is_successful = 1;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * row.relative_decrease - 1.0, 3));
+      radius = std::min(opt.max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+      row.cost = x_cost; row.gradient_max_norm = gmax; row.gradient_norm = gnorm;
+    } else {  // HandleUnsuccessfulStep
+      radius = radius / decrease_factor; decrease_factor *= 2.0;
+      row.cost = cand_cost;
+    }
+    go = finalize(row);
+  }
+  Z.num_iterations = (int32_t)p->rows.size();
+  Z.final_cost = x_cost;
+  Z.total_time_s = now_s() - t_start;
+  Z.ms_jacobian = p->fam_ms[F_JAC]; Z.ms_schur = p->fam_ms[F_SCHUR]; Z.ms_rcs_solve = p->fam_ms[F_SOLVE];
+  Z.ms_update = p->fam_ms[F_UPDATE]; Z.ms_cost = p->fam_ms[F_COST]; Z.ms_collective = p->fam_ms[F_COLL];
+  if (sum) *sum = Z;
+  return BA_OK;
+}
+
+// number of active blocks (host side, from the CSR pointers)
+int count_active(ba_cuda_problem* p, const DVec<int64_t>& ptr, int64_t nblk, int64_t* out) {
+  std::vector<int64_t> h(nblk + 1);
+  BA_CUDA_TRY(cudaMemcpyAsync(h.data(), ptr.p, sizeof(int64_t) * (nblk + 1), cudaMemcpyDeviceToHost, p->st));
+  BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  int64_t c = 0;
+  for (int64_t i = 0; i < nblk; ++i) c += h[i + 1] > h[i] ? 1 : 0;
+  *out = c;
+  return BA_OK;
+}
+
+int alloc_workspace(ba_cuda_problem* p, int RD, int DE) {
+  const Structure& S = p->S;
+  const int64_t n = p->n_rcs();
+  if (n > 2048) return fail(BA_ERR_UNSUPPORTED, "reduced camera system of dimension %lld needs the PCG solver (not in this build yet)", (long long)n);
+  cudaStream_t st = p->st;
+  BA_TRY(p->xf.alloc_zero(S.nf * 6, st)); BA_TRY(p->xf_c.alloc_zero(S.nf * 6, st));
+  BA_TRY(p->xe.alloc_zero(S.ne * DE, st)); BA_TRY(p->xe_c.alloc_zero(S.ne * DE, st));
+  BA_TRY(p->sf.alloc(S.nf * 6)); BA_TRY(p->se.alloc(S.ne * DE));
+  k_fill<<<grid_for(S.nf * 6, 256), 256, 0, st>>>(p->sf.p, S.nf * 6, 1.0);
+  k_fill<<<grid_for(S.ne * DE, 256), 256, 0, st>>>(p->se.p, S.ne * DE, 1.0);
+  BA_TRY(p->tab_f.alloc(S.nf * TAB)); BA_TRY(p->tabc_f.alloc(S.nf * TAB));
+  if (p->model == 1) { BA_TRY(p->tab_e.alloc(S.ne * TAB)); BA_TRY(p->tabc_e.alloc(S.ne * TAB)); }
+  BA_TRY(p->RES.alloc(S.nb * RD)); BA_TRY(p->JE.alloc(S.nb * RD * DE)); BA_TRY(p->JF0.alloc(S.nb * RD * 6));
+  BA_TRY(p->JF1.alloc(p->model == 1 ? S.nb * RD * 6 : 0));
+  BA_TRY(p->ME.alloc(S.ne * (DE * (DE + 1) / 2 + DE))); BA_TRY(p->HG.alloc(S.nf * NV_F));
+  BA_TRY(p->Wt.alloc(p->model == 1 ? S.ninc * 36 : 0));
+  BA_TRY(p->Lb.alloc(S.ne * DE * DE)); BA_TRY(p->zb.alloc(S.ne * DE));
+  BA_TRY(p->Yt.alloc(S.ninc * DE * 6)); BA_TRY(p->vb.alloc(S.ninc * 6));
+  BA_TRY(p->Pacc.alloc((int64_t)S.ndest * 36)); BA_TRY(p->Qacc.alloc(p->model == 1 ? (int64_t)S.ndest * 36 : 0));
+  BA_TRY(p->Sd.alloc(n * n + n)); BA_TRY(p->rhs.alloc(n)); BA_TRY(p->yf.alloc_zero(n, st)); BA_TRY(p->ye.alloc_zero(S.ne * DE, st));
+  BA_TRY(p->part_fobs.alloc((int64_t)S.ch_fobs.n * NV_F)); BA_TRY(p->part_finc.alloc((int64_t)S.ch_finc.n * 6));
+  BA_TRY(p->part_pairs.alloc((int64_t)S.ch_pairs.n * 36));
+  BA_TRY(p->part_dobs.alloc(p->model == 1 ? (int64_t)S.ch_dobs.n * 36 : 0));
+  const int64_t maxgrid = std::max<int64_t>({(int64_t)grid_for(S.nb * 4, 128), (int64_t)grid_for(S.ne * DE, 256), (int64_t)grid_for(S.nf * 6, 256)}) + 1;
+  BA_TRY(p->bp0.alloc(maxgrid)); BA_TRY(p->bp1.alloc(maxgrid));
+  BA_TRY(p->scal.alloc_zero(S_COUNT, st)); BA_TRY(p->status.alloc_zero(1, st));
+  BA_CUDA_TRY(cudaStreamSynchronize(st));
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
+__global__ void k_gather_uv(const double* __restrict__ src, const int32_t* __restrict__ perm, int64_t n, int width, double* __restrict__ dst) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  dst[t] = src[(int64_t)perm[t / width] * width + t % width];
+}
+
+
+// ---- K5 / post-BA outputs ---------------------------------------------------------------
+// cv::Rodrigues(rvec -> R) as used by BAManager::Write (bundle_adjustment_manager.cpp:121) and by
+// cv::projectPoints inside ReprojectionCheck::Reproject (reprojection_check.cpp:69).
+__global__ void k_rodrigues_cv(const double* __restrict__ rt6, int n, double* __restrict__ R9, double* __restrict__ inv12) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double rx = rt6[6 * i], ry = rt6[6 * i + 1], rz = rt6[6 * i + 2];
+  const double theta = sqrt(rx * rx + ry * ry + rz * rz);
+  double R[9];
+  if (theta < DBL_EPSILON) {
+#pragma unroll
+    for (int q = 0; q < 9; ++q) R[q] = (q % 4 == 0) ? 1.0 : 0.0;
+  } else {
+    const double c = cos(theta), s = sin(theta), c1 = 1.0 - c, it = 1.0 / theta;
+    const double k0 = rx * it, k1 = ry * it, k2 = rz * it;
+    R[0] = c + c1 * k0 * k0;      R[1] = c1 * k0 * k1 - s * k2; R[2] = c1 * k0 * k2 + s * k1;
+    R[3] = c1 * k0 * k1 + s * k2; R[4] = c + c1 * k1 * k1;      R[5] = c1 * k1 * k2 - s * k0;
+    R[6] = c1 * k0 * k2 - s * k1; R[7] = c1 * k1 * k2 + s * k0; R[8] = c + c1 * k2 * k2;
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) R9[9 * i + q] = R[q];
+  if (inv12) {  // rows of [R^T | -R^T t], bundle_adjustment_manager.cpp:135-149
+    const double t0 = rt6[6 * i + 3], t1 = rt6[6 * i + 4], t2 = rt6[6 * i + 5];
+#pragma unroll
+    for (int row = 0; row < 3; ++row) {
+      double* o = inv12 + 12 * i + 4 * row;
+      o[0] = R[row]; o[1] = R[3 + row]; o[2] = R[6 + row];
+      o[3] = -(R[row] * t0 + R[3 + row] * t1 + R[6 + row] * t2);
+    }
+  }
+}
+
+// cv::projectPoints with zero distortion, then ((x^ - x)^2 + (y^ - y)^2) / 2 (reprojection_check.cpp:81)
+__global__ void __launch_bounds__(256)
+k_project_error(int64_t n, const double* __restrict__ xyz, const int32_t* __restrict__ cam, const double* __restrict__ R9,
+                const double* __restrict__ rt6, const double* __restrict__ K4, const float* __restrict__ img,
+                double* __restrict__ rep, double* __restrict__ partial) {
+  __shared__ double sm[32];
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (i < n) {
+    const int c = cam[i];
+    const double* R = R9 + 9 * c;
+    const double* t = rt6 + 6 * c + 3;
+    const double X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
+    const double x = R[0] * X + R[1] * Y + R[2] * Z + t[0];
+    const double y = R[3] * X + R[4] * Y + R[5] * Z + t[1];
+    const double z = R[6] * X + R[7] * Y + R[8] * Z + t[2];
+    const double iz = z != 0.0 ? 1.0 / z : 1.0;
+    const double u = (x * iz) * K4[4 * c] + K4[4 * c + 2], v = (y * iz) * K4[4 * c + 1] + K4[4 * c + 3];
+    if (rep) { rep[2 * i] = u; rep[2 * i + 1] = v; }
+    const double dx = (double)img[2 * i] - u, dy = (double)img[2 * i + 1] - v;
+    e = (dx * dx + dy * dy) / 2;
+  }
+  e = block_sum(e, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = e;
+}
+
+// BALProblem::getPoint3dCoordinates (bundle_adjustment.cpp:89-130): marker corner -> base-marker frame -> base camera
+__global__ void k_corners_b(int64_t nb, const int32_t* __restrict__ perm, const int32_t* __restrict__ ob_e,
+                            const int32_t* __restrict__ ob_marker, int32_t n_cam, const double* __restrict__ tab_f,
+                            const double* __restrict__ tab_e, double half, double* __restrict__ corners) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nb * 4) return;
+  const int64_t b = t >> 2;
+  const int corner = (int)(t & 3);
+  const double* Tm = tab_f + TAB * (int64_t)(n_cam + ob_marker[b]);
+  const double* Tt = tab_e + TAB * (int64_t)ob_e[b];
+  const double q0[3] = {(corner == 0 || corner == 3) ? -half : half, (corner < 2) ? half : -half, 0.0};
+  double r[3], p1[3];
+  mat3_vec(Tm, q0, r);
+  p1[0] = r[0] + Tm[18]; p1[1] = r[1] + Tm[19]; p1[2] = r[2] + Tm[20];
+  mat3_vec(Tt, p1, r);
+  double* o = corners + ((int64_t)perm[b] * 4 + corner) * 3;
+  o[0] = r[0] + Tt[18]; o[1] = r[1] + Tt[19]; o[2] = r[2] + Tt[20];
+}
+
+void reset_problem(ba_cuda_problem* p) {
+  p->model = -1;
+  p->params_set = false;
+  p->rows.clear();
+  p->S.~Structure();
+  new (&p->S) Structure();
+}
+
+}  // namespace
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+extern "C" {
+
+void ba_cuda_options_init(ba_cuda_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->max_num_iterations = 50; o->max_num_consecutive_invalid_steps = 5; o->jacobi_scaling = 1;
+  o->rcs_solver = BA_RCS_AUTO; o->pcg_max_iterations = 500; o->pcg_min_iterations = 0;
+  o->pcg_residual_reset_period = 10; o->minimizer_progress_to_stdout = 0;
+  o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+  o->pcg_eta = 1e-1; o->pcg_r_tolerance = -1.0;
+}
+
+const char* ba_cuda_last_error(void) { return err_buf(); }
+
+int ba_cuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int ba_cuda_create(ba_cuda_problem** out, int device_id) {
+  if (!out) return fail(BA_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(BA_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  }
+  if (device_id < 0 || device_id >= n) return fail(BA_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device_id, n);
+  BA_CUDA_TRY(cudaSetDevice(device_id));
+  ba_cuda_problem* p = new ba_cuda_problem();
+  p->device = device_id;
+  BA_CUDA_TRY(cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
+  for (int f = 0; f < F_COUNT; ++f) { BA_CUDA_TRY(cudaEventCreate(&p->ev[f][0])); BA_CUDA_TRY(cudaEventCreate(&p->ev[f][1])); }
+  BA_CUDA_TRY(cudaEventCreate(&p->k0)); BA_CUDA_TRY(cudaEventCreate(&p->k1));
+  BA_CUDA_TRY(cudaMallocHost((void**)&p->h_scal, sizeof(double) * S_COUNT));
+  BA_CUDA_TRY(cudaMallocHost((void**)&p->h_status, sizeof(int)));
+  *out = p;
+  return BA_OK;
+}
+
+void ba_cuda_destroy(ba_cuda_problem* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  if (p->st) cudaStreamSynchronize(p->st);
+  if (p->comm && nccl().ok()) nccl().CommDestroy(p->comm);
+  for (int f = 0; f < F_COUNT; ++f) { if (p->ev[f][0]) cudaEventDestroy(p->ev[f][0]); if (p->ev[f][1]) cudaEventDestroy(p->ev[f][1]); }
+  if (p->k0) cudaEventDestroy(p->k0);
+  if (p->k1) cudaEventDestroy(p->k1);
+  if (p->h_scal) cudaFreeHost(p->h_scal);
+  if (p->h_status) cudaFreeHost(p->h_status);
+  cudaStream_t st = p->st;
+  delete p;
+  if (st) cudaStreamDestroy(st);
+}
+
+int ba_cuda_comm_unique_id(uint8_t id[BA_CUDA_UNIQUE_ID_BYTES]) {
+  if (!nccl().ok()) return fail(BA_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  NcclUniqueId u;
+  const int rc = nccl().GetUniqueId(&u);
+  if (rc != 0) return fail(BA_ERR_NCCL, "ncclGetUniqueId failed (%d)", rc);
+  std::memcpy(id, u.internal, BA_CUDA_UNIQUE_ID_BYTES);
+  return BA_OK;
+}
+
+int ba_cuda_comm_init(ba_cuda_problem* p, int rank, int world_size, const uint8_t id[BA_CUDA_UNIQUE_ID_BYTES]) {
+  if (!p || world_size < 1 || rank < 0 || rank >= world_size) return fail(BA_ERR_INVALID_ARGUMENT, "bad rank/world");
+  BA_TRY(use_device(p));
+  p->rank = rank; p->world = world_size;
+  if (world_size == 1) return BA_OK;
+  if (!nccl().ok()) return fail(BA_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  NcclUniqueId u;
+  std::memcpy(u.internal, id, BA_CUDA_UNIQUE_ID_BYTES);
+  const int rc = nccl().CommInitRank(&p->comm, world_size, u, rank);
+  if (rc != 0) return fail(BA_ERR_NCCL, "ncclCommInitRank failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
+  return BA_OK;
+}
+
+int ba_cuda_shard_blocks(int64_t n_blocks, const int64_t* weight, int world_size, int64_t* range_begin) {
+  if (n_blocks < 0 || world_size < 1 || !range_begin) return fail(BA_ERR_INVALID_ARGUMENT, "bad shard arguments");
+  long double total = 0;
+  for (int64_t i = 0; i < n_blocks; ++i) total += weight ? (long double)weight[i] : 1.0L;
+  range_begin[0] = 0;
+  int64_t i = 0;
+  long double acc = 0;
+  for (int r = 1; r < world_size; ++r) {
+    const long double target = total * r / world_size;
+    while (i < n_blocks && acc + (weight ? weight[i] : 1) * 0.5L <= target) { acc += weight ? weight[i] : 1; ++i; }
+    range_begin[r] = i;
+  }
+  range_begin[world_size] = n_blocks;
+  return BA_OK;
+}
+
+int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t n_obs, const int32_t* cam_idx,
+                        const int32_t* pt_idx, const double* obs_xy, const double* intr, int32_t intr_stride) {
+  if (!p || n_cam < 1 || n_pt < 0 || n_obs < 0 || (n_obs > 0 && (!cam_idx || !pt_idx || !obs_xy)) || !intr ||
+      (intr_stride != 0 && intr_stride != 4))
+    return fail(BA_ERR_INVALID_ARGUMENT, "ba_cuda_set_model_a: bad arguments");
+  if (n_pt >= (int64_t)INT32_MAX) return fail(BA_ERR_UNSUPPORTED, "too many points for one GPU shard");
+  for (int64_t i = 0; i < n_obs; ++i)
+    if (cam_idx[i] < 0 || cam_idx[i] >= n_cam || pt_idx[i] < 0 || pt_idx[i] >= n_pt)
+      return fail(BA_ERR_INVALID_ARGUMENT, "observation %lld references camera %d / point %d out of range", (long long)i, cam_idx[i], pt_idx[i]);
+  BA_TRY(use_device(p));
+  reset_problem(p);
+  p->n_cam = n_cam; p->n_pt = n_pt; p->n_time = 0; p->n_marker = 0;
+  p->n_params = 6 * (int64_t)n_cam + 3 * n_pt;
+  BA_TRY(build_structure(p->S, n_obs, n_pt, n_cam, pt_idx, cam_idx, nullptr, p->st));
+  p->model = 0;
+  // observations in sorted order, intrinsics per f-block
+  {
+    DVec<double> tmp;
+    BA_TRY(tmp.upload(obs_xy, 2 * n_obs, p->st));
+    BA_TRY(p->uv.alloc(n_obs));
+    k_gather_uv<<<grid_for(2 * n_obs, 256), 256, 0, p->st>>>(tmp.p, p->S.perm.p, n_obs, 2, reinterpret_cast<double*>(p->uv.p));
+    std::vector<double> K(4 * (size_t)n_cam);
+    for (int32_t c = 0; c < n_cam; ++c)
+      for (int q = 0; q < 4; ++q) K[4 * c + q] = intr[(size_t)intr_stride * c + q];
+    BA_TRY(p->intr_f.upload(K.data(), K.size(), p->st));
+    BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  }
+  p->h_perm.resize(n_obs);
+  BA_CUDA_TRY(cudaMemcpy(p->h_perm.data(), p->S.perm.p, sizeof(int32_t) * n_obs, cudaMemcpyDeviceToHost));
+  BA_TRY(alloc_workspace(p, 2, 3));
+  return BA_OK;
+}
+
+int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32_t n_marker, int64_t n_mobs,
+                        const int32_t* time_idx, const int32_t* cam_idx, const int32_t* marker_idx, const double* obs8,
+                        const double* intr4_per_cam, double marker_side, int32_t fix_cam0, int32_t fix_marker0) {
+  if (!p || n_cam < 1 || n_time < 0 || n_marker < 1 || n_mobs < 0 || (n_mobs > 0 && (!time_idx || !cam_idx || !marker_idx || !obs8)) ||
+      !intr4_per_cam)
+    return fail(BA_ERR_INVALID_ARGUMENT, "ba_cuda_set_model_b: bad arguments");
+  if (!fix_cam0) return fail(BA_ERR_UNSUPPORTED, "camera 0 is never a parameter block in the reference (fix_cam0 must be 1)");
+  std::vector<int32_t> f0(n_mobs), f1(n_mobs);
+  for (int64_t i = 0; i < n_mobs; ++i) {
+    if (time_idx[i] < 0 || time_idx[i] >= n_time || cam_idx[i] < 0 || cam_idx[i] >= n_cam || marker_idx[i] < 0 || marker_idx[i] >= n_marker)
+      return fail(BA_ERR_INVALID_ARGUMENT, "marker observation %lld has an index out of range", (long long)i);
+    f0[i] = cam_idx[i] == 0 ? -1 : cam_idx[i];                                    // bundle_adjustment_manager.cpp:26
+    f1[i] = (fix_marker0 && marker_idx[i] == 0) ? -1 : n_cam + marker_idx[i];     // bundle_adjustment_manager.cpp:28,58
+  }
+  BA_TRY(use_device(p));
+  reset_problem(p);
+  p->n_cam = n_cam; p->n_time = n_time; p->n_marker = n_marker; p->n_pt = 0;
+  p->n_params = 6 * ((int64_t)n_cam + n_time + n_marker);
+  p->half_side = marker_side / 2;
+  const int64_t nf = (int64_t)n_cam + n_marker;
+  BA_TRY(build_structure(p->S, n_mobs, n_time, nf, time_idx, f0.data(), f1.data(), p->st));
+  p->model = 1;
+  {
+    DVec<double> tmp;
+    DVec<int32_t> cam_in, mk_in;
+    BA_TRY(tmp.upload(obs8, 8 * n_mobs, p->st));
+    BA_TRY(cam_in.upload(cam_idx, n_mobs, p->st));
+    BA_TRY(mk_in.upload(marker_idx, n_mobs, p->st));
+    BA_TRY(p->obs8.alloc(8 * n_mobs)); BA_TRY(p->ob_cam.alloc(n_mobs)); BA_TRY(p->ob_marker.alloc(n_mobs));
+    k_gather_uv<<<grid_for(8 * n_mobs, 256), 256, 0, p->st>>>(tmp.p, p->S.perm.p, n_mobs, 8, p->obs8.p);
+    k_gather_i32<<<grid_for(n_mobs, 256), 256, 0, p->st>>>(p->ob_cam.p, cam_in.p, p->S.perm.p, n_mobs);
+    k_gather_i32<<<grid_for(n_mobs, 256), 256, 0, p->st>>>(p->ob_marker.p, mk_in.p, p->S.perm.p, n_mobs);
+    std::vector<double> K(4 * (size_t)nf, 0.0);
+    std::memcpy(K.data(), intr4_per_cam, sizeof(double) * 4 * n_cam);
+    BA_TRY(p->intr_f.upload(K.data(), K.size(), p->st));
+    BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  }
+  p->h_perm.resize(n_mobs);
+  BA_CUDA_TRY(cudaMemcpy(p->h_perm.data(), p->S.perm.p, sizeof(int32_t) * n_mobs, cudaMemcpyDeviceToHost));
+  BA_TRY(alloc_workspace(p, 8, 6));
+  return BA_OK;
+}
+
+int64_t ba_cuda_num_parameters(const ba_cuda_problem* p) { return p ? p->n_params : 0; }
+
+int ba_cuda_set_parameters(ba_cuda_problem* p, const double* params, int64_t n) {
+  if (!p || !params) return fail(BA_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (p->model < 0) return fail(BA_ERR_STATE, "set_model_* must be called first");
+  if (n != p->n_params) return fail(BA_ERR_INVALID_ARGUMENT, "expected %lld parameters, got %lld", (long long)p->n_params, (long long)n);
+  BA_TRY(use_device(p));
+  const size_t D = sizeof(double);
+  if (p->model == 0) {
+    BA_CUDA_TRY(cudaMemcpyAsync(p->xf.p, params, D * 6 * p->n_cam, cudaMemcpyHostToDevice, p->st));
+    if (p->n_pt) BA_CUDA_TRY(cudaMemcpyAsync(p->xe.p, params + 6 * (int64_t)p->n_cam, D * 3 * p->n_pt, cudaMemcpyHostToDevice, p->st));
+  } else {
+    const int64_t C = p->n_cam, T = p->n_time, M = p->n_marker;
+    BA_CUDA_TRY(cudaMemcpyAsync(p->xf.p, params, D * 6 * C, cudaMemcpyHostToDevice, p->st));
+    if (T) BA_CUDA_TRY(cudaMemcpyAsync(p->xe.p, params + 6 * C, D * 6 * T, cudaMemcpyHostToDevice, p->st));
+    BA_CUDA_TRY(cudaMemcpyAsync(p->xf.p + 6 * C, params + 6 * (C + T), D * 6 * M, cudaMemcpyHostToDevice, p->st));
+  }
+  BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  p->params_set = true;
+  return BA_OK;
+}
+
+int ba_cuda_get_parameters(ba_cuda_problem* p, double* params, int64_t n) {
+  if (!p || !params) return fail(BA_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (p->model < 0 || !p->params_set) return fail(BA_ERR_STATE, "no parameters have been set");
+  if (n != p->n_params) return fail(BA_ERR_INVALID_ARGUMENT, "expected %lld parameters, got %lld", (long long)p->n_params, (long long)n);
+  BA_TRY(use_device(p));
+  const size_t D = sizeof(double);
+  if (p->model == 0) {
+    BA_CUDA_TRY(cudaMemcpyAsync(params, p->xf.p, D * 6 * p->n_cam, cudaMemcpyDeviceToHost, p->st));
+    if (p->n_pt) BA_CUDA_TRY(cudaMemcpyAsync(params + 6 * (int64_t)p->n_cam, p->xe.p, D * 3 * p->n_pt, cudaMemcpyDeviceToHost, p->st));
+  } else {
+    const int64_t C = p->n_cam, T = p->n_time, M = p->n_marker;
+    BA_CUDA_TRY(cudaMemcpyAsync(params, p->xf.p, D * 6 * C, cudaMemcpyDeviceToHost, p->st));
+    if (T) BA_CUDA_TRY(cudaMemcpyAsync(params + 6 * C, p->xe.p, D * 6 * T, cudaMemcpyDeviceToHost, p->st));
+    BA_CUDA_TRY(cudaMemcpyAsync(params + 6 * (C + T), p->xf.p + 6 * C, D * 6 * M, cudaMemcpyDeviceToHost, p->st));
+  }
+  BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  return BA_OK;
+}
+
+int ba_cuda_solve(ba_cuda_problem* p, const ba_cuda_options* options, ba_cuda_summary* summary) {
+  if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
+  if (p->model < 0 || !p->params_set) return fail(BA_ERR_STATE, "set_model_* and set_parameters must be called before solve");
+  BA_TRY(use_device(p));
+  ba_cuda_options opt;
+  if (options) opt = *options; else ba_cuda_options_init(&opt);
+  if (opt.rcs_solver == BA_RCS_PCG) return fail(BA_ERR_UNSUPPORTED, "PCG reduced-system solver is not in this build yet");
+  int rc;
+  if (p->model == 0) rc = minimize<2, 3, 1, 1>(p, opt, summary);
+  else rc = minimize<8, 6, 32, 2>(p, opt, summary);
+  if (rc != BA_OK) return rc;
+  if (summary) {
+    int64_t ae = 0, af = 0;
+    BA_TRY(count_active(p, p->S.e_ptr, p->S.ne, &ae));
+    BA_TRY(count_active(p, p->S.fobs_ptr, p->S.nf, &af));
+    summary->num_free_parameters = ae * (p->model == 0 ? 3 : 6) + af * 6;
+    summary->rcs_dim = (int32_t)(6 * af);
+  }
+  return BA_OK;
+}
+
+int ba_cuda_get_iterations(ba_cuda_problem* p, ba_cuda_iteration* rows, int cap) {
+  if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
+  const int n = (int)p->rows.size();
+  if (rows) for (int i = 0; i < std::min(n, cap); ++i) rows[i] = p->rows[i];
+  return n;
+}
+
+int ba_cuda_eval(ba_cuda_problem* p, double* cost, double* residuals, double* jac) {
+  if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
+  if (p->model < 0 || !p->params_set) return fail(BA_ERR_STATE, "set_model_* and set_parameters must be called before eval");
+  BA_TRY(use_device(p));
+  const Structure& S = p->S;
+  const int RD = p->model == 0 ? 2 : 8, DE = p->model == 0 ? 3 : 6;
+  k_fill<<<grid_for(S.ne * DE, 256), 256, 0, p->st>>>(p->se.p, S.ne * DE, 1.0);
+  k_fill<<<grid_for(S.nf * 6, 256), 256, 0, p->st>>>(p->sf.p, S.nf * 6, 1.0);
+  BA_TRY(build_tables(p, false));  // warm the tables outside the timed kernel
+  BA_CUDA_TRY(cudaEventRecord(p->k0, p->st));
+  BA_TRY(run_jacobian(p));
+  BA_CUDA_TRY(cudaEventRecord(p->k1, p->st));
+  BA_TRY(allreduce(p, p->scal.p + S_COST, 1, kNcclSum));
+  BA_TRY(fetch_scalars(p));
+  BA_CUDA_TRY(cudaEventElapsedTime(&p->last_kernel_ms, p->k0, p->k1));
+  if (cost) *cost = 0.5 * p->h_scal[S_COST];
+  if (residuals) {
+    std::vector<double> h(S.nb * RD);
+    BA_CUDA_TRY(cudaMemcpy(h.data(), p->RES.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+    for (int64_t b = 0; b < S.nb; ++b) std::memcpy(residuals + (int64_t)p->h_perm[b] * RD, &h[b * RD], sizeof(double) * RD);
+  }
+  if (jac) {
+    std::vector<double> he(S.nb * RD * DE), h0(S.nb * RD * 6), h1;
+    BA_CUDA_TRY(cudaMemcpy(he.data(), p->JE.p, sizeof(double) * he.size(), cudaMemcpyDeviceToHost));
+    BA_CUDA_TRY(cudaMemcpy(h0.data(), p->JF0.p, sizeof(double) * h0.size(), cudaMemcpyDeviceToHost));
+    if (p->model == 1) { h1.resize(S.nb * RD * 6); BA_CUDA_TRY(cudaMemcpy(h1.data(), p->JF1.p, sizeof(double) * h1.size(), cudaMemcpyDeviceToHost)); }
+    for (int64_t b = 0; b < S.nb; ++b) {
+      const int64_t o = p->h_perm[b];
+      if (p->model == 0) {
+        std::memcpy(jac + o * 18, &h0[b * 12], sizeof(double) * 12);
+        std::memcpy(jac + o * 18 + 12, &he[b * 6], sizeof(double) * 6);
+      } else {
+        std::memcpy(jac + o * 144, &h0[b * 48], sizeof(double) * 48);
+        std::memcpy(jac + o * 144 + 48, &he[b * 48], sizeof(double) * 48);
+        std::memcpy(jac + o * 144 + 96, &h1[b * 48], sizeof(double) * 48);
+      }
+    }
+  }
+  return BA_OK;
+}
+
+
+int ba_cuda_reprojection_error(ba_cuda_problem* p, double* sum_half_sq, double* rms_per_coord) {
+  if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
+  if (p->model < 0 || !p->params_set) return fail(BA_ERR_STATE, "set_model_* and set_parameters must be called first");
+  BA_TRY(use_device(p));
+  // evaluate at x through the candidate buffers (same kernel as the LM cost evaluation)
+  BA_CUDA_TRY(cudaMemcpyAsync(p->xf_c.p, p->xf.p, p->xf.bytes(), cudaMemcpyDeviceToDevice, p->st));
+  BA_CUDA_TRY(cudaMemcpyAsync(p->xe_c.p, p->xe.p, p->xe.bytes(), cudaMemcpyDeviceToDevice, p->st));
+  BA_TRY(build_tables(p, true));
+  BA_CUDA_TRY(cudaEventRecord(p->k0, p->st));
+  BA_TRY(run_cost_candidate(p));
+  BA_CUDA_TRY(cudaEventRecord(p->k1, p->st));
+  BA_TRY(allreduce(p, p->scal.p + S_CAND, 1, kNcclSum));
+  BA_TRY(fetch_scalars(p));
+  BA_CUDA_TRY(cudaEventElapsedTime(&p->last_kernel_ms, p->k0, p->k1));
+  const double err = 0.5 * p->h_scal[S_CAND];
+  const double n_points = (double)(p->model == 0 ? p->S.nb : 4 * p->S.nb) * p->world;  // exact for equal shards only
+  if (sum_half_sq) *sum_half_sq = err;
+  if (rms_per_coord) *rms_per_coord = std::pow((err * 2.0) / (n_points * 2.0), 0.5);
+  return BA_OK;
+}
+
+int ba_cuda_project_points_error(ba_cuda_problem* p, int64_t n_points, const double* xyz, const int32_t* cam_of_point,
+                                 int32_t n_cam, const double* rvec_tvec6, const double* intr4, const float* image_xy,
+                                 double* sum_half_sq, double* rms_per_coord, double* reprojected_xy) {
+  if (!p || n_points < 0 || n_cam < 1 || !rvec_tvec6 || !intr4 || (n_points > 0 && (!xyz || !cam_of_point || !image_xy)))
+    return fail(BA_ERR_INVALID_ARGUMENT, "ba_cuda_project_points_error: bad arguments");
+  for (int64_t i = 0; i < n_points; ++i)
+    if (cam_of_point[i] < 0 || cam_of_point[i] >= n_cam) return fail(BA_ERR_INVALID_ARGUMENT, "point %lld: camera out of range", (long long)i);
+  BA_TRY(use_device(p));
+  cudaStream_t st = p->st;
+  DVec<double> d_xyz, d_rt, d_K, d_R, d_rep, d_part, d_out;
+  DVec<int32_t> d_cam;
+  DVec<float> d_img;
+  BA_TRY(d_xyz.upload(xyz, 3 * n_points, st)); BA_TRY(d_cam.upload(cam_of_point, n_points, st));
+  BA_TRY(d_img.upload(image_xy, 2 * n_points, st)); BA_TRY(d_rt.upload(rvec_tvec6, 6 * (size_t)n_cam, st));
+  BA_TRY(d_K.upload(intr4, 4 * (size_t)n_cam, st)); BA_TRY(d_R.alloc(9 * (size_t)n_cam));
+  const int grid = (int)grid_for(n_points, 256);
+  BA_TRY(d_rep.alloc(reprojected_xy ? 2 * n_points : 0)); BA_TRY(d_part.alloc(grid)); BA_TRY(d_out.alloc(1));
+  k_rodrigues_cv<<<grid_for(n_cam, 64), 64, 0, st>>>(d_rt.p, n_cam, d_R.p, nullptr);
+  BA_CUDA_TRY(cudaEventRecord(p->k0, st));
+  k_project_error<<<grid, 256, 0, st>>>(n_points, d_xyz.p, d_cam.p, d_R.p, d_rt.p, d_K.p, d_img.p, reprojected_xy ? d_rep.p : nullptr, d_part.p);
+  k_fold_partials<<<1, 1024, 0, st>>>(d_part.p, grid, d_out.p, 0, 0);
+  BA_CUDA_TRY(cudaEventRecord(p->k1, st));
+  BA_CUDA_TRY(cudaGetLastError());
+  double err = 0.0;
+  BA_CUDA_TRY(cudaMemcpyAsync(&err, d_out.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (reprojected_xy) BA_CUDA_TRY(cudaMemcpyAsync(reprojected_xy, d_rep.p, sizeof(double) * 2 * n_points, cudaMemcpyDeviceToHost, st));
+  BA_CUDA_TRY(cudaStreamSynchronize(st));
+  BA_CUDA_TRY(cudaEventElapsedTime(&p->last_kernel_ms, p->k0, p->k1));
+  if (n_points == 0) err = 0.0;
+  if (sum_half_sq) *sum_half_sq = err;
+  if (rms_per_coord) *rms_per_coord = std::pow((err * 2.0) / (n_points * 2.0), 0.5);
+  return BA_OK;
+}
+
+int ba_cuda_model_b_outputs(ba_cuda_problem* p, double* rot9, double* inv12, double* corners) {
+  if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
+  if (p->model != 1 || !p->params_set) return fail(BA_ERR_STATE, "a Model B problem with parameters is required");
+  BA_TRY(use_device(p));
+  cudaStream_t st = p->st;
+  const int C = p->n_cam;
+  const Structure& S = p->S;
+  DVec<double> d_R, d_inv, d_c;
+  BA_TRY(d_R.alloc(9 * (size_t)C)); BA_TRY(d_inv.alloc(12 * (size_t)C)); BA_TRY(d_c.alloc(12 * S.nb));
+  k_rodrigues_cv<<<grid_for(C, 64), 64, 0, st>>>(p->xf.p, C, d_R.p, d_inv.p);  // the first C f-blocks are the cameras
+  BA_TRY(build_tables(p, false));
+  k_corners_b<<<grid_for(S.nb * 4, 256), 256, 0, st>>>(S.nb, S.perm.p, S.ob_e.p, p->ob_marker.p, C, p->tab_f.p, p->tab_e.p, p->half_side, d_c.p);
+  BA_CUDA_TRY(cudaGetLastError());
+  if (rot9) BA_CUDA_TRY(cudaMemcpyAsync(rot9, d_R.p, d_R.bytes(), cudaMemcpyDeviceToHost, st));
+  if (inv12) BA_CUDA_TRY(cudaMemcpyAsync(inv12, d_inv.p, d_inv.bytes(), cudaMemcpyDeviceToHost, st));
+  if (corners && S.nb) BA_CUDA_TRY(cudaMemcpyAsync(corners, d_c.p, d_c.bytes(), cudaMemcpyDeviceToHost, st));
+  BA_CUDA_TRY(cudaStreamSynchronize(st));
+  return BA_OK;
+}
+
+double ba_cuda_last_kernel_ms(const ba_cuda_problem* p) { return p ? (double)p->last_kernel_ms : 0.0; }
+
+}  // extern "C"

@@ -1,0 +1,359 @@
+// ba_structure.cuh -- one-time, on-device construction of the index structure of a problem.
+//
+// Every residual block ("obs") touches one eliminated block e (Model A: point, Model B:
+// frame) and up to two kept blocks f (Model A: camera; Model B: camera and marker).  This
+// file sorts the observations by e, enumerates the (e,f) incidences, the per-f gather
+// lists, and the destination blocks (fa <= fb) of the reduced camera system together with
+// the list of incidence pairs that contribute to each of them.  All lists are produced by
+// stable radix sorts, so every later reduction runs in a fixed, reproducible order.
+//
+// Replaces what ceres::Problem::AddResidualBlock + Program/ParameterBlockOrdering build on
+// the host (reference call sites: bundle_adjustment_manager.cpp:37,50,67,81).
+#pragma once
+#include "ba_util.cuh"
+
+namespace ba {
+
+struct Chunks {
+  int n = 0;     // number of chunks
+  int nseg = 0;  // number of segments
+  int ch = 0;    // max entries per chunk
+  DVec<int32_t> seg;        // chunk -> segment
+  DVec<int64_t> begin;      // chunk -> first entry (end = min(begin + ch, ptr[seg + 1]))
+  DVec<int32_t> seg_first;  // nseg + 1: first chunk of every segment
+};
+
+struct Structure {
+  int64_t nb = 0, ne = 0, nf = 0, ninc = 0, npairs = 0;
+  int ndest = 0;
+  int nslots = 1;  // f slots per obs
+  DVec<int32_t> perm, ob_e, ob_f0, ob_f1;
+  DVec<int64_t> e_ptr;
+  // incidences; for nslots == 1 they alias the observation arrays (incidence id == obs id)
+  DVec<int32_t> own_inc_e, own_inc_f, own_ob_inc0, ob_inc1;
+  DVec<int64_t> own_einc_ptr;
+  const int32_t* inc_e = nullptr;
+  const int32_t* inc_f = nullptr;
+  const int32_t* ob_inc0 = nullptr;  // nullptr => identity
+  const int64_t* einc_ptr = nullptr;
+  DVec<int64_t> incobs_ptr;  // nslots == 2 only: incidence -> (obs << 1 | slot)
+  DVec<int32_t> incobs;
+  DVec<int64_t> finc_ptr, fobs_ptr;
+  DVec<int32_t> finc, fobs;  // fobs entries are (obs << 1 | slot)
+  DVec<int32_t> dest_fa, dest_fb, diag_dest;
+  DVec<int64_t> dpair_ptr;
+  DVec<int2> pairs;
+  DVec<int64_t> dobs_ptr;  // nslots == 2 only: dest -> obs having (f0,f1) == (fa,fb)
+  DVec<int32_t> dobs;
+  Chunks ch_fobs, ch_finc, ch_pairs, ch_dobs;
+};
+
+// ---- small setup kernels ---------------------------------------------------------------
+__global__ void k_iota(int32_t* a, int64_t n, int shift) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (int32_t)(i << shift);
+}
+__global__ void k_gather_i32(int32_t* dst, const int32_t* src, const int32_t* idx, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src ? src[idx[i]] : -1;
+}
+// ptr[s] = first position whose key >= s, for s in [0, nseg]; keys sorted ascending, keys >= nseg are "invalid tail".
+template <typename K>
+__global__ void k_seg_ptr(const K* __restrict__ keys, int64_t n, int64_t nseg, int64_t* ptr) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n == 0) {
+    if (i <= nseg) ptr[i] = 0;
+    return;
+  }
+  if (i >= n) return;
+  const int64_t k = min((int64_t)keys[i], nseg);
+  const int64_t kp = (i == 0) ? -1 : min((int64_t)keys[i - 1], nseg);
+  for (int64_t s = kp + 1; s <= k; ++s) ptr[s] = i;
+  if (i == n - 1)
+    for (int64_t s = k + 1; s <= nseg; ++s) ptr[s] = n;
+}
+__global__ void k_slot_keys(const int32_t* f0, const int32_t* f1, int64_t nb, int32_t* keys, int32_t* vals) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  keys[2 * i] = f0[i] >= 0 ? f0[i] : INT32_MAX;
+  vals[2 * i] = (int32_t)(i << 1);
+  keys[2 * i + 1] = f1[i] >= 0 ? f1[i] : INT32_MAX;
+  vals[2 * i + 1] = (int32_t)(i << 1) | 1;
+}
+__global__ void k_ef_keys(const int32_t* e, const int32_t* f0, const int32_t* f1, int64_t nb, int64_t nf, uint64_t* keys) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  keys[2 * i] = f0[i] >= 0 ? (uint64_t)e[i] * nf + f0[i] : ~0ull;
+  keys[2 * i + 1] = f1[i] >= 0 ? (uint64_t)e[i] * nf + f1[i] : ~0ull;
+}
+__global__ void k_split_ef(const uint64_t* keys, int64_t n, int64_t nf, int32_t* e, int32_t* f) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  e[i] = (int32_t)(keys[i] / nf);
+  f[i] = (int32_t)(keys[i] % nf);
+}
+__device__ __forceinline__ int64_t lower_bound_u64(const uint64_t* a, int64_t n, uint64_t v) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__global__ void k_obs_inc(const int32_t* e, const int32_t* f0, const int32_t* f1, int64_t nb, int64_t nf,
+                          const uint64_t* uniq, int64_t ninc, int32_t* inc0, int32_t* inc1, int32_t* keys, int32_t* vals) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const int32_t a = f0[i] >= 0 ? (int32_t)lower_bound_u64(uniq, ninc, (uint64_t)e[i] * nf + f0[i]) : -1;
+  const int32_t b = f1[i] >= 0 ? (int32_t)lower_bound_u64(uniq, ninc, (uint64_t)e[i] * nf + f1[i]) : -1;
+  inc0[i] = a; inc1[i] = b;
+  keys[2 * i] = a >= 0 ? a : INT32_MAX; vals[2 * i] = (int32_t)(i << 1);
+  keys[2 * i + 1] = b >= 0 ? b : INT32_MAX; vals[2 * i + 1] = (int32_t)(i << 1) | 1;
+}
+// ordered incidence pairs (i,j) of one e-block with f_i < f_j, or f_i == f_j (both orders, and i == j)
+__global__ void k_pair_count(const int64_t* einc_ptr, const int32_t* inc_f, int64_t ne, int64_t* cnt) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e > ne) return;
+  if (e == ne) { cnt[e] = 0; return; }
+  int64_t c = 0;
+  for (int64_t i = einc_ptr[e]; i < einc_ptr[e + 1]; ++i)
+    for (int64_t j = einc_ptr[e]; j < einc_ptr[e + 1]; ++j) c += (inc_f[i] <= inc_f[j]) ? 1 : 0;
+  cnt[e] = c;
+}
+__global__ void k_pair_fill(const int64_t* einc_ptr, const int32_t* inc_f, int64_t ne, int64_t nf, const int64_t* off,
+                            uint64_t* keys, uint64_t* vals) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int64_t o = off[e];
+  for (int64_t i = einc_ptr[e]; i < einc_ptr[e + 1]; ++i)
+    for (int64_t j = einc_ptr[e]; j < einc_ptr[e + 1]; ++j)
+      if (inc_f[i] <= inc_f[j]) {
+        keys[o] = (uint64_t)inc_f[i] * nf + inc_f[j];
+        vals[o] = (uint64_t)(uint32_t)i | ((uint64_t)(uint32_t)j << 32);
+        ++o;
+      }
+}
+__global__ void k_pair_diag_sentinels(int64_t nf, int64_t base, uint64_t* keys, uint64_t* vals) {
+  const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  keys[base + f] = (uint64_t)f * nf + f;
+  vals[base + f] = ~0ull;  // i = j = -1: contributes nothing, only guarantees the (f,f) destination exists
+}
+__global__ void k_dest_finish(const uint64_t* ukeys, int ndest, int64_t nf, int32_t* fa, int32_t* fb, int32_t* diag_dest) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= ndest) return;
+  const int32_t a = (int32_t)(ukeys[d] / nf), b = (int32_t)(ukeys[d] % nf);
+  fa[d] = a; fb[d] = b;
+  if (a == b) diag_dest[a] = d;
+}
+__global__ void k_unpack_pairs(const uint64_t* vals, int64_t n, int2* pairs) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pairs[i] = make_int2((int32_t)(uint32_t)(vals[i] & 0xffffffffu), (int32_t)(uint32_t)(vals[i] >> 32));
+}
+__global__ void k_ff_keys(const int32_t* f0, const int32_t* f1, int64_t nb, int64_t nf, uint64_t* keys) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  keys[i] = (f0[i] >= 0 && f1[i] >= 0) ? (uint64_t)f0[i] * nf + f1[i] : ~0ull;
+}
+__global__ void k_dobs_ptr(const uint64_t* sorted_keys, int64_t nb, const uint64_t* dest_keys, int ndest, int64_t* ptr) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d > ndest) return;
+  ptr[d] = d < ndest ? lower_bound_u64(sorted_keys, nb, dest_keys[d]) : lower_bound_u64(sorted_keys, nb, ~0ull);
+}
+__global__ void k_chunk_count(const int64_t* ptr, int nseg, int ch, int32_t* cnt) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > nseg) return;
+  cnt[s] = s < nseg ? (int32_t)((ptr[s + 1] - ptr[s] + ch - 1) / ch) : 0;
+}
+__global__ void k_chunk_fill(const int64_t* ptr, int nseg, int ch, const int32_t* first, int32_t* seg, int64_t* begin) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  int64_t b = ptr[s];
+  for (int c = first[s]; c < first[s + 1]; ++c, b += ch) { seg[c] = s; begin[c] = b; }
+}
+
+inline int bits_for(uint64_t max_value) {
+  int b = 1;
+  while (b < 64 && (max_value >> b) != 0) ++b;
+  return b;
+}
+
+inline int build_chunks(Chunks& C, const int64_t* ptr, int nseg, int ch, cudaStream_t st) {
+  C.nseg = nseg; C.ch = ch;
+  DVec<int32_t> cnt;
+  BA_TRY(cnt.alloc(nseg + 1));
+  BA_TRY(C.seg_first.alloc(nseg + 1));
+  k_chunk_count<<<grid_for(nseg + 1, 256), 256, 0, st>>>(ptr, nseg, ch, cnt.p);
+  BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt.p, C.seg_first.p, nseg + 1, st); }));
+  int32_t total = 0;
+  BA_CUDA_TRY(cudaMemcpyAsync(&total, C.seg_first.p + nseg, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  BA_CUDA_TRY(cudaStreamSynchronize(st));
+  C.n = total;
+  BA_TRY(C.seg.alloc(total));
+  BA_TRY(C.begin.alloc(total));
+  if (nseg > 0) k_chunk_fill<<<grid_for(nseg, 256), 256, 0, st>>>(ptr, nseg, ch, C.seg_first.p, C.seg.p, C.begin.p);
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
+// sorts (key,val) int32 pairs where invalid entries carry key INT32_MAX; returns CSR over [0,nseg)
+inline int sort_to_csr(const int32_t* keys_in, const int32_t* vals_in, int64_t n, int64_t nseg, DVec<int64_t>& ptr,
+                       DVec<int32_t>& vals_out, cudaStream_t st) {
+  DVec<int32_t> keys_sorted;
+  BA_TRY(keys_sorted.alloc(n));
+  BA_TRY(vals_out.alloc(n));
+  BA_TRY(ptr.alloc(nseg + 1));
+  if (n > 0)
+    BA_TRY(cub_call([&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, keys_in, keys_sorted.p, vals_in, vals_out.p, (int)n, 0, 32, st);
+    }));
+  k_seg_ptr<int32_t><<<grid_for(n > nseg + 1 ? n : nseg + 1, 256), 256, 0, st>>>(keys_sorted.p, n, nseg, ptr.p);
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
+// h_e / h_f0 / h_f1 are in the caller's observation order; h_f1 may be NULL (one f slot).
+inline int build_structure(Structure& S, int64_t nb, int64_t ne, int64_t nf, const int32_t* h_e, const int32_t* h_f0,
+                           const int32_t* h_f1, cudaStream_t st) {
+  if (nb >= (int64_t)1 << 30) return fail(BA_ERR_UNSUPPORTED, "more than 2^30 residual blocks per GPU are not supported");
+  S.nb = nb; S.ne = ne; S.nf = nf; S.nslots = h_f1 ? 2 : 1;
+  const int B = 256;
+  DVec<int32_t> e_in, f0_in, f1_in, iota;
+  BA_TRY(e_in.upload(h_e, nb, st));
+  BA_TRY(f0_in.upload(h_f0, nb, st));
+  if (h_f1) BA_TRY(f1_in.upload(h_f1, nb, st));
+  BA_TRY(iota.alloc(nb));
+  k_iota<<<grid_for(nb, B), B, 0, st>>>(iota.p, nb, 0);
+  // 1. observations sorted by e (stable)
+  BA_TRY(S.ob_e.alloc(nb)); BA_TRY(S.perm.alloc(nb)); BA_TRY(S.ob_f0.alloc(nb)); BA_TRY(S.ob_f1.alloc(nb));
+  if (nb > 0)
+    BA_TRY(cub_call([&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, e_in.p, S.ob_e.p, iota.p, S.perm.p, (int)nb, 0, bits_for((uint64_t)ne), st);
+    }));
+  k_gather_i32<<<grid_for(nb, B), B, 0, st>>>(S.ob_f0.p, f0_in.p, S.perm.p, nb);
+  k_gather_i32<<<grid_for(nb, B), B, 0, st>>>(S.ob_f1.p, h_f1 ? f1_in.p : nullptr, S.perm.p, nb);
+  BA_TRY(S.e_ptr.alloc(ne + 1));
+  k_seg_ptr<int32_t><<<grid_for(nb > ne + 1 ? nb : ne + 1, B), B, 0, st>>>(S.ob_e.p, nb, ne, S.e_ptr.p);
+  BA_CUDA_TRY(cudaGetLastError());
+
+  // 2. incidences
+  if (S.nslots == 1) {
+    S.ninc = nb;
+    S.inc_e = S.ob_e.p; S.inc_f = S.ob_f0.p; S.ob_inc0 = nullptr; S.einc_ptr = S.e_ptr.p;
+    BA_TRY(S.ob_inc1.alloc(0));
+  } else {
+    DVec<uint64_t> k2, k2s, uniq;
+    DVec<int64_t> nuniq;
+    BA_TRY(k2.alloc(2 * nb)); BA_TRY(k2s.alloc(2 * nb)); BA_TRY(uniq.alloc(2 * nb)); BA_TRY(nuniq.alloc(1));
+    k_ef_keys<<<grid_for(nb, B), B, 0, st>>>(S.ob_e.p, S.ob_f0.p, S.ob_f1.p, nb, nf, k2.p);
+    int64_t n_unique = 0;
+    uint64_t last = 0;
+    if (nb > 0) {
+      BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, k2.p, k2s.p, (int)(2 * nb), 0, 64, st); }));
+      BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceSelect::Unique(t, b, k2s.p, uniq.p, nuniq.p, (int)(2 * nb), st); }));
+      BA_CUDA_TRY(cudaMemcpyAsync(&n_unique, nuniq.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      BA_CUDA_TRY(cudaStreamSynchronize(st));
+      BA_CUDA_TRY(cudaMemcpyAsync(&last, uniq.p + (n_unique - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      BA_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    S.ninc = n_unique - ((n_unique > 0 && last == ~0ull) ? 1 : 0);
+    BA_TRY(S.own_inc_e.alloc(S.ninc)); BA_TRY(S.own_inc_f.alloc(S.ninc));
+    k_split_ef<<<grid_for(S.ninc, B), B, 0, st>>>(uniq.p, S.ninc, nf, S.own_inc_e.p, S.own_inc_f.p);
+    BA_TRY(S.own_ob_inc0.alloc(nb)); BA_TRY(S.ob_inc1.alloc(nb));
+    DVec<int32_t> ik, iv;
+    BA_TRY(ik.alloc(2 * nb)); BA_TRY(iv.alloc(2 * nb));
+    k_obs_inc<<<grid_for(nb, B), B, 0, st>>>(S.ob_e.p, S.ob_f0.p, S.ob_f1.p, nb, nf, uniq.p, S.ninc, S.own_ob_inc0.p, S.ob_inc1.p, ik.p, iv.p);
+    BA_TRY(sort_to_csr(ik.p, iv.p, 2 * nb, S.ninc, S.incobs_ptr, S.incobs, st));
+    BA_TRY(S.own_einc_ptr.alloc(ne + 1));
+    k_seg_ptr<int32_t><<<grid_for(S.ninc > ne + 1 ? S.ninc : ne + 1, B), B, 0, st>>>(S.own_inc_e.p, S.ninc, ne, S.own_einc_ptr.p);
+    S.inc_e = S.own_inc_e.p; S.inc_f = S.own_inc_f.p; S.ob_inc0 = S.own_ob_inc0.p; S.einc_ptr = S.own_einc_ptr.p;
+    BA_CUDA_TRY(cudaStreamSynchronize(st));  // uniq etc. go out of scope
+  }
+  if (S.ninc >= (int64_t)1 << 30) return fail(BA_ERR_UNSUPPORTED, "too many incidences");
+
+  // 3. f -> incidences, f -> observations
+  {
+    DVec<int32_t> inc_iota;
+    BA_TRY(inc_iota.alloc(S.ninc));
+    k_iota<<<grid_for(S.ninc, B), B, 0, st>>>(inc_iota.p, S.ninc, 0);
+    BA_TRY(sort_to_csr(S.inc_f, inc_iota.p, S.ninc, nf, S.finc_ptr, S.finc, st));
+    if (S.nslots == 1) {
+      DVec<int32_t> v;
+      BA_TRY(v.alloc(nb));
+      k_iota<<<grid_for(nb, B), B, 0, st>>>(v.p, nb, 1);
+      BA_TRY(sort_to_csr(S.ob_f0.p, v.p, nb, nf, S.fobs_ptr, S.fobs, st));
+      BA_CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+      DVec<int32_t> k, v;
+      BA_TRY(k.alloc(2 * nb)); BA_TRY(v.alloc(2 * nb));
+      k_slot_keys<<<grid_for(nb, B), B, 0, st>>>(S.ob_f0.p, S.ob_f1.p, nb, k.p, v.p);
+      BA_TRY(sort_to_csr(k.p, v.p, 2 * nb, nf, S.fobs_ptr, S.fobs, st));
+      BA_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+  }
+
+  // 4. destination blocks of the reduced system and their incidence-pair lists
+  DVec<uint64_t> dest_keys;
+  {
+    DVec<int64_t> cnt, off;
+    BA_TRY(cnt.alloc(ne + 1)); BA_TRY(off.alloc(ne + 1));
+    k_pair_count<<<grid_for(ne + 1, 128), 128, 0, st>>>(S.einc_ptr, S.inc_f, ne, cnt.p);
+    BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt.p, off.p, (int)(ne + 1), st); }));
+    int64_t np = 0;
+    BA_CUDA_TRY(cudaMemcpyAsync(&np, off.p + ne, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+    S.npairs = np + nf;
+    if (S.npairs >= (int64_t)INT32_MAX) return fail(BA_ERR_UNSUPPORTED, "too many incidence pairs (%lld) for one GPU", (long long)S.npairs);
+    DVec<uint64_t> pk, pv, pks, pvs;
+    BA_TRY(pk.alloc(S.npairs)); BA_TRY(pv.alloc(S.npairs)); BA_TRY(pks.alloc(S.npairs)); BA_TRY(pvs.alloc(S.npairs));
+    if (ne > 0) k_pair_fill<<<grid_for(ne, 128), 128, 0, st>>>(S.einc_ptr, S.inc_f, ne, nf, off.p, pk.p, pv.p);
+    k_pair_diag_sentinels<<<grid_for(nf, B), B, 0, st>>>(nf, np, pk.p, pv.p);
+    BA_TRY(cub_call([&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, pk.p, pks.p, pv.p, pvs.p, (int)S.npairs, 0, bits_for((uint64_t)nf * nf), st);
+    }));
+    pk.release(); pv.release();
+    DVec<int64_t> run_cnt;
+    DVec<int32_t> nruns;
+    BA_TRY(dest_keys.alloc(S.npairs)); BA_TRY(run_cnt.alloc(S.npairs + 1)); BA_TRY(nruns.alloc(1));
+    BA_TRY(cub_call([&](void* t, size_t& b) {
+      return cub::DeviceRunLengthEncode::Encode(t, b, pks.p, dest_keys.p, run_cnt.p, nruns.p, (int)S.npairs, st);
+    }));
+    int32_t nd = 0;
+    BA_CUDA_TRY(cudaMemcpyAsync(&nd, nruns.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+    S.ndest = nd;
+    BA_TRY(S.dpair_ptr.alloc(nd + 1));
+    BA_CUDA_TRY(cudaMemsetAsync(run_cnt.p + nd, 0, sizeof(int64_t), st));
+    BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, run_cnt.p, S.dpair_ptr.p, nd + 1, st); }));
+    BA_TRY(S.dest_fa.alloc(nd)); BA_TRY(S.dest_fb.alloc(nd)); BA_TRY(S.diag_dest.alloc(nf));
+    k_dest_finish<<<grid_for(nd, B), B, 0, st>>>(dest_keys.p, nd, nf, S.dest_fa.p, S.dest_fb.p, S.diag_dest.p);
+    BA_TRY(S.pairs.alloc(S.npairs));
+    k_unpack_pairs<<<grid_for(S.npairs, B), B, 0, st>>>(pvs.p, S.npairs, S.pairs.p);
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  // 5. Model B: observations whose (f0,f1) is a destination block (off-diagonal F^T F terms)
+  if (S.nslots == 2) {
+    DVec<uint64_t> k, ks;
+    DVec<int32_t> v;
+    BA_TRY(k.alloc(nb)); BA_TRY(ks.alloc(nb)); BA_TRY(v.alloc(nb)); BA_TRY(S.dobs.alloc(nb));
+    k_ff_keys<<<grid_for(nb, B), B, 0, st>>>(S.ob_f0.p, S.ob_f1.p, nb, nf, k.p);
+    k_iota<<<grid_for(nb, B), B, 0, st>>>(v.p, nb, 0);
+    if (nb > 0)
+      BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortPairs(t, b, k.p, ks.p, v.p, S.dobs.p, (int)nb, 0, 64, st); }));
+    BA_TRY(S.dobs_ptr.alloc(S.ndest + 1));
+    k_dobs_ptr<<<grid_for(S.ndest + 1, B), B, 0, st>>>(ks.p, nb, dest_keys.p, S.ndest, S.dobs_ptr.p);
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  dest_keys.release();
+  // 6. chunk tables of the gather reductions
+  BA_TRY(build_chunks(S.ch_fobs, S.fobs_ptr.p, (int)nf, 256, st));
+  BA_TRY(build_chunks(S.ch_finc, S.finc_ptr.p, (int)nf, 512, st));
+  BA_TRY(build_chunks(S.ch_pairs, S.dpair_ptr.p, S.ndest, 256, st));
+  if (S.nslots == 2) BA_TRY(build_chunks(S.ch_dobs, S.dobs_ptr.p, S.ndest, 128, st));
+  BA_CUDA_TRY(cudaStreamSynchronize(st));
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
+}  // namespace ba

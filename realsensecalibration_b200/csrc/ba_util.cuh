@@ -1,0 +1,189 @@
+// ba_util.cuh -- error plumbing, device buffers, cub wrappers, deterministic reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "ba_cuda.h"
+
+namespace ba {
+
+// ---- thread-local last error --------------------------------------------------------
+inline char* err_buf() {
+  static thread_local char buf[1024] = {0};
+  return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 1024, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define BA_CUDA_TRY(expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return ba::fail(e__ == cudaErrorMemoryAllocation ? BA_ERR_OUT_OF_MEMORY : BA_ERR_CUDA,    \
+                      "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));   \
+  } while (0)
+
+#define BA_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != BA_OK) return rc__; \
+  } while (0)
+
+// ---- owning device buffer -----------------------------------------------------------
+template <typename T>
+struct DVec {
+  T* p = nullptr;
+  size_t n = 0;
+  DVec() = default;
+  DVec(const DVec&) = delete;
+  DVec& operator=(const DVec&) = delete;
+  ~DVec() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  int alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) count = 1;  // keep pointers non-null so kernels can take them
+    BA_CUDA_TRY(cudaMalloc((void**)&p, count * sizeof(T)));
+    return BA_OK;
+  }
+  int alloc_zero(size_t count, cudaStream_t s) {
+    BA_TRY(alloc(count));
+    BA_CUDA_TRY(cudaMemsetAsync(p, 0, (count ? count : 1) * sizeof(T), s));
+    return BA_OK;
+  }
+  int upload(const T* host, size_t count, cudaStream_t s) {
+    BA_TRY(alloc(count));
+    if (count) BA_CUDA_TRY(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    return BA_OK;
+  }
+  void swap(DVec& o) {
+    T* tp = p; p = o.p; o.p = tp;
+    size_t tn = n; n = o.n; o.n = tn;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block > 0 ? (n + block - 1) / block : 1); }
+
+// ---- cub two-phase call helper --------------------------------------------------------
+template <typename F>
+int cub_call(F&& f) {
+  void* tmp = nullptr;
+  size_t bytes = 0;
+  BA_CUDA_TRY(f(tmp, bytes));
+  BA_CUDA_TRY(cudaMalloc(&tmp, bytes ? bytes : 1));
+  cudaError_t e = f(tmp, bytes);
+  cudaFree(tmp);
+  BA_CUDA_TRY(e);
+  return BA_OK;
+}
+
+// ---- device-side deterministic reductions ----------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;  // valid in lane 0
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+// Sum over a CTA in a fixed tree order; result valid in thread 0.  blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ double block_sum(double v, double* smem32) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem32[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? smem32[threadIdx.x] : 0.0;
+  if (warp == 0) v = warp_sum(v);
+  return v;
+}
+__device__ __forceinline__ double block_max(double v, double* smem32) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) smem32[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? smem32[threadIdx.x] : 0.0;
+  if (warp == 0) v = warp_max(v);
+  return v;
+}
+
+// Folds `n` partials (one per CTA of a previous kernel) into out[slot]; launched <<<1,1024>>>.
+__global__ void k_fold_partials(const double* __restrict__ partial, int n, double* out, int slot, int is_max) {
+  __shared__ double sm[32];
+  double v = 0.0;
+  if (is_max) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v = fmax(v, partial[i]);
+    v = block_max(v, sm);
+  } else {
+    // fixed strided order per thread, then fixed tree: bitwise reproducible for a given n
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += partial[i];
+    v = block_sum(v, sm);
+  }
+  if (threadIdx.x == 0) out[slot] = v;
+}
+
+// ---- small dense algebra in registers ---------------------------------------------------
+template <int D>
+__device__ __forceinline__ bool chol_small(double* A) {  // lower Cholesky in place, row-major
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double d = A[j * D + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= A[j * D + k] * A[j * D + k];
+    if (!(d > 0.0) || !isfinite(d)) return false;
+    const double l = sqrt(d);
+    A[j * D + j] = l;
+    const double inv = 1.0 / l;
+#pragma unroll
+    for (int i = j + 1; i < D; ++i) {
+      double s = A[i * D + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= A[i * D + k] * A[j * D + k];
+      A[i * D + j] = s * inv;
+    }
+  }
+  return true;
+}
+template <int D>
+__device__ __forceinline__ void fwd_small(const double* L, double* x) {  // x <- L^-1 x
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double s = x[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= L[i * D + k] * x[k];
+    x[i] = s / L[i * D + i];
+  }
+}
+template <int D>
+__device__ __forceinline__ void bwd_small(const double* L, double* x) {  // x <- L^-T x
+#pragma unroll
+  for (int i = D - 1; i >= 0; --i) {
+    double s = x[i];
+#pragma unroll
+    for (int k = i + 1; k < D; ++k) s -= L[k * D + i] * x[k];
+    x[i] = s / L[i * D + i];
+  }
+}
+
+}  // namespace ba

@@ -1,0 +1,265 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference's goldens.
+
+Tolerances (BASELINE.json north_star): per-iteration cost within 1e-10 relative with the same trust-region
+schedule and iteration count; final poses within 1e-7 rad / 1e-7 m."""
+import os
+
+import numpy as np
+import pytest
+
+from realsensecalibration_b200 import abi, cuda, formats as F, synthetic as S
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+COST_RTOL = 1e-10
+POSE_ATOL = 1e-7
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    if cuda.device_count() == 0:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+    P = cuda.Problem(0)
+    yield P
+    P.close()
+
+
+def _set_b(P, pb, intr, side, fix0, params=None):
+    P.set_model_b(pb.n_cam, pb.n_time, pb.n_marker, pb.time_idx, pb.cam_idx, pb.marker_idx, pb.obs8, intr, side, fix0)
+    P.set_parameters(pb.params if params is None else params)
+
+
+def _check_rows(rows, rows_o):
+    assert len(rows) == len(rows_o)
+    for a, b in zip(rows, rows_o):
+        assert a["iteration"] == b["iteration"]
+        assert a["step_is_successful"] == b["step_is_successful"] and a["step_is_valid"] == b["step_is_valid"]
+        assert H.rel(a["cost"], b["cost"]) <= COST_RTOL, (a, b)
+        assert H.rel(a["trust_region_radius"], b["trust_region_radius"]) <= 1e-8
+        if b["gradient_max_norm"] > 0:
+            assert H.rel(a["gradient_max_norm"], b["gradient_max_norm"]) <= 1e-7
+        if b["step_norm"] > 0:
+            assert H.rel(a["step_norm"], b["step_norm"]) <= 1e-6
+
+
+def _jac_close(j, jo):
+    scale = np.maximum(np.abs(jo).max(axis=-1, keepdims=True), 1.0)
+    return np.abs(j - jo).max() if j.size == 0 else (np.abs(j - jo) / scale).max()
+
+
+# ---- K1: residual + Jacobian ------------------------------------------------------------------
+def test_eval_model_b_hongo(gpu, oracle):
+    pb, intr, side, fix0 = H.hongo()
+    _set_b(gpu, pb, intr, side, fix0)
+    cost, res, jac = gpu.eval()
+    co, ro, jo = oracle.eval_model_b(pb, intr, side, fix0)
+    assert H.rel(cost, co) < 1e-13 and H.rel(cost, H.HONGO_COSTS[0]) < 1e-12
+    assert np.abs(res - ro).max() < 1e-9
+    assert _jac_close(jac, jo) < 1e-11
+
+
+def test_eval_model_b_test2_zero_angle_branch(gpu, oracle):
+    # all marker rvecs are exactly 0 in this fixture: exercises the theta^2 <= eps branch and its derivative
+    pb, intr, side, fix0 = H.test2()
+    _set_b(gpu, pb, intr, side, fix0)
+    cost, res, jac = gpu.eval()
+    co, ro, jo = oracle.eval_model_b(pb, intr, side, fix0)
+    assert H.rel(cost, co) < 1e-13
+    assert np.abs(res - ro).max() < 1e-9
+    assert _jac_close(jac, jo) < 1e-11
+
+
+def test_eval_model_a_two_cam(gpu, oracle):
+    pa, intr = H.two_cam()
+    gpu.set_model_a(pa.n_cam, pa.n_pt, pa.cam_idx, pa.pt_idx, pa.obs_xy, intr)
+    gpu.set_parameters(pa.params)
+    cost, res, jac = gpu.eval()
+    co, ro, jo = oracle.eval_model_a(pa.n_cam, pa.n_pt, pa.cam_idx, pa.pt_idx, pa.obs_xy, intr, pa.params)
+    assert H.rel(cost, co) < 1e-13
+    assert np.abs(res - ro).max() < 1e-10
+    assert _jac_close(jac, jo) < 1e-11
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_eval_model_a_synthetic_unsorted(gpu, oracle, seed):
+    pr = S.bal_like(40, 3000, 6, 16, seed, variable_degree=True)
+    rng = np.random.default_rng(seed)
+    sh = rng.permutation(pr.n_obs)  # caller order is arbitrary: the library sorts by point itself
+    ci, pi, ob = pr.cam_idx[sh], pr.pt_idx[sh], pr.obs_xy[sh]
+    gpu.set_model_a(pr.n_cam, pr.n_pt, ci, pi, ob, pr.intr)
+    gpu.set_parameters(pr.params)
+    cost, res, jac = gpu.eval()
+    co, ro, jo = oracle.eval_model_a(pr.n_cam, pr.n_pt, ci, pi, ob, pr.intr, pr.params)
+    assert H.rel(cost, co) < 1e-12
+    assert np.abs(res - ro).max() < 1e-9
+    assert _jac_close(jac, jo) < 1e-11
+
+
+# ---- full LM solves against the reference's goldens -------------------------------------------
+def test_solve_hongo_golden(gpu, oracle):
+    pb, intr, side, fix0 = H.hongo()
+    _set_b(gpu, pb, intr, side, fix0)
+    s, rows = gpu.solve()
+    x = gpu.get_parameters()
+    xo, so, rows_o = oracle.solve_model_b(pb, intr, side, fix0)
+    assert s.termination_type == abi.CONVERGENCE and s.termination_reason == abi.REASON_FUNCTION_TOLERANCE
+    assert s.num_iterations == 7 and s.num_free_parameters == 114 and s.num_residuals == 544 and s.rcs_dim == 78
+    _check_rows(rows, rows_o)
+    for r, c in zip(rows, H.HONGO_COSTS):
+        assert H.rel(r["cost"], c) < COST_RTOL
+    H.check_hongo_golden(x, POSE_ATOL, POSE_ATOL)     # the reference's own committed Ceres output
+    H.check_hongo_golden(x, 1e-10, 1e-10)             # and much tighter than the acceptance bar
+    assert np.abs(x - xo).max() < 1e-9
+    assert np.all(x[:6] == pb.params[:6])             # camera 0 is not a parameter block
+    m0 = 6 * (pb.n_cam + pb.n_time)
+    assert np.all(x[m0:m0 + 6] == pb.params[m0:m0 + 6])  # nor is marker 0 under the Main dispatch
+
+
+def test_solve_test2_golden(gpu, oracle):
+    pb, intr, side, fix0 = H.test2()
+    _set_b(gpu, pb, intr, side, fix0)
+    s, rows = gpu.solve()
+    x = gpu.get_parameters()
+    xo, so, rows_o = oracle.solve_model_b(pb, intr, side, fix0)
+    assert s.termination_reason == abi.REASON_FUNCTION_TOLERANCE and s.num_iterations == 4
+    _check_rows(rows, rows_o)
+    H.check_test2_golden(x, 1e-10)
+    assert np.abs(x - xo).max() < 1e-9
+
+
+def test_solve_two_cam(gpu, oracle):
+    pa, intr = H.two_cam()
+    gpu.set_model_a(pa.n_cam, pa.n_pt, pa.cam_idx, pa.pt_idx, pa.obs_xy, intr)
+    gpu.set_parameters(pa.params)
+    s, rows = gpu.solve()
+    x = gpu.get_parameters()
+    xo, so, rows_o = oracle.solve_model_a(pa.n_cam, pa.n_pt, pa.cam_idx, pa.pt_idx, pa.obs_xy, intr, pa.params)
+    assert s.termination_reason == so.termination_reason == abi.REASON_PARAMETER_TOLERANCE
+    assert s.num_iterations == so.num_iterations == 3
+    assert H.rel(rows[0]["cost"], rows_o[0]["cost"]) < COST_RTOL
+    assert H.rel(rows[1]["cost"], rows_o[1]["cost"]) < 1e-7   # cost ~1e-4 of 32 residuals: near cancellation
+    assert rows[2]["cost"] < 1e-10                            # exact fit: under-determined problem, cost -> 0
+    assert np.abs(x - xo).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["cfg1", "rigA", "balA", "rigB", "rigB_sparse"])
+def test_solve_synthetic_vs_oracle(gpu, oracle, name):
+    if name in ("rigB", "rigB_sparse"):
+        pr = S.marker_rig_b(4, 12, 30, 7, visibility=1.0 if name == "rigB" else 0.3)
+        pb = F.ModelBFile(pr.n_time, pr.n_cam, pr.n_marker, pr.counts, pr.time_idx, pr.cam_idx, pr.marker_idx, pr.obs8, pr.params)
+        _set_b(gpu, pb, pr.intr, pr.marker_side, 1)
+        xo, so, rows_o = oracle.solve_model_b(pb, pr.intr, pr.marker_side, 1)
+    else:
+        pr = {"cfg1": lambda: S.two_cam_like(50, 11), "rigA": lambda: S.marker_rig_a(8, 10, 20, 12),
+              "balA": lambda: S.bal_like(60, 5000, 6, 16, 13, variable_degree=True)}[name]()
+        gpu.set_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr)
+        gpu.set_parameters(pr.params)
+        xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params)
+    s, rows = gpu.solve()
+    x = gpu.get_parameters()
+    assert (s.termination_type, s.termination_reason) == (so.termination_type, so.termination_reason)
+    assert s.num_free_parameters == so.num_free_parameters and s.rcs_dim == so.rcs_dim
+    if name == "cfg1":   # zero-residual problem: the last rows sit at round-off level cost
+        assert len(rows) == len(rows_o)
+        assert H.rel(rows[0]["cost"], rows_o[0]["cost"]) <= COST_RTOL
+    else:
+        _check_rows(rows, rows_o)
+        assert np.abs(x - xo).max() < POSE_ATOL
+
+
+def test_rejected_steps_follow_the_same_schedule(gpu, oracle):
+    # a huge initial radius (almost undamped Gauss-Newton) from a poor start forces rejected steps
+    pr = S.marker_rig_a(6, 8, 15, 21, perturb=(0.2, 0.06, 0.04))
+    opt_g, opt_o = cuda.default_options(), oracle.default_options()
+    for o in (opt_g, opt_o):
+        o.initial_trust_region_radius = 1e12
+        o.max_num_iterations = 30
+    gpu.set_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr)
+    gpu.set_parameters(pr.params)
+    s, rows = gpu.solve(opt_g)
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o)
+    assert so.num_unsuccessful_steps > 0, "test problem no longer produces a rejected step"
+    assert s.num_unsuccessful_steps == so.num_unsuccessful_steps and s.num_iterations == so.num_iterations
+    for a, b in zip(rows, rows_o):
+        assert a["step_is_successful"] == b["step_is_successful"]
+        assert H.rel(a["trust_region_radius"], b["trust_region_radius"]) <= 1e-6
+        assert H.rel(a["cost"], b["cost"]) <= 1e-8
+
+
+def test_max_iterations_and_determinism(gpu):
+    pr = S.bal_like(30, 2000, 5, 12, 5)
+    opt = cuda.default_options()
+    opt.max_num_iterations = 2
+    xs = []
+    for _ in range(2):
+        gpu.set_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr)
+        gpu.set_parameters(pr.params)
+        s, rows = gpu.solve(opt)
+        assert s.termination_type == abi.NO_CONVERGENCE and s.termination_reason == abi.REASON_MAX_ITERATIONS
+        assert s.num_iterations == 3
+        xs.append(gpu.get_parameters())
+    assert np.array_equal(xs[0], xs[1])   # no floating-point atomics: bitwise reproducible
+
+
+# ---- K5 and the post-BA outputs ------------------------------------------------------------------
+def test_outputs_and_reprojection_hongo(gpu, oracle, golden_dir):
+    pb, intr, side, fix0 = H.hongo()
+    _set_b(gpu, pb, intr, side, fix0)
+    err0, rms0 = gpu.reprojection_error()
+    assert H.rel(err0, H.HONGO_COSTS[0]) < 1e-12
+    gpu.solve()
+    x = gpu.get_parameters()
+    err, rms = gpu.reprojection_error()
+    assert H.rel(err, 143.62938885186) < 1e-10 and abs(rms - 0.72667) < 1e-4
+    rot, inv, corners = gpu.model_b_outputs()
+    rot_o, inv_o, corners_o = oracle.model_b_outputs(pb, x, side)
+    assert np.abs(rot - rot_o).max() < 1e-14 and np.abs(inv - inv_o).max() < 1e-14
+    assert np.abs(corners - corners_o).max() < 1e-14
+    gold = F.load_opencv_xml(os.path.join(golden_dir, "Correspondence", "hongo", "Camera_Transform.xml"))
+    for c in range(4):
+        assert np.abs(rot[c] - gold["R%d" % c]).max() < 1e-10
+        ext = F.load_extrinsics(os.path.join(golden_dir, "Calibration", "Extrinsics", "mat%d.txt" % c))
+        assert np.abs(inv[c] - ext).max() < 6e-7
+    _, pts = F.load_point3d(os.path.join(golden_dir, "Correspondence", "hongo", "point3d.txt"))
+    assert np.abs(pts - corners).max() < 6e-7
+    # ReprojectionCheck::Reproject on the 6-digit points of point3d.txt with float image points
+    cam_of_point = np.repeat(pb.cam_idx, 4)
+    rt = x[:24].reshape(4, 6)
+    img = pb.obs8.reshape(-1, 2).astype(np.float32)
+    e_g, r_g, rep_g = gpu.project_points_error(pts, cam_of_point, rt, intr, img)
+    e_o, r_o, rep_o = oracle.project_points_error(pts, cam_of_point, rt, intr, img)
+    assert H.rel(e_g, e_o) < 1e-12 and H.rel(r_g, r_o) < 1e-12 and np.abs(rep_g - rep_o).max() < 1e-9
+    assert abs(e_g - 143.63) < 0.5   # 6-digit rounding of the points moves the error slightly
+
+
+def test_empty_and_ragged_inputs(gpu, oracle):
+    # a point / camera that no observation references is not part of the problem; zero observations is legal
+    pr = S.bal_like(12, 300, 4, 8, 9)
+    keep = (pr.pt_idx % 7 != 3) & (pr.cam_idx != 5)
+    ci, pi, ob = pr.cam_idx[keep], pr.pt_idx[keep], pr.obs_xy[keep]
+    gpu.set_model_a(pr.n_cam, pr.n_pt, ci, pi, ob, pr.intr)
+    gpu.set_parameters(pr.params)
+    s, rows = gpu.solve()
+    x = gpu.get_parameters()
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, ci, pi, ob, pr.intr, pr.params)
+    _check_rows(rows, rows_o)
+    assert s.num_free_parameters == so.num_free_parameters
+    assert np.abs(x - xo).max() < POSE_ATOL
+    unused_pt = np.where(np.bincount(pi, minlength=pr.n_pt) == 0)[0]
+    assert unused_pt.size > 0
+    X0 = pr.params[6 * pr.n_cam:].reshape(-1, 3); X1 = x[6 * pr.n_cam:].reshape(-1, 3)
+    assert np.array_equal(X0[unused_pt], X1[unused_pt]) and np.array_equal(x[30:36], pr.params[30:36])
+    gpu.set_model_a(2, 3, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 2)), pr.intr[:2])
+    gpu.set_parameters(np.zeros(21))
+    cost, res, jac = gpu.eval()
+    assert cost == 0.0 and res.shape == (0, 2)
+
+
+def test_error_paths(gpu):
+    with pytest.raises(cuda.BAError):
+        gpu.set_model_a(2, 3, np.array([2], np.int32), np.array([0], np.int32), np.zeros((1, 2)), np.ones(8))
+    P2 = cuda.Problem(0)
+    with pytest.raises(cuda.BAError):
+        P2.solve()
+    P2.close()
