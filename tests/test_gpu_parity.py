@@ -32,13 +32,14 @@ def _set_b(P, pb, intr, side, fix0, params=None):
 
 def _check_rows(rows, rows_o):
     assert len(rows) == len(rows_o)
+    g0 = rows_o[0]["gradient_max_norm"]   # near convergence the gradient is a difference of large terms: scale by row 0
     for a, b in zip(rows, rows_o):
         assert a["iteration"] == b["iteration"]
         assert a["step_is_successful"] == b["step_is_successful"] and a["step_is_valid"] == b["step_is_valid"]
         assert H.rel(a["cost"], b["cost"]) <= COST_RTOL, (a, b)
         assert H.rel(a["trust_region_radius"], b["trust_region_radius"]) <= 1e-8
         if b["gradient_max_norm"] > 0:
-            assert H.rel(a["gradient_max_norm"], b["gradient_max_norm"]) <= 1e-7
+            assert abs(a["gradient_max_norm"] - b["gradient_max_norm"]) <= 1e-7 * b["gradient_max_norm"] + 1e-9 * g0
         if b["step_norm"] > 0:
             assert H.rel(a["step_norm"], b["step_norm"]) <= 1e-6
 
@@ -168,23 +169,25 @@ def test_solve_synthetic_vs_oracle(gpu, oracle, name):
         assert np.abs(x - xo).max() < POSE_ATOL
 
 
-def test_rejected_steps_follow_the_same_schedule(gpu, oracle):
-    # a huge initial radius (almost undamped Gauss-Newton) from a poor start forces rejected steps
-    pr = S.marker_rig_a(6, 8, 15, 21, perturb=(0.2, 0.06, 0.04))
-    opt_g, opt_o = cuda.default_options(), oracle.default_options()
-    for o in (opt_g, opt_o):
-        o.initial_trust_region_radius = 1e12
-        o.max_num_iterations = 30
-    gpu.set_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr)
-    gpu.set_parameters(pr.params)
-    s, rows = gpu.solve(opt_g)
-    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o)
-    assert so.num_unsuccessful_steps > 0, "test problem no longer produces a rejected step"
+@pytest.mark.parametrize("seed,perturb", [(24, (0.25, 0.07)), (27, (0.3, 0.08))])
+def test_rejected_steps_follow_the_same_schedule(gpu, oracle, seed, perturb):
+    # a poor start makes LM overshoot: rejected steps (2 resp. 3 of them), radius halving / quartering, then recovery.
+    # The cases are picked so that the oracle's dense-normal and Schur paths agree to 1e-11 on every row, i.e. the
+    # schedule is a property of the algorithm and not of round-off.
+    pr = S.marker_rig_b(4, 8, 15, seed, perturb=perturb)
+    pb = F.ModelBFile(pr.n_time, pr.n_cam, pr.n_marker, pr.counts, pr.time_idx, pr.cam_idx, pr.marker_idx, pr.obs8, pr.params)
+    _set_b(gpu, pb, pr.intr, pr.marker_side, 1)
+    s, rows = gpu.solve()
+    x = gpu.get_parameters()
+    xo, so, rows_o = oracle.solve_model_b(pb, pr.intr, pr.marker_side, 1)
+    assert so.num_unsuccessful_steps >= 2, "test problem no longer produces rejected steps"
     assert s.num_unsuccessful_steps == so.num_unsuccessful_steps and s.num_iterations == so.num_iterations
+    assert (s.termination_type, s.termination_reason) == (so.termination_type, so.termination_reason)
     for a, b in zip(rows, rows_o):
         assert a["step_is_successful"] == b["step_is_successful"]
-        assert H.rel(a["trust_region_radius"], b["trust_region_radius"]) <= 1e-6
-        assert H.rel(a["cost"], b["cost"]) <= 1e-8
+        assert H.rel(a["trust_region_radius"], b["trust_region_radius"]) <= 1e-8
+        assert H.rel(a["cost"], b["cost"]) <= 1e-9
+    assert np.abs(x - xo).max() < POSE_ATOL
 
 
 def test_max_iterations_and_determinism(gpu):
