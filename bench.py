@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/s of the bundle-adjustment hot path on B200 (and the CPU reference arm beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W     (one rank per GPU)
+
+A "step" is ONE Levenberg-Marquardt iteration (one row of Ceres' progress table: Schur elimination of the
+current Jacobian, reduced-camera-system solve, back-substitution, candidate cost, accept/reject, and on
+acceptance the residual + Jacobian evaluation at the new point) on the synthetic problem named by
+--workload.  A bundle-adjustment solve only runs 5-10 such iterations before it converges, so the K timed
+steps are run as ceil(K / ITERS_PER_SOLVE) solves that each restart from the same initial guess (a
+device-to-device restore); the initial evaluation every solve starts with (TrustRegionMinimizer's iteration
+zero) IS inside the timed region but is not counted as a step, so `value` under-reports rather than
+over-reports.
+
+  value   K / device time of those solves, problem resident in HBM (CUDA events on the solve stream, max over ranks)
+  e2e     the same K steps through the public C ABI from HOST buffers: ba_cuda_set_model_a (observations,
+          indices -> HBM, structure build) + ba_cuda_set_parameters + ba_cuda_solve + ba_cuda_get_parameters,
+          all inside the timed region
+  roofline      the kernel with the largest share of device time: algorithmic bytes / its
+                CUDA-event duration, against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (oracle/, a restatement of the Ceres 1.14 path the reference runs) on the host cores
+
+--impl reference times that CPU oracle alone, with all host threads, on the same workload/metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ITERS_PER_SOLVE = 5
+
+# name -> (description, model, generator kwargs, rcs solver)
+WORKLOADS = {
+    "cfg3a": dict(desc="large rig, Model A reading: 8 cameras x 100 markers x 1000 frames = 400k corner points, 3.2M observations",
+                  kind="rig_a", args=(8, 100, 1000, 0xBA03)),
+    "cfg4": dict(desc="BAL-shaped synthetic: 1000 cameras x 1M points x 5M observations (window 20)",
+                 kind="bal", args=(1000, 1000000, 5, 20, 0xBA04)),
+    "cfg5": dict(desc="BAL-shaped synthetic: 10000 cameras x 4M points x ~30M observations (Poisson 2..16 per point, window 30)",
+                 kind="bal", args=(10000, 4000000, 7.5, 30, 0xBA05), kwargs=dict(variable_degree=True)),
+    "small": dict(desc="smoke-sized BAL-shaped synthetic: 50 cameras x 20k points x 100k observations",
+                  kind="bal", args=(50, 20000, 5, 12, 0xBA00)),
+}
+DEFAULT_WORKLOAD = "cfg3a"
+
+
+def make_workload(name):
+    from realsensecalibration_b200 import synthetic as S
+    w = WORKLOADS[name]
+    if w["kind"] == "rig_a":
+        return S.marker_rig_a(*w["args"])
+    return S.bal_like(*w["args"], **w.get("kwargs", {}))
+
+
+def shard_model_a(pr, rank, world):
+    """Points (with all their observations) are block-distributed over ranks, balanced by observation count;
+    cameras are replicated.  Returns the rank-local arrays."""
+    from realsensecalibration_b200 import cuda
+    if world == 1:
+        return pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.params
+    deg = np.bincount(pr.pt_idx, minlength=pr.n_pt).astype(np.int64)
+    rng = cuda.shard_blocks(deg, world)
+    lo, hi = int(rng[rank]), int(rng[rank + 1])
+    sel = (pr.pt_idx >= lo) & (pr.pt_idx < hi)
+    cams = pr.params[:6 * pr.n_cam]
+    pts = pr.params[6 * pr.n_cam:].reshape(-1, 3)[lo:hi]
+    return hi - lo, pr.cam_idx[sel], (pr.pt_idx[sel] - lo).astype(np.int32), pr.obs_xy[sel], np.concatenate([cams, pts.ravel()])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [l for t, l in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for _, l in self.lines]
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def bench_options(cuda, profile):
+    o = cuda.default_options()
+    o.max_num_iterations = ITERS_PER_SOLVE
+    o.function_tolerance = 0.0      # never stop early: exactly ITERS_PER_SOLVE rows per solve
+    o.parameter_tolerance = 0.0
+    o.gradient_tolerance = 0.0
+    o.profile_kernels = 1 if profile else 0
+    return o
+
+
+def run_steps(P, opts, k):
+    """k LM iterations as solves of ITERS_PER_SOLVE, each restarting from the saved initial guess."""
+    done = 0
+    while done < k:
+        n = min(ITERS_PER_SOLVE, k - done)
+        P.restore_parameters()
+        P.solve_begin(opts)
+        P.solve_iterate(n)
+        done += n
+    return P.solve_end()
+
+
+def oracle_steps(pr, k, threads, linear_solver):
+    """The reference arm: the CPU oracle on the same workload, same restart rule; returns (seconds, rows)."""
+    from oracle import oracle_py as O
+    o = O.default_options()
+    o.function_tolerance = 0.0; o.parameter_tolerance = 0.0; o.gradient_tolerance = 0.0
+    done, t, rows = 0, 0.0, []
+    while done < k:
+        n = min(ITERS_PER_SOLVE, k - done)
+        o.max_num_iterations = n
+        t0 = time.perf_counter()
+        _, s, rows = O.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=o,
+                                     linear_solver=linear_solver, n_threads=threads)
+        t += time.perf_counter() - t0
+        done += n
+    return t, rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = a.steps, max(a.warmup, 0)
+    metric, unit = "LM iterations/sec", "it/s"
+    wl = WORKLOADS[a.workload]
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle import oracle_py as O
+        pr = make_workload(a.workload)
+        threads = O.max_threads()
+        if W > 0:
+            oracle_steps(pr, min(W, 1), threads, O.SCHUR_DENSE if pr.n_cam <= 64 else O.SCHUR_PCG)
+        secs, rows = oracle_steps(pr, K, threads, O.SCHUR_DENSE if pr.n_cam <= 64 else O.SCHUR_PCG)
+        v = K / secs
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": a.workload, "description": wl["desc"], "iters_per_solve": ITERS_PER_SOLVE},
+            "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port",
+                             "sample": "full workload, %d LM iterations in solves of %d (problem construction + initial evaluation "
+                                       "of each solve included)" % (K, ITERS_PER_SOLVE)},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "jacobian_mobs_per_sec": None, "gpu_launches": 0}))
+        return 0
+
+    import torch
+    from realsensecalibration_b200 import cuda
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pr = make_workload(a.workload)
+    n_pt_l, cam_l, pt_l, obs_l, par_l = shard_model_a(pr, rank, world)
+    stream = torch.cuda.Stream()
+    P = cuda.Problem(local_rank)
+    P.set_stream(stream.cuda_stream)
+    if world > 1:
+        ids = [cuda.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        P.comm_init(rank, world, ids[0])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident measurement ("value") ----------------------------------------------------
+    P.set_model_a(pr.n_cam, n_pt_l, cam_l, pt_l, obs_l, pr.intr)
+    P.set_parameters(par_l)
+    P.save_parameters()
+    opts = bench_options(cuda, profile=True)
+    if W > 0:
+        run_steps(P, opts, W)
+    barrier()
+    P.reset_stats()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        summary, rows = run_steps(P, opts, K)
+        e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    stats = P.kernel_stats()
+    launches = P.num_launches()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = K / (ms * 1e-3)
+
+    # residual+Jacobian throughput (the other half of BASELINE.json's metric), from the kernel's own events
+    k1 = next((s for s in stats if s["name"] == "k1_residual_jacobian"), None)
+    jac_mobs = None
+    if k1 and k1["total_ms"] > 0:
+        jac_mobs = pr.n_obs / 1e6 / (k1["total_ms"] / k1["launches"] * 1e-3)   # whole job: shards run concurrently
+
+    # roofline of the dominant kernel
+    peak, peak_src = peaks()
+    timed = [s for s in stats if s["total_ms"] > 0 and s["algorithmic_bytes_per_launch"] > 0]
+    roofline = None
+    if timed:
+        top = max(timed, key=lambda s: s["total_ms"])
+        avg_s = top["total_ms"] / top["launches"] * 1e-3
+        ach = top["algorithmic_bytes_per_launch"] / avg_s / 1e9
+        roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_s * 1e3, "launches": top["launches"],
+                    "share_of_step": top["total_ms"] / ms,
+                    "all_kernels": [{"name": s["name"], "launches": s["launches"], "ms_per_launch": s["total_ms"] / s["launches"],
+                                     "share": s["total_ms"] / ms,
+                                     "gbs": (s["algorithmic_bytes_per_launch"] / (s["total_ms"] / s["launches"] * 1e-3) / 1e9)
+                                     if s["total_ms"] > 0 and s["algorithmic_bytes_per_launch"] > 0 else None} for s in stats]}
+
+    # ---- end to end through the public C ABI from host buffers ("e2e") ------------------------------
+    e2e = None
+    if not a.no_e2e:
+        opts_e = bench_options(cuda, profile=False)
+        h2d = cam_l.nbytes + pt_l.nbytes + np.asarray(obs_l).nbytes + pr.intr.nbytes + par_l.nbytes
+        d2h = par_l.nbytes
+        def e2e_solves(k):
+            done = 0
+            x = None
+            while done < k:
+                n = min(ITERS_PER_SOLVE, k - done)
+                opts_e.max_num_iterations = n
+                P.set_model_a(pr.n_cam, n_pt_l, cam_l, pt_l, obs_l, pr.intr)
+                P.set_parameters(par_l)
+                P.solve(opts_e)
+                x = P.get_parameters()
+                done += n
+            return x
+        e2e_solves(min(W, ITERS_PER_SOLVE) or 1)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_solves(K)
+        barrier()
+        secs = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([secs], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        n_solves = (K + ITERS_PER_SOLVE - 1) // ITERS_PER_SOLVE
+        e2e = {"value": K / secs, "unit": unit, "h2d_bytes_per_step": int(h2d * n_solves / K), "d2h_bytes_per_step": int(d2h * n_solves / K),
+               "ms_per_step": 1e3 * secs / K, "timed": "host wall clock around set_model_a + set_parameters + solve + get_parameters, max over ranks"}
+
+    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import oracle_py as O
+        threads = O.max_threads()
+        kc = min(K, ITERS_PER_SOLVE)
+        secs, _ = oracle_steps(pr, kc, threads, O.SCHUR_DENSE if pr.n_cam <= 64 else O.SCHUR_PCG)
+        cpu = {"value": kc / secs, "unit": unit, "cores": threads, "kind": "port",
+               "sample": "full workload, one solve of %d LM iterations (problem construction + initial evaluation included), "
+                         "oracle/ba_oracle.cpp with OpenMP" % kc}
+
+    if rank == 0:
+        out = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": a.workload, "description": wl["desc"], "n_cameras": pr.n_cam, "n_points": pr.n_pt, "n_obs": pr.n_obs,
+                       "iters_per_solve": ITERS_PER_SOLVE, "parallelism": "points sharded over %d rank(s), cameras replicated" % world,
+                       "l2": "working set (Jacobian %.0f MB per rank) exceeds the 126 MB L2; no explicit flush" % (pr.n_obs * 160 / 1e6 / world),
+                       "rcs_solver": {1: "dense_cholesky", 2: "pcg"}.get(int(summary.rcs_solver_used), "?"), "rcs_dim": int(summary.rcs_dim)},
+            "jacobian_mobs_per_sec": jac_mobs, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "final_cost_last_solve": float(summary.final_cost),
+            "device_ms": {"jacobian": summary.ms_jacobian, "schur": summary.ms_schur, "rcs_solve": summary.ms_rcs_solve,
+                          "update": summary.ms_update, "cost": summary.ms_cost, "collective": summary.ms_collective, "of_last_solve": True},
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -89,6 +89,9 @@ typedef struct ba_cuda_options {
   int32_t pcg_min_iterations;                /* 0 */
   int32_t pcg_residual_reset_period;         /* 10 */
   int32_t minimizer_progress_to_stdout;      /* 0 */
+  int32_t profile_kernels;                   /* 0; 1 = CUDA-event timing of every kernel family member
+                                                (ba_cuda_get_kernel_stats), costs ~2 us of host time per launch */
+  int32_t reserved0;                         /* 0 */
   double initial_trust_region_radius;        /* 1e4 */
   double max_trust_region_radius;            /* 1e16 */
   double min_trust_region_radius;            /* 1e-32 */
@@ -151,6 +154,24 @@ void ba_cuda_destroy(ba_cuda_problem* p);
 const char* ba_cuda_last_error(void); /* thread-local message of the last failure */
 int ba_cuda_device_count(void);
 
+/* All work of a problem is enqueued on one CUDA stream: by default a private non-blocking stream; a caller
+ * that wants to order / time the work with its own events passes its cudaStream_t here (NULL restores the
+ * private stream).  Must not be called while a solve is in flight. */
+int ba_cuda_set_stream(ba_cuda_problem* p, void* cuda_stream);
+
+/* Per-kernel accounting since the last ba_cuda_reset_stats(): number of launches of this library's own
+ * kernels (always counted) and, with options.profile_kernels = 1, CUDA-event device time per kernel together
+ * with the ALGORITHMIC bytes one launch has to move ("kernels and rooflines"). */
+typedef struct ba_cuda_kernel_stat {
+  char name[32];
+  int64_t launches;
+  double total_ms;                     /* 0 unless profile_kernels was set */
+  double algorithmic_bytes_per_launch; /* compulsory HBM traffic of one launch on the current problem */
+} ba_cuda_kernel_stat;
+int ba_cuda_get_kernel_stats(ba_cuda_problem* p, ba_cuda_kernel_stat* stats, int cap); /* returns the count */
+int64_t ba_cuda_num_launches(const ba_cuda_problem* p);
+void ba_cuda_reset_stats(ba_cuda_problem* p);
+
 /* ---- multi-GPU plumbing (NCCL; rendezvous bytes travel by the caller's own
  *      channel, e.g. torch.distributed broadcast) ------------------------------ */
 #define BA_CUDA_UNIQUE_ID_BYTES 128
@@ -197,9 +218,20 @@ int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32
 int ba_cuda_set_parameters(ba_cuda_problem* p, const double* params, int64_t n);
 int ba_cuda_get_parameters(ba_cuda_problem* p, double* params, int64_t n);
 int64_t ba_cuda_num_parameters(const ba_cuda_problem* p);
+/* Device-side snapshot / rollback of the whole parameter vector (no host traffic): the in-HBM analogue of a
+ * caller keeping a copy of BALProblem::parameters_ to re-run ceres::Solve from the same start. */
+int ba_cuda_save_parameters(ba_cuda_problem* p);
+int ba_cuda_restore_parameters(ba_cuda_problem* p);
 
 /* ---- the hot path: replaces ceres::Solve (bundle_adjustment_manager.cpp:94) -- */
 int ba_cuda_solve(ba_cuda_problem* p, const ba_cuda_options* options, ba_cuda_summary* summary);
+/* The same solve in three calls, so that a caller (bench.py, an interactive tool) can run the LM loop a few
+ * iterations at a time: begin = TrustRegionMinimizer's IterationZero; iterate = up to max_new_iterations more
+ * rows of the progress table (*finished = 1 once a termination rule fired); end = the summary.
+ * ba_cuda_solve(p,o,s) == begin(p,o); iterate(p, INT32_MAX, &f); end(p,s). */
+int ba_cuda_solve_begin(ba_cuda_problem* p, const ba_cuda_options* options);
+int ba_cuda_solve_iterate(ba_cuda_problem* p, int32_t max_new_iterations, int32_t* finished);
+int ba_cuda_solve_end(ba_cuda_problem* p, ba_cuda_summary* summary);
 /* rows of the progress table; returns the number of rows available (>= 0) */
 int ba_cuda_get_iterations(ba_cuda_problem* p, ba_cuda_iteration* rows, int cap);
 

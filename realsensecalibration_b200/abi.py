@@ -20,6 +20,8 @@ class Options(C.Structure):
         ("pcg_min_iterations", C.c_int32),
         ("pcg_residual_reset_period", C.c_int32),
         ("minimizer_progress_to_stdout", C.c_int32),
+        ("profile_kernels", C.c_int32),
+        ("reserved0", C.c_int32),
         ("initial_trust_region_radius", C.c_double),
         ("max_trust_region_radius", C.c_double),
         ("min_trust_region_radius", C.c_double),
@@ -52,6 +54,19 @@ class Iteration(C.Structure):
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class KernelStat(C.Structure):
+    _fields_ = [
+        ("name", C.c_char * 32),
+        ("launches", C.c_int64),
+        ("total_ms", C.c_double),
+        ("algorithmic_bytes_per_launch", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {"name": self.name.decode(), "launches": int(self.launches), "total_ms": float(self.total_ms),
+                "algorithmic_bytes_per_launch": float(self.algorithmic_bytes_per_launch)}
 
 
 class Summary(C.Structure):

@@ -58,11 +58,28 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 
 enum Scal { S_COST = 0, S_G2E, S_GMAXE, S_CAND, S_MCC, S_XE2, S_DE2, S_XF2, S_DF2, S_GMAXF, S_G2F, S_RADIUS, S_COUNT = 16 };
 enum Family { F_JAC = 0, F_SCHUR, F_SOLVE, F_UPDATE, F_COST, F_COLL, F_COUNT };
+// one entry per kernel (family member) of the solve path; names are what ba_cuda_get_kernel_stats() reports
+enum KT {
+  KT_TABLES = 0, KT_JAC, KT_COST, KT_FOBS, KT_EM, KT_INCW, KT_DOBS, KT_ECHOL, KT_INCY, KT_FINC, KT_PAIRS, KT_SEGFIN,
+  KT_ASSEMBLE, KT_RCS, KT_BACKSUB, KT_MODELCOST, KT_CANDIDATE, KT_GRADNORM, KT_FOLD, KT_MISC, KT_COUNT
+};
+const char* const kKtName[KT_COUNT] = {
+  "k1_tables", "k1_residual_jacobian", "k5_cost", "k2_fobs_partial", "k2_e_normal", "k2_inc_w", "k2_dobs_partial",
+  "k2_e_cholesky", "k2_inc_y", "k2_finc_partial", "k2_pairs_partial", "k2_seg_final", "k2_assemble", "k3_rcs_solve",
+  "k4_backsub", "k4_model_cost", "k4_candidate", "k4_gradient_norm", "fold_partials", "misc"};
 }  // namespace
+
+struct LmState {  // TrustRegionMinimizer's loop variables, kept between ba_cuda_solve_iterate() calls
+  ba_cuda_options opt;
+  ba_cuda_summary Z;
+  double radius = 0.0, decrease_factor = 2.0, x_cost = 0.0, gmax = 0.0, gnorm = 0.0, t_start = 0.0;
+  int num_invalid = 0;
+  bool began = false, go = false;
+};
 
 struct ba_cuda_problem {
   int device = 0;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr, own_st = nullptr;
   int model = -1;  // 0 = A, 1 = B
   int32_t n_cam = 0, n_time = 0, n_marker = 0;
   int64_t n_pt = 0, n_params = 0;
@@ -74,7 +91,7 @@ struct ba_cuda_problem {
   DVec<double> obs8, intr_f;
   DVec<int32_t> ob_cam, ob_marker;
   // parameters (x), candidate (xc), Jacobi scaling, block tables
-  DVec<double> xf, xe, xf_c, xe_c, sf, se, tab_f, tab_e, tabc_f, tabc_e;
+  DVec<double> xf, xe, xf_c, xe_c, xf_s, xe_s, sf, se, tab_f, tab_e, tabc_f, tabc_e;  // _s: saved snapshot
   // Jacobian and Schur workspace
   DVec<double> RES, JE, JF0, JF1, ME, HG, Wt, Lb, zb, Yt, vb, Pacc, Qacc, Sd, rhs, yf, ye;
   DVec<double> part_fobs, part_finc, part_pairs, part_dobs, bp0, bp1, scal;
@@ -83,6 +100,7 @@ struct ba_cuda_problem {
   int* h_status = nullptr;   // pinned
   bool params_set = false;
   std::vector<ba_cuda_iteration> rows;
+  LmState lm;
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -92,6 +110,14 @@ struct ba_cuda_problem {
   bool fam_open[F_COUNT] = {};
   cudaEvent_t k0 = nullptr, k1 = nullptr;
   float last_kernel_ms = 0.f;
+  // per-kernel accounting
+  bool profile = false;
+  int64_t kt_launches[KT_COUNT] = {};
+  double kt_ms[KT_COUNT] = {};
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
+  struct Pending { int kt; size_t e0, e1; };
+  std::vector<Pending> pending;
   int64_t n_rcs() const { return 6 * S.nf; }
   double* vsum() { return Sd.p + n_rcs() * n_rcs(); }  // tail of the dense RCS buffer: one collective covers both
 };
@@ -101,6 +127,42 @@ namespace {
 int use_device(ba_cuda_problem* p) {
   BA_CUDA_TRY(cudaSetDevice(p->device));
   return BA_OK;
+}
+
+// ---- per-kernel accounting -------------------------------------------------------------
+cudaEvent_t pool_event(ba_cuda_problem* p, size_t* idx) {
+  if (p->ev_next == p->ev_pool.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    p->ev_pool.push_back(e);
+  }
+  *idx = p->ev_next++;
+  return p->ev_pool[*idx];
+}
+struct LaunchScope {  // counts the launch; with profiling on, brackets it with two pooled events
+  ba_cuda_problem* p; int kt; size_t e0 = 0, e1 = 0;
+  LaunchScope(ba_cuda_problem* p_, int kt_) : p(p_), kt(kt_) {
+    ++p->kt_launches[kt];
+    if (p->profile) cudaEventRecord(pool_event(p, &e0), p->st);
+  }
+  ~LaunchScope() {
+    if (p->profile) { cudaEventRecord(pool_event(p, &e1), p->st); p->pending.push_back({kt, e0, e1}); }
+  }
+};
+// BA_LAUNCH(p, KT_X, (kernel<T...>), grid, block, smem, args...)
+#define BA_LAUNCH(p, kt, kern, grid, block, smem, ...)            \
+  do {                                                            \
+    LaunchScope scope__((p), (kt));                               \
+    kern<<<(grid), (block), (smem), (p)->st>>>(__VA_ARGS__);      \
+  } while (0)
+
+void kt_collect(ba_cuda_problem* p) {  // call after a stream synchronize
+  for (const auto& q : p->pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->ev_pool[q.e0], p->ev_pool[q.e1]) == cudaSuccess) p->kt_ms[q.kt] += ms;
+  }
+  p->pending.clear();
+  p->ev_next = 0;
 }
 
 // ---- family timers: one event pair per family, accumulated at the iteration's host sync ----
@@ -113,10 +175,11 @@ void fam_collect(ba_cuda_problem* p) {  // call after a stream synchronize
       if (cudaEventElapsedTime(&ms, p->ev[f][0], p->ev[f][1]) == cudaSuccess) p->fam_ms[f] += ms;
       p->fam_open[f] = false;
     }
+  kt_collect(p);
 }
 
 int fold(ba_cuda_problem* p, const double* partial, int n, int slot, bool is_max = false) {
-  k_fold_partials<<<1, 1024, 0, p->st>>>(partial, n, p->scal.p, slot, is_max ? 1 : 0);
+  BA_LAUNCH(p, KT_FOLD, k_fold_partials, 1, 1024, 0, partial, n, p->scal.p, slot, is_max ? 1 : 0);
   BA_CUDA_TRY(cudaGetLastError());
   return BA_OK;
 }
@@ -132,11 +195,11 @@ int build_tables(ba_cuda_problem* p, bool candidate) {
   const Structure& S = p->S;
   const double* xf = candidate ? p->xf_c.p : p->xf.p;
   double* tf = candidate ? p->tabc_f.p : p->tab_f.p;
-  k_tables<<<grid_for(S.nf, 128), 128, 0, p->st>>>(xf, p->intr_f.p, p->sf.p, S.nf, tf);
+  BA_LAUNCH(p, KT_TABLES, k_tables, grid_for(S.nf, 128), 128, 0, xf, p->intr_f.p, p->sf.p, S.nf, tf);
   if (p->model == 1) {
     const double* xe = candidate ? p->xe_c.p : p->xe.p;
     double* te = candidate ? p->tabc_e.p : p->tab_e.p;
-    k_tables<<<grid_for(S.ne, 128), 128, 0, p->st>>>(xe, nullptr, p->se.p, S.ne, te);
+    BA_LAUNCH(p, KT_TABLES, k_tables, grid_for(S.ne, 128), 128, 0, xe, nullptr, p->se.p, S.ne, te);
   }
   BA_CUDA_TRY(cudaGetLastError());
   return BA_OK;
@@ -149,12 +212,12 @@ int run_jacobian(ba_cuda_problem* p) {
   int grid;
   if (p->model == 0) {
     grid = (int)grid_for(S.nb, 256);
-    k_jac_a<<<grid, 256, 0, p->st>>>(S.nb, S.ob_e.p, S.ob_f0.p, p->uv.p, p->tab_f.p, p->xe.p, p->se.p, p->RES.p, p->JE.p,
-                                     p->JF0.p, p->bp0.p);
+    BA_LAUNCH(p, KT_JAC, k_jac_a, grid, 256, 0, S.nb, S.ob_e.p, S.ob_f0.p, p->uv.p, p->tab_f.p, p->xe.p, p->se.p, p->RES.p,
+              p->JE.p, p->JF0.p, p->bp0.p);
   } else {
     grid = (int)grid_for(S.nb * 4, 128);
-    k_jac_b<<<grid, 128, 0, p->st>>>(S.nb, S.ob_e.p, S.ob_f0.p, S.ob_f1.p, p->ob_cam.p, p->obs8.p, p->tab_f.p, p->tab_e.p,
-                                     p->half_side, p->RES.p, p->JE.p, p->JF0.p, p->JF1.p, p->bp0.p);
+    BA_LAUNCH(p, KT_JAC, k_jac_b, grid, 128, 0, S.nb, S.ob_e.p, S.ob_f0.p, S.ob_f1.p, p->ob_cam.p, p->obs8.p, p->tab_f.p,
+              p->tab_e.p, p->half_side, p->RES.p, p->JE.p, p->JF0.p, p->JF1.p, p->bp0.p);
   }
   BA_CUDA_TRY(cudaGetLastError());
   return fold(p, p->bp0.p, grid, S_COST);
@@ -167,11 +230,11 @@ int run_cost_candidate(ba_cuda_problem* p) {
   int grid;
   if (p->model == 0) {
     grid = (int)grid_for(S.nb, 256);
-    k_cost_a<<<grid, 256, 0, p->st>>>(S.nb, S.ob_e.p, S.ob_f0.p, p->uv.p, p->tabc_f.p, p->xe_c.p, p->bp0.p);
+    BA_LAUNCH(p, KT_COST, k_cost_a, grid, 256, 0, S.nb, S.ob_e.p, S.ob_f0.p, p->uv.p, p->tabc_f.p, p->xe_c.p, p->bp0.p);
   } else {
     grid = (int)grid_for(S.nb * 4, 128);
-    k_cost_b<<<grid, 128, 0, p->st>>>(S.nb, S.ob_e.p, S.ob_f0.p, S.ob_f1.p, p->ob_cam.p, p->obs8.p, p->tabc_f.p, p->tabc_e.p,
-                                      p->half_side, p->bp0.p);
+    BA_LAUNCH(p, KT_COST, k_cost_b, grid, 128, 0, S.nb, S.ob_e.p, S.ob_f0.p, S.ob_f1.p, p->ob_cam.p, p->obs8.p, p->tabc_f.p,
+              p->tabc_e.p, p->half_side, p->bp0.p);
   }
   BA_CUDA_TRY(cudaGetLastError());
   return fold(p, p->bp0.p, grid, S_CAND);
@@ -182,21 +245,20 @@ int run_cost_candidate(ba_cuda_problem* p) {
 template <int RD, int DE, int GE>
 int run_normal_parts(ba_cuda_problem* p) {
   const Structure& S = p->S;
-  constexpr int NVE = DE * (DE + 1) / 2 + DE;
   if (S.ch_fobs.n > 0)
-    k_fobs_partial<RD><<<grid_for(S.ch_fobs.n, 4), 128, 0, p->st>>>(S.ch_fobs.n, S.ch_fobs.ch, S.ch_fobs.seg.p, S.ch_fobs.begin.p,
-                                                                    S.fobs_ptr.p, S.fobs.p, p->RES.p, p->JF0.p, p->JF1.p, p->part_fobs.p);
-  k_seg_final<NV_F><<<grid_for(S.nf, 4), 128, 0, p->st>>>((int)S.nf, S.ch_fobs.seg_first.p, p->part_fobs.p, p->HG.p);
-  k_e_M<RD, DE, GE><<<grid_for(S.ne * GE, 128), 128, 0, p->st>>>(S.ne, S.e_ptr.p, p->RES.p, p->JE.p, p->ME.p);
+    BA_LAUNCH(p, KT_FOBS, (k_fobs_partial<RD>), grid_for(S.ch_fobs.n, 4), 128, 0, S.ch_fobs.n, S.ch_fobs.ch, S.ch_fobs.seg.p,
+              S.ch_fobs.begin.p, S.fobs_ptr.p, S.fobs.p, p->RES.p, p->JF0.p, p->JF1.p, p->part_fobs.p);
+  BA_LAUNCH(p, KT_SEGFIN, (k_seg_final<NV_F>), grid_for(S.nf, 4), 128, 0, (int)S.nf, S.ch_fobs.seg_first.p, p->part_fobs.p, p->HG.p);
+  BA_LAUNCH(p, KT_EM, (k_e_M<RD, DE, GE>), grid_for(S.ne * GE, 128), 128, 0, S.ne, S.e_ptr.p, p->RES.p, p->JE.p, p->ME.p);
   if (p->model == 1) {
-    k_inc_W<RD><<<grid_for(S.ninc * 8, 128), 128, 0, p->st>>>(S.ninc, S.incobs_ptr.p, S.incobs.p, p->JE.p, p->JF0.p, p->JF1.p, p->Wt.p);
+    BA_LAUNCH(p, KT_INCW, (k_inc_W<RD>), grid_for(S.ninc * 8, 128), 128, 0, S.ninc, S.incobs_ptr.p, S.incobs.p, p->JE.p, p->JF0.p,
+              p->JF1.p, p->Wt.p);
     if (S.ch_dobs.n > 0)
-      k_dobs_partial<RD><<<grid_for(S.ch_dobs.n, 4), 128, 0, p->st>>>(S.ch_dobs.n, S.ch_dobs.ch, S.ch_dobs.seg.p, S.ch_dobs.begin.p,
-                                                                      S.dobs_ptr.p, S.dobs.p, p->JF0.p, p->JF1.p, p->part_dobs.p);
-    k_seg_final<36><<<grid_for(S.ndest, 4), 128, 0, p->st>>>(S.ndest, S.ch_dobs.seg_first.p, p->part_dobs.p, p->Qacc.p);
+      BA_LAUNCH(p, KT_DOBS, (k_dobs_partial<RD>), grid_for(S.ch_dobs.n, 4), 128, 0, S.ch_dobs.n, S.ch_dobs.ch, S.ch_dobs.seg.p,
+                S.ch_dobs.begin.p, S.dobs_ptr.p, S.dobs.p, p->JF0.p, p->JF1.p, p->part_dobs.p);
+    BA_LAUNCH(p, KT_SEGFIN, (k_seg_final<36>), grid_for(S.ndest, 4), 128, 0, S.ndest, S.ch_dobs.seg_first.p, p->part_dobs.p, p->Qacc.p);
   }
   BA_CUDA_TRY(cudaGetLastError());
-  (void)NVE;
   return BA_OK;
 }
 
@@ -205,10 +267,10 @@ int run_gradient_norms(ba_cuda_problem* p) {
   const Structure& S = p->S;
   constexpr int NU = DE * (DE + 1) / 2;
   const int ge = (int)grid_for(S.ne * DE, 256), gf = (int)grid_for(S.nf * 6, 256);
-  k_gradient_norm<DE, NU + DE, NU><<<ge, 256, 0, p->st>>>(S.ne, S.e_ptr.p, p->xe.p, p->se.p, p->ME.p, p->bp0.p, p->bp1.p);
+  BA_LAUNCH(p, KT_GRADNORM, (k_gradient_norm<DE, NU + DE, NU>), ge, 256, 0, S.ne, S.e_ptr.p, p->xe.p, p->se.p, p->ME.p, p->bp0.p, p->bp1.p);
   BA_TRY(fold(p, p->bp0.p, ge, S_GMAXE, true));
   BA_TRY(fold(p, p->bp1.p, ge, S_G2E));
-  k_gradient_norm<6, NV_F, 21><<<gf, 256, 0, p->st>>>(S.nf, S.fobs_ptr.p, p->xf.p, p->sf.p, p->HG.p, p->bp0.p, p->bp1.p);
+  BA_LAUNCH(p, KT_GRADNORM, (k_gradient_norm<6, NV_F, 21>), gf, 256, 0, S.nf, S.fobs_ptr.p, p->xf.p, p->sf.p, p->HG.p, p->bp0.p, p->bp1.p);
   BA_TRY(fold(p, p->bp0.p, gf, S_GMAXF, true));
   BA_TRY(fold(p, p->bp1.p, gf, S_G2F));
   BA_CUDA_TRY(cudaGetLastError());
@@ -222,8 +284,8 @@ int eval_gradient_and_jacobian(ba_cuda_problem* p, bool first, bool jacobi_scali
   const Structure& S = p->S;
   fam_begin(p, F_JAC);
   if (first) {
-    k_fill<<<grid_for(S.ne * DE, 256), 256, 0, p->st>>>(p->se.p, S.ne * DE, 1.0);
-    k_fill<<<grid_for(S.nf * 6, 256), 256, 0, p->st>>>(p->sf.p, S.nf * 6, 1.0);
+    BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.ne * DE, 256), 256, 0, p->se.p, S.ne * DE, 1.0);
+    BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.nf * 6, 256), 256, 0, p->sf.p, S.nf * 6, 1.0);
   }
   BA_TRY(run_jacobian(p));
   fam_end(p, F_JAC);
@@ -232,8 +294,8 @@ int eval_gradient_and_jacobian(ba_cuda_problem* p, bool first, bool jacobi_scali
   if (first && jacobi_scaling) {
     BA_TRY(allreduce(p, p->HG.p, S.nf * NV_F, kNcclSum));  // column norms of the kept blocks are global sums
     constexpr int NU = DE * (DE + 1) / 2;
-    k_jacobi_scale<DE, NU + DE><<<grid_for(S.ne * DE, 256), 256, 0, p->st>>>(S.ne, p->ME.p, p->se.p);
-    k_jacobi_scale<6, NV_F><<<grid_for(S.nf * 6, 256), 256, 0, p->st>>>(S.nf, p->HG.p, p->sf.p);
+    BA_LAUNCH(p, KT_MISC, (k_jacobi_scale<DE, NU + DE>), grid_for(S.ne * DE, 256), 256, 0, S.ne, p->ME.p, p->se.p);
+    BA_LAUNCH(p, KT_MISC, (k_jacobi_scale<6, NV_F>), grid_for(S.nf * 6, 256), 256, 0, S.nf, p->HG.p, p->sf.p);
     BA_TRY(run_jacobian(p));  // same residuals, Jacobian now column scaled
     BA_TRY((run_normal_parts<RD, DE, GE>(p)));
   }
@@ -260,21 +322,24 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   const double* radius = p->scal.p + S_RADIUS;
   fam_begin(p, F_SCHUR);
   BA_CUDA_TRY(cudaMemsetAsync(p->status.p, 0, sizeof(int), p->st));
-  k_e_chol<DE><<<grid_for(S.ne, 256), 256, 0, p->st>>>(S.ne, p->ME.p, radius, opt.min_lm_diagonal, opt.max_lm_diagonal, p->Lb.p, p->zb.p, p->status.p);
+  BA_LAUNCH(p, KT_ECHOL, (k_e_chol<DE>), grid_for(S.ne, 256), 256, 0, S.ne, p->ME.p, radius, opt.min_lm_diagonal, opt.max_lm_diagonal,
+            p->Lb.p, p->zb.p, p->status.p);
   if (p->model == 0)
-    k_inc_Y<RD, DE, true><<<grid_for(S.ninc, 128), 128, 0, p->st>>>(S.ninc, S.inc_e, p->JE.p, p->JF0.p, nullptr, p->Lb.p, p->zb.p, p->Yt.p, p->vb.p);
+    BA_LAUNCH(p, KT_INCY, (k_inc_Y<RD, DE, true>), grid_for(S.ninc, 128), 128, 0, S.ninc, S.inc_e, p->JE.p, p->JF0.p, nullptr, p->Lb.p,
+              p->zb.p, p->Yt.p, p->vb.p);
   else
-    k_inc_Y<RD, DE, false><<<grid_for(S.ninc, 128), 128, 0, p->st>>>(S.ninc, S.inc_e, nullptr, nullptr, p->Wt.p, p->Lb.p, p->zb.p, p->Yt.p, p->vb.p);
+    BA_LAUNCH(p, KT_INCY, (k_inc_Y<RD, DE, false>), grid_for(S.ninc, 128), 128, 0, S.ninc, S.inc_e, nullptr, nullptr, p->Wt.p, p->Lb.p,
+              p->zb.p, p->Yt.p, p->vb.p);
   BA_CUDA_TRY(cudaMemsetAsync(p->Sd.p, 0, sizeof(double) * (n * n + n), p->st));
   if (S.ch_finc.n > 0)
-    k_finc_partial<<<grid_for(S.ch_finc.n, 4), 128, 0, p->st>>>(S.ch_finc.n, S.ch_finc.ch, S.ch_finc.seg.p, S.ch_finc.begin.p, S.finc_ptr.p,
-                                                                S.finc.p, p->vb.p, p->part_finc.p);
-  k_seg_final<6><<<grid_for(S.nf, 4), 128, 0, p->st>>>((int)S.nf, S.ch_finc.seg_first.p, p->part_finc.p, p->vsum());
-  k_pairs_partial<DE><<<grid_for(S.ch_pairs.n, 4), 128, 0, p->st>>>(S.ch_pairs.n, S.ch_pairs.ch, S.ch_pairs.seg.p, S.ch_pairs.begin.p,
-                                                                    S.dpair_ptr.p, S.pairs.p, p->Yt.p, p->part_pairs.p);
-  k_seg_final<36><<<grid_for(S.ndest, 4), 128, 0, p->st>>>(S.ndest, S.ch_pairs.seg_first.p, p->part_pairs.p, p->Pacc.p);
-  k_assemble_dense<<<grid_for((int64_t)S.ndest * 36, 256), 256, 0, p->st>>>(S.ndest, S.dest_fa.p, S.dest_fb.p, p->Pacc.p,
-                                                                            p->model == 1 ? p->Qacc.p : nullptr, n, p->Sd.p);
+    BA_LAUNCH(p, KT_FINC, k_finc_partial, grid_for(S.ch_finc.n, 4), 128, 0, S.ch_finc.n, S.ch_finc.ch, S.ch_finc.seg.p, S.ch_finc.begin.p,
+              S.finc_ptr.p, S.finc.p, p->vb.p, p->part_finc.p);
+  BA_LAUNCH(p, KT_SEGFIN, (k_seg_final<6>), grid_for(S.nf, 4), 128, 0, (int)S.nf, S.ch_finc.seg_first.p, p->part_finc.p, p->vsum());
+  BA_LAUNCH(p, KT_PAIRS, (k_pairs_partial<DE>), grid_for(S.ch_pairs.n, 4), 128, 0, S.ch_pairs.n, S.ch_pairs.ch, S.ch_pairs.seg.p,
+            S.ch_pairs.begin.p, S.dpair_ptr.p, S.pairs.p, p->Yt.p, p->part_pairs.p);
+  BA_LAUNCH(p, KT_SEGFIN, (k_seg_final<36>), grid_for(S.ndest, 4), 128, 0, S.ndest, S.ch_pairs.seg_first.p, p->part_pairs.p, p->Pacc.p);
+  BA_LAUNCH(p, KT_ASSEMBLE, k_assemble_dense, grid_for((int64_t)S.ndest * 36, 256), 256, 0, S.ndest, S.dest_fa.p, S.dest_fb.p, p->Pacc.p,
+            p->model == 1 ? p->Qacc.p : nullptr, n, p->Sd.p);
   BA_CUDA_TRY(cudaGetLastError());
   fam_end(p, F_SCHUR);
   if (p->world > 1) {
@@ -283,21 +348,25 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
     fam_end(p, F_COLL);
   }
   fam_begin(p, F_SOLVE);
-  k_diag_rhs_dense<<<grid_for(S.nf * 6, 128), 128, 0, p->st>>>(S.nf, p->HG.p, p->vsum(), radius, opt.min_lm_diagonal, opt.max_lm_diagonal, n,
-                                                               p->Sd.p, p->rhs.p);
-  BA_TRY(launch_chol_solve((int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p, p->st));
+  BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_dense, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->HG.p, p->vsum(), radius, opt.min_lm_diagonal,
+            opt.max_lm_diagonal, n, p->Sd.p, p->rhs.p);
+  {
+    LaunchScope scope(p, KT_RCS);
+    BA_TRY(launch_chol_solve((int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p, p->st));
+  }
   fam_end(p, F_SOLVE);
   fam_begin(p, F_UPDATE);
-  k_e_backsub<DE, GE><<<grid_for(S.ne * GE, 128), 128, 0, p->st>>>(S.ne, S.einc_ptr, S.inc_f, p->Yt.p, p->Lb.p, p->zb.p, p->yf.p, p->ye.p);
+  BA_LAUNCH(p, KT_BACKSUB, (k_e_backsub<DE, GE>), grid_for(S.ne * GE, 128), 128, 0, S.ne, S.einc_ptr, S.inc_f, p->Yt.p, p->Lb.p, p->zb.p,
+            p->yf.p, p->ye.p);
   const int gm = (int)grid_for(S.nb, 256);
-  k_model_cost<RD, DE, NSLOT><<<gm, 256, 0, p->st>>>(S.nb, S.ob_e.p, S.ob_f0.p, S.ob_f1.p, p->RES.p, p->JE.p, p->JF0.p, p->JF1.p, p->ye.p,
-                                                     p->yf.p, p->bp0.p);
+  BA_LAUNCH(p, KT_MODELCOST, (k_model_cost<RD, DE, NSLOT>), gm, 256, 0, S.nb, S.ob_e.p, S.ob_f0.p, S.ob_f1.p, p->RES.p, p->JE.p, p->JF0.p,
+            p->JF1.p, p->ye.p, p->yf.p, p->bp0.p);
   BA_TRY(fold(p, p->bp0.p, gm, S_MCC));
   const int gce = (int)grid_for(S.ne * DE, 256), gcf = (int)grid_for(S.nf * 6, 256);
-  k_candidate<DE><<<gce, 256, 0, p->st>>>(S.ne, S.e_ptr.p, p->xe.p, p->se.p, p->ye.p, p->xe_c.p, p->bp0.p, p->bp1.p);
+  BA_LAUNCH(p, KT_CANDIDATE, (k_candidate<DE>), gce, 256, 0, S.ne, S.e_ptr.p, p->xe.p, p->se.p, p->ye.p, p->xe_c.p, p->bp0.p, p->bp1.p);
   BA_TRY(fold(p, p->bp0.p, gce, S_XE2));
   BA_TRY(fold(p, p->bp1.p, gce, S_DE2));
-  k_candidate<6><<<gcf, 256, 0, p->st>>>(S.nf, S.fobs_ptr.p, p->xf.p, p->sf.p, p->yf.p, p->xf_c.p, p->bp0.p, p->bp1.p);
+  BA_LAUNCH(p, KT_CANDIDATE, (k_candidate<6>), gcf, 256, 0, S.nf, S.fobs_ptr.p, p->xf.p, p->sf.p, p->yf.p, p->xf_c.p, p->bp0.p, p->bp1.p);
   BA_TRY(fold(p, p->bp0.p, gcf, S_XF2));
   BA_TRY(fold(p, p->bp1.p, gcf, S_DF2));
   BA_CUDA_TRY(cudaGetLastError());
@@ -317,66 +386,81 @@ int fetch_scalars(ba_cuda_problem* p) {
   return BA_OK;
 }
 
+// FinalizeIterationAndCheckIfMinimizerCanContinue
+bool lm_finalize(ba_cuda_problem* p, ba_cuda_iteration row, double iter_t0) {
+  LmState& L = p->lm;
+  const ba_cuda_options& opt = L.opt;
+  ba_cuda_summary& Z = L.Z;
+  if (row.step_is_successful) Z.num_successful_steps++; else Z.num_unsuccessful_steps++;
+  row.trust_region_radius = L.radius;
+  row.iteration_time_s = now_s() - iter_t0;
+  p->rows.push_back(row);
+  if (opt.minimizer_progress_to_stdout && p->rank == 0) {
+    if (row.iteration == 0) std::printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius\n");
+    std::printf("%4d % 14.6e % 10.2e % 10.2e % 10.2e % 10.2e % 10.2e\n", row.iteration, row.cost, row.cost_change,
+                row.gradient_max_norm, row.step_norm, row.relative_decrease, row.trust_region_radius);
+  }
+  if (row.iteration >= opt.max_num_iterations) { Z.termination_type = BA_NO_CONVERGENCE; Z.termination_reason = BA_REASON_MAX_ITERATIONS; return false; }
+  if (row.step_is_successful && row.gradient_max_norm <= opt.gradient_tolerance) { Z.termination_type = BA_CONVERGENCE; Z.termination_reason = BA_REASON_GRADIENT_TOLERANCE; return false; }
+  if (row.trust_region_radius <= opt.min_trust_region_radius) { Z.termination_type = BA_CONVERGENCE; Z.termination_reason = BA_REASON_MIN_TRUST_REGION_RADIUS; return false; }
+  return true;
+}
+
+void lm_read_gradient(ba_cuda_problem* p) {
+  LmState& L = p->lm;
+  L.x_cost = 0.5 * p->h_scal[S_COST];
+  L.gmax = std::max(p->h_scal[S_GMAXE], p->h_scal[S_GMAXF]);
+  L.gnorm = std::sqrt(p->h_scal[S_G2E] + p->h_scal[S_G2F]);
+}
+
+// TrustRegionMinimizer::IterationZero
 template <int RD, int DE, int GE, int NSLOT>
-int minimize(ba_cuda_problem* p, const ba_cuda_options& opt, ba_cuda_summary* sum) {
+int lm_begin(ba_cuda_problem* p, const ba_cuda_options& opt) {
   const Structure& S = p->S;
-  const double t_start = now_s();
-  ba_cuda_summary Z;
-  std::memset(&Z, 0, sizeof(Z));
+  LmState& L = p->lm;
+  L = LmState();
+  L.opt = opt;
+  L.t_start = now_s();
+  std::memset(&L.Z, 0, sizeof(L.Z));
   p->rows.clear();
+  p->profile = opt.profile_kernels != 0;
   for (int f = 0; f < F_COUNT; ++f) { p->fam_ms[f] = 0.0; p->fam_open[f] = false; }
-  Z.num_residuals = S.nb * RD;
-  Z.rcs_solver_used = BA_RCS_DENSE_CHOLESKY;
-
-  double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
-  int num_invalid = 0;
-  double iter_t0 = now_s();
-  double x_cost = 0.0, gmax = 0.0, gnorm = 0.0;
-
-  auto finalize = [&](ba_cuda_iteration row) -> bool {  // FinalizeIterationAndCheckIfMinimizerCanContinue
-    if (row.step_is_successful) Z.num_successful_steps++; else Z.num_unsuccessful_steps++;
-    row.trust_region_radius = radius;
-    row.iteration_time_s = now_s() - iter_t0;
-    p->rows.push_back(row);
-    if (opt.minimizer_progress_to_stdout && p->rank == 0) {
-      if (row.iteration == 0) std::printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius\n");
-      std::printf("%4d % 14.6e % 10.2e % 10.2e % 10.2e % 10.2e % 10.2e\n", row.iteration, row.cost, row.cost_change,
-                  row.gradient_max_norm, row.step_norm, row.relative_decrease, row.trust_region_radius);
-    }
-    if (row.iteration >= opt.max_num_iterations) { Z.termination_type = BA_NO_CONVERGENCE; Z.termination_reason = BA_REASON_MAX_ITERATIONS; return false; }
-    if (row.step_is_successful && row.gradient_max_norm <= opt.gradient_tolerance) { Z.termination_type = BA_CONVERGENCE; Z.termination_reason = BA_REASON_GRADIENT_TOLERANCE; return false; }
-    if (row.trust_region_radius <= opt.min_trust_region_radius) { Z.termination_type = BA_CONVERGENCE; Z.termination_reason = BA_REASON_MIN_TRUST_REGION_RADIUS; return false; }
-    return true;
-  };
-  auto read_gradient = [&]() {
-    x_cost = 0.5 * p->h_scal[S_COST];
-    gmax = std::max(p->h_scal[S_GMAXE], p->h_scal[S_GMAXF]);
-    gnorm = std::sqrt(p->h_scal[S_G2E] + p->h_scal[S_G2F]);
-  };
-
-  // IterationZero
+  L.Z.num_residuals = S.nb * RD;
+  L.Z.rcs_solver_used = BA_RCS_DENSE_CHOLESKY;
+  L.radius = opt.initial_trust_region_radius;
+  L.decrease_factor = 2.0;
+  L.began = true;
+  const double iter_t0 = now_s();
   BA_TRY((eval_gradient_and_jacobian<RD, DE, GE>(p, true, opt.jacobi_scaling != 0)));
-  Z.num_jacobian_evaluations++;
+  L.Z.num_jacobian_evaluations++;
   BA_TRY(fetch_scalars(p));
-  read_gradient();
+  lm_read_gradient(p);
   ba_cuda_iteration row;
   std::memset(&row, 0, sizeof(row));
-  if (!std::isfinite(x_cost)) {
-    Z.termination_type = BA_FAILURE; Z.termination_reason = BA_REASON_INITIAL_EVALUATION_FAILED;
-    Z.initial_cost = Z.final_cost = x_cost;
-    if (sum) *sum = Z;
+  L.Z.initial_cost = L.Z.final_cost = L.x_cost;
+  if (!std::isfinite(L.x_cost)) {
+    L.Z.termination_type = BA_FAILURE; L.Z.termination_reason = BA_REASON_INITIAL_EVALUATION_FAILED;
+    L.go = false;
     return BA_OK;
   }
-  Z.initial_cost = x_cost;
-  row.iteration = 0; row.step_is_valid = 1; row.step_is_successful = 1; row.cost = x_cost;
-  row.gradient_max_norm = gmax; row.gradient_norm = gnorm;
-  bool go = finalize(row);
+  row.iteration = 0; row.step_is_valid = 1; row.step_is_successful = 1; row.cost = L.x_cost;
+  row.gradient_max_norm = L.gmax; row.gradient_norm = L.gnorm;
+  L.go = lm_finalize(p, row, iter_t0);
+  return BA_OK;
+}
 
-  while (go) {
-    iter_t0 = now_s();
+// the trust-region loop body, at most max_new more rows
+template <int RD, int DE, int GE, int NSLOT>
+int lm_iterate(ba_cuda_problem* p, int32_t max_new) {
+  LmState& L = p->lm;
+  const ba_cuda_options& opt = L.opt;
+  ba_cuda_summary& Z = L.Z;
+  ba_cuda_iteration row;
+  for (int32_t it = 0; L.go && it < max_new; ++it) {
+    const double iter_t0 = now_s();
     std::memset(&row, 0, sizeof(row));
     row.iteration = p->rows.back().iteration + 1;
-    BA_CUDA_TRY(cudaMemcpyAsync(p->scal.p + S_RADIUS, &radius, sizeof(double), cudaMemcpyHostToDevice, p->st));
+    BA_CUDA_TRY(cudaMemcpyAsync(p->scal.p + S_RADIUS, &L.radius, sizeof(double), cudaMemcpyHostToDevice, p->st));
     BA_TRY((compute_step<RD, DE, GE, NSLOT>(p, opt)));
     Z.num_linear_solves++;
     Z.num_cost_evaluations++;
@@ -394,29 +478,32 @@ int minimize(ba_cuda_problem* p, const ba_cuda_options& opt, ba_cuda_summary* su
     const bool solve_ok = status == 0 && std::isfinite(model_cost_change);
     row.step_is_valid = solve_ok && model_cost_change > 0.0;
     if (!row.step_is_valid) {  // HandleInvalidStep
-      if (++num_invalid >= opt.max_num_consecutive_invalid_steps) {
+      if (++L.num_invalid >= opt.max_num_consecutive_invalid_steps) {
         Z.termination_type = BA_FAILURE; Z.termination_reason = BA_REASON_TOO_MANY_INVALID_STEPS;
+        L.go = false;
         break;
       }
-      radius = radius / decrease_factor; decrease_factor *= 2.0;
-      row.cost = x_cost; row.cost_change = 0.0;
+      L.radius = L.radius / L.decrease_factor; L.decrease_factor *= 2.0;
+      row.cost = L.x_cost; row.cost_change = 0.0;
       row.gradient_max_norm = p->rows.back().gradient_max_norm; row.gradient_norm = p->rows.back().gradient_norm;
-      go = finalize(row);
+      L.go = lm_finalize(p, row, iter_t0);
       continue;
     }
-    num_invalid = 0;
+    L.num_invalid = 0;
     const double cand_cost = 0.5 * p->h_scal[S_CAND];
     // ParameterToleranceReached
     const double x_norm = std::sqrt(p->h_scal[S_XE2] + p->h_scal[S_XF2]);
     row.step_norm = std::sqrt(p->h_scal[S_DE2] + p->h_scal[S_DF2]);
     if (row.step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
       Z.termination_type = BA_CONVERGENCE; Z.termination_reason = BA_REASON_PARAMETER_TOLERANCE;
+      L.go = false;
       break;
     }
     // FunctionToleranceReached
-    row.cost_change = x_cost - cand_cost;
-    if (std::fabs(row.cost_change) <= opt.function_tolerance * x_cost) {
+    row.cost_change = L.x_cost - cand_cost;
+    if (std::fabs(row.cost_change) <= opt.function_tolerance * L.x_cost) {
       Z.termination_type = BA_CONVERGENCE; Z.termination_reason = BA_REASON_FUNCTION_TOLERANCE;
+      L.go = false;
       break;
     }
     row.relative_decrease = row.cost_change / model_cost_change;
@@ -426,25 +513,30 @@ int minimize(ba_cuda_problem* p, const ba_cuda_options& opt, ba_cuda_summary* su
       BA_TRY((eval_gradient_and_jacobian<RD, DE, GE>(p, false, opt.jacobi_scaling != 0)));
       Z.num_jacobian_evaluations++;
       BA_TRY(fetch_scalars(p));
-      read_gradient();
+      lm_read_gradient(p);
       row.step_is_successful = 1;
-      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * row.relative_decrease - 1.0, 3));
-      radius = std::min(opt.max_trust_region_radius, radius);
-      decrease_factor = 2.0;
-      row.cost = x_cost; row.gradient_max_norm = gmax; row.gradient_norm = gnorm;
+      L.radius = L.radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * row.relative_decrease - 1.0, 3));
+      L.radius = std::min(opt.max_trust_region_radius, L.radius);
+      L.decrease_factor = 2.0;
+      row.cost = L.x_cost; row.gradient_max_norm = L.gmax; row.gradient_norm = L.gnorm;
     } else {  // HandleUnsuccessfulStep
-      radius = radius / decrease_factor; decrease_factor *= 2.0;
+      L.radius = L.radius / L.decrease_factor; L.decrease_factor *= 2.0;
       row.cost = cand_cost;
     }
-    go = finalize(row);
+    L.go = lm_finalize(p, row, iter_t0);
   }
+  return BA_OK;
+}
+
+void lm_end(ba_cuda_problem* p, ba_cuda_summary* sum) {
+  LmState& L = p->lm;
+  ba_cuda_summary& Z = L.Z;
   Z.num_iterations = (int32_t)p->rows.size();
-  Z.final_cost = x_cost;
-  Z.total_time_s = now_s() - t_start;
+  Z.final_cost = L.x_cost;
+  Z.total_time_s = now_s() - L.t_start;
   Z.ms_jacobian = p->fam_ms[F_JAC]; Z.ms_schur = p->fam_ms[F_SCHUR]; Z.ms_rcs_solve = p->fam_ms[F_SOLVE];
   Z.ms_update = p->fam_ms[F_UPDATE]; Z.ms_cost = p->fam_ms[F_COST]; Z.ms_collective = p->fam_ms[F_COLL];
   if (sum) *sum = Z;
-  return BA_OK;
 }
 
 // number of active blocks (host side, from the CSR pointers)
@@ -577,6 +669,8 @@ void reset_problem(ba_cuda_problem* p) {
   p->model = -1;
   p->params_set = false;
   p->rows.clear();
+  p->xf_s.release(); p->xe_s.release();
+  p->lm.began = false;
   p->S.~Structure();
   new (&p->S) Structure();
 }
@@ -620,7 +714,8 @@ int ba_cuda_create(ba_cuda_problem** out, int device_id) {
   BA_CUDA_TRY(cudaSetDevice(device_id));
   ba_cuda_problem* p = new ba_cuda_problem();
   p->device = device_id;
-  BA_CUDA_TRY(cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
+  BA_CUDA_TRY(cudaStreamCreateWithFlags(&p->own_st, cudaStreamNonBlocking));
+  p->st = p->own_st;
   for (int f = 0; f < F_COUNT; ++f) { BA_CUDA_TRY(cudaEventCreate(&p->ev[f][0])); BA_CUDA_TRY(cudaEventCreate(&p->ev[f][1])); }
   BA_CUDA_TRY(cudaEventCreate(&p->k0)); BA_CUDA_TRY(cudaEventCreate(&p->k1));
   BA_CUDA_TRY(cudaMallocHost((void**)&p->h_scal, sizeof(double) * S_COUNT));
@@ -639,7 +734,8 @@ void ba_cuda_destroy(ba_cuda_problem* p) {
   if (p->k1) cudaEventDestroy(p->k1);
   if (p->h_scal) cudaFreeHost(p->h_scal);
   if (p->h_status) cudaFreeHost(p->h_status);
-  cudaStream_t st = p->st;
+  for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+  cudaStream_t st = p->own_st;
   delete p;
   if (st) cudaStreamDestroy(st);
 }
@@ -799,17 +895,51 @@ int ba_cuda_get_parameters(ba_cuda_problem* p, double* params, int64_t n) {
   return BA_OK;
 }
 
-int ba_cuda_solve(ba_cuda_problem* p, const ba_cuda_options* options, ba_cuda_summary* summary) {
+int ba_cuda_save_parameters(ba_cuda_problem* p) {
+  if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
+  if (p->model < 0 || !p->params_set) return fail(BA_ERR_STATE, "no parameters have been set");
+  BA_TRY(use_device(p));
+  if (p->xf_s.n != p->xf.n) BA_TRY(p->xf_s.alloc(p->xf.n));
+  if (p->xe_s.n != p->xe.n) BA_TRY(p->xe_s.alloc(p->xe.n));
+  BA_CUDA_TRY(cudaMemcpyAsync(p->xf_s.p, p->xf.p, p->xf.bytes(), cudaMemcpyDeviceToDevice, p->st));
+  BA_CUDA_TRY(cudaMemcpyAsync(p->xe_s.p, p->xe.p, p->xe.bytes(), cudaMemcpyDeviceToDevice, p->st));
+  return BA_OK;
+}
+
+int ba_cuda_restore_parameters(ba_cuda_problem* p) {
+  if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
+  if (p->model < 0 || p->xf_s.n != p->xf.n || p->xe_s.n != p->xe.n || p->xf_s.p == nullptr)
+    return fail(BA_ERR_STATE, "ba_cuda_save_parameters has not been called for this problem");
+  BA_TRY(use_device(p));
+  BA_CUDA_TRY(cudaMemcpyAsync(p->xf.p, p->xf_s.p, p->xf.bytes(), cudaMemcpyDeviceToDevice, p->st));
+  BA_CUDA_TRY(cudaMemcpyAsync(p->xe.p, p->xe_s.p, p->xe.bytes(), cudaMemcpyDeviceToDevice, p->st));
+  return BA_OK;
+}
+
+int ba_cuda_solve_begin(ba_cuda_problem* p, const ba_cuda_options* options) {
   if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
   if (p->model < 0 || !p->params_set) return fail(BA_ERR_STATE, "set_model_* and set_parameters must be called before solve");
   BA_TRY(use_device(p));
   ba_cuda_options opt;
   if (options) opt = *options; else ba_cuda_options_init(&opt);
   if (opt.rcs_solver == BA_RCS_PCG) return fail(BA_ERR_UNSUPPORTED, "PCG reduced-system solver is not in this build yet");
-  int rc;
-  if (p->model == 0) rc = minimize<2, 3, 1, 1>(p, opt, summary);
-  else rc = minimize<8, 6, 32, 2>(p, opt, summary);
-  if (rc != BA_OK) return rc;
+  return p->model == 0 ? lm_begin<2, 3, 1, 1>(p, opt) : lm_begin<8, 6, 32, 2>(p, opt);
+}
+
+int ba_cuda_solve_iterate(ba_cuda_problem* p, int32_t max_new_iterations, int32_t* finished) {
+  if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
+  if (!p->lm.began) return fail(BA_ERR_STATE, "ba_cuda_solve_begin must be called first");
+  BA_TRY(use_device(p));
+  const int rc = p->model == 0 ? lm_iterate<2, 3, 1, 1>(p, max_new_iterations) : lm_iterate<8, 6, 32, 2>(p, max_new_iterations);
+  if (finished) *finished = p->lm.go ? 0 : 1;
+  return rc;
+}
+
+int ba_cuda_solve_end(ba_cuda_problem* p, ba_cuda_summary* summary) {
+  if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
+  if (!p->lm.began) return fail(BA_ERR_STATE, "ba_cuda_solve_begin must be called first");
+  BA_TRY(use_device(p));
+  lm_end(p, summary);
   if (summary) {
     int64_t ae = 0, af = 0;
     BA_TRY(count_active(p, p->S.e_ptr, p->S.ne, &ae));
@@ -818,6 +948,70 @@ int ba_cuda_solve(ba_cuda_problem* p, const ba_cuda_options* options, ba_cuda_su
     summary->rcs_dim = (int32_t)(6 * af);
   }
   return BA_OK;
+}
+
+int ba_cuda_solve(ba_cuda_problem* p, const ba_cuda_options* options, ba_cuda_summary* summary) {
+  BA_TRY(ba_cuda_solve_begin(p, options));
+  int32_t finished = 0;
+  BA_TRY(ba_cuda_solve_iterate(p, INT32_MAX, &finished));
+  return ba_cuda_solve_end(p, summary);
+}
+
+int ba_cuda_set_stream(ba_cuda_problem* p, void* cuda_stream) {
+  if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
+  BA_TRY(use_device(p));
+  BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  p->st = cuda_stream ? (cudaStream_t)cuda_stream : p->own_st;
+  return BA_OK;
+}
+
+// compulsory HBM traffic of one launch of each kernel on the current problem ("kernels and rooflines")
+static double algorithmic_bytes(const ba_cuda_problem* p, int kt) {
+  const Structure& S = p->S;
+  const double nb = (double)S.nb, ne = (double)S.ne, nf = (double)S.nf, ninc = (double)S.ninc;
+  const bool A = p->model == 0;
+  switch (kt) {
+    case KT_JAC:  // idx + obs in, r + J out, parameter blocks once
+      return A ? nb * 184.0 + nf * 80.0 + ne * 24.0 : nb * 1292.0 + (nf + ne) * 48.0;
+    case KT_COST: return A ? nb * 24.0 + nf * 80.0 + ne * 24.0 : nb * 76.0 + (nf + ne) * 48.0;
+    case KT_FOBS: return A ? nb * (96.0 + 16.0 + 4.0) + nf * 216.0 : nb * 2.0 * (384.0 + 64.0 + 4.0) + nf * 216.0;
+    case KT_EM: return A ? nb * 64.0 + ne * 72.0 : nb * 448.0 + ne * 216.0;
+    case KT_ECHOL: return A ? ne * (72.0 + 72.0 + 24.0) : ne * (216.0 + 288.0 + 48.0);
+    case KT_INCY: return A ? nb * (144.0 + 144.0 + 48.0) + ne * 96.0 : ninc * (288.0 + 288.0 + 48.0) + ne * 336.0;
+    case KT_FINC: return ninc * 52.0 + nf * 48.0;
+    case KT_PAIRS: return (double)S.npairs * (8.0 + (A ? 288.0 : 576.0)) + (double)S.ndest * 288.0;
+    case KT_BACKSUB: return A ? ninc * (144.0 + 4.0) + ne * 120.0 : ninc * (288.0 + 4.0) + ne * 384.0;
+    case KT_MODELCOST: return A ? nb * (160.0 + 8.0) + ne * 24.0 : nb * (1216.0 + 12.0) + ne * 48.0;
+    default: return 0.0;
+  }
+}
+
+int ba_cuda_get_kernel_stats(ba_cuda_problem* p, ba_cuda_kernel_stat* stats, int cap) {
+  if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
+  int n = 0;
+  for (int k = 0; k < KT_COUNT; ++k) {
+    if (p->kt_launches[k] == 0) continue;
+    if (stats && n < cap) {
+      std::memset(&stats[n], 0, sizeof(stats[n]));
+      std::snprintf(stats[n].name, sizeof(stats[n].name), "%s", kKtName[k]);
+      stats[n].launches = p->kt_launches[k];
+      stats[n].total_ms = p->kt_ms[k];
+      stats[n].algorithmic_bytes_per_launch = p->model >= 0 ? algorithmic_bytes(p, k) : 0.0;
+    }
+    ++n;
+  }
+  return n;
+}
+
+int64_t ba_cuda_num_launches(const ba_cuda_problem* p) {
+  int64_t n = 0;
+  if (p) for (int k = 0; k < KT_COUNT; ++k) n += p->kt_launches[k];
+  return n;
+}
+
+void ba_cuda_reset_stats(ba_cuda_problem* p) {
+  if (!p) return;
+  for (int k = 0; k < KT_COUNT; ++k) { p->kt_launches[k] = 0; p->kt_ms[k] = 0.0; }
 }
 
 int ba_cuda_get_iterations(ba_cuda_problem* p, ba_cuda_iteration* rows, int cap) {
@@ -833,8 +1027,8 @@ int ba_cuda_eval(ba_cuda_problem* p, double* cost, double* residuals, double* ja
   BA_TRY(use_device(p));
   const Structure& S = p->S;
   const int RD = p->model == 0 ? 2 : 8, DE = p->model == 0 ? 3 : 6;
-  k_fill<<<grid_for(S.ne * DE, 256), 256, 0, p->st>>>(p->se.p, S.ne * DE, 1.0);
-  k_fill<<<grid_for(S.nf * 6, 256), 256, 0, p->st>>>(p->sf.p, S.nf * 6, 1.0);
+  BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.ne * DE, 256), 256, 0, p->se.p, S.ne * DE, 1.0);
+  BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.nf * 6, 256), 256, 0, p->sf.p, S.nf * 6, 1.0);
   BA_TRY(build_tables(p, false));  // warm the tables outside the timed kernel
   BA_CUDA_TRY(cudaEventRecord(p->k0, p->st));
   BA_TRY(run_jacobian(p));

@@ -10,7 +10,7 @@ import subprocess
 
 import numpy as np
 
-from .abi import UNIQUE_ID_BYTES, Iteration, Options, Summary
+from .abi import UNIQUE_ID_BYTES, Iteration, KernelStat, Options, Summary
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libba_cuda.so")
@@ -21,7 +21,9 @@ EXPORTS = [
     "ba_cuda_comm_unique_id", "ba_cuda_comm_init", "ba_cuda_shard_blocks", "ba_cuda_set_model_a", "ba_cuda_set_model_b",
     "ba_cuda_set_parameters", "ba_cuda_get_parameters", "ba_cuda_num_parameters", "ba_cuda_solve",
     "ba_cuda_get_iterations", "ba_cuda_eval", "ba_cuda_last_kernel_ms", "ba_cuda_reprojection_error",
-    "ba_cuda_project_points_error", "ba_cuda_model_b_outputs",
+    "ba_cuda_project_points_error", "ba_cuda_model_b_outputs", "ba_cuda_solve_begin", "ba_cuda_solve_iterate",
+    "ba_cuda_solve_end", "ba_cuda_set_stream", "ba_cuda_get_kernel_stats", "ba_cuda_num_launches", "ba_cuda_reset_stats",
+    "ba_cuda_save_parameters", "ba_cuda_restore_parameters",
 ]
 
 
@@ -44,6 +46,8 @@ def lib():
         L.ba_cuda_last_error.restype = C.c_char_p
         L.ba_cuda_num_parameters.restype = C.c_int64
         L.ba_cuda_last_kernel_ms.restype = C.c_double
+        L.ba_cuda_num_launches.restype = C.c_int64
+        L.ba_cuda_reset_stats.restype = None
         L.ba_cuda_options_init.argtypes = [C.POINTER(Options)]
         _LIB = L
     return _LIB
@@ -136,6 +140,12 @@ class Problem:
         _check(lib().ba_cuda_get_parameters(self._h, x.ctypes, C.c_int64(x.shape[0])))
         return x
 
+    def save_parameters(self):
+        _check(lib().ba_cuda_save_parameters(self._h))
+
+    def restore_parameters(self):
+        _check(lib().ba_cuda_restore_parameters(self._h))
+
     def solve(self, options=None):
         opts = options or default_options()
         s = Summary()
@@ -144,6 +154,41 @@ class Problem:
         rows = (Iteration * max(n, 1))()
         lib().ba_cuda_get_iterations(self._h, rows, C.c_int(n))
         return s, [rows[i].as_dict() for i in range(n)]
+
+    def _rows(self):
+        n = lib().ba_cuda_get_iterations(self._h, None, C.c_int(0))
+        rows = (Iteration * max(n, 1))()
+        lib().ba_cuda_get_iterations(self._h, rows, C.c_int(n))
+        return [rows[i].as_dict() for i in range(n)]
+
+    def solve_begin(self, options=None):
+        opts = options or default_options()
+        _check(lib().ba_cuda_solve_begin(self._h, C.byref(opts)))
+
+    def solve_iterate(self, max_new_iterations):
+        fin = C.c_int32(0)
+        _check(lib().ba_cuda_solve_iterate(self._h, C.c_int32(max_new_iterations), C.byref(fin)))
+        return bool(fin.value)
+
+    def solve_end(self):
+        s = Summary()
+        _check(lib().ba_cuda_solve_end(self._h, C.byref(s)))
+        return s, self._rows()
+
+    def set_stream(self, cuda_stream_handle):
+        _check(lib().ba_cuda_set_stream(self._h, C.c_void_p(cuda_stream_handle)))
+
+    def kernel_stats(self):
+        n = lib().ba_cuda_get_kernel_stats(self._h, None, C.c_int(0))
+        buf = (KernelStat * max(n, 1))()
+        lib().ba_cuda_get_kernel_stats(self._h, buf, C.c_int(n))
+        return [buf[i].as_dict() for i in range(n)]
+
+    def num_launches(self):
+        return int(lib().ba_cuda_num_launches(self._h))
+
+    def reset_stats(self):
+        lib().ba_cuda_reset_stats(self._h)
 
     def eval(self, want_residuals=True, want_jac=True):
         rd, jw = (2, 18) if self.model == "A" else (8, 144)

@@ -115,7 +115,12 @@ def bal_like(n_cam, n_pt, obs_per_pt, window, seed, noise_px=0.5, perturb=(0.02,
         uv[~keep] = (PPX, PPY)
     uv = uv + rng.normal(0.0, noise_px, uv.shape)
     truth = np.concatenate([cams.ravel(), X.ravel()])
-    init_c = cams + np.concatenate([rng.normal(0, perturb[0], (n_cam, 3)), rng.normal(0, perturb[1], (n_cam, 3))], 1)
+    # initial guess: rotation perturbed about the camera CENTRE (perturbing t = -R c directly would move a camera that
+    # sits 50 m down the trajectory by metres), centre and points jittered
+    rv_init = rv_true + rng.normal(0, perturb[0], (n_cam, 3))
+    c_init = cam_pos + rng.normal(0, perturb[1], (n_cam, 3))
+    t_init = -np.einsum("nij,nj->ni", _rodrigues(rv_init), c_init)
+    init_c = np.concatenate([rv_init, t_init], 1)
     init_X = X + rng.normal(0, perturb[2], X.shape)
     params = np.concatenate([init_c.ravel(), init_X.ravel()])
     return ModelA(n_cam, n_pt, cam_idx.astype(np.int32), pt_idx.astype(np.int32), uv, np.tile(INTR, (n_cam, 1)), params, truth)
