@@ -16,6 +16,7 @@
 #include "ba_dense.cuh"
 #include "ba_kernels.cuh"
 #include "ba_structure.cuh"
+#include "ba_rcs.cuh"
 
 using namespace ba;
 
@@ -29,10 +30,11 @@ struct Nccl {
   int (*CommInitRank)(ncclComm_t*, int, NcclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok() const { return handle != nullptr; }
 };
-constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+constexpr int kNcclFloat64 = 8, kNcclInt64 = 4, kNcclUint64 = 5, kNcclSum = 0, kNcclMax = 2;
 Nccl& nccl() {
   static Nccl n;
   static bool tried = false;
@@ -49,6 +51,7 @@ Nccl& nccl() {
       n.CommDestroy = (int (*)(ncclComm_t))dlsym(n.handle, "ncclCommDestroy");
       n.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclAllReduce");
       n.GetErrorString = (const char* (*)(int))dlsym(n.handle, "ncclGetErrorString");
+      n.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclAllGather");
       if (!n.GetUniqueId || !n.CommInitRank || !n.CommDestroy || !n.AllReduce) n.handle = nullptr;
     }
   }
@@ -96,6 +99,12 @@ struct ba_cuda_problem {
   DVec<double> RES, JE, JF0, JF1, ME, HG, Wt, Lb, zb, Yt, vb, Pacc, Qacc, Sd, rhs, yf, ye;
   DVec<double> part_fobs, part_finc, part_pairs, part_dobs, bp0, bp1, scal;
   DVec<int> status;
+  // reduced camera system: block-sparse pattern (shared by all ranks), values, PCG workspace
+  RcsPattern R;
+  PcgWork pcg;
+  DVec<double> Sb;           // R.nd * 36 block values | nf * 6 rhs correction (one collective covers both)
+  int solver = 0;            // ba_rcs_solver resolved for the current solve
+  int h_pcg_iters = 0;
   double* h_scal = nullptr;  // pinned
   int* h_status = nullptr;   // pinned
   bool params_set = false;
@@ -119,7 +128,8 @@ struct ba_cuda_problem {
   struct Pending { int kt; size_t e0, e1; };
   std::vector<Pending> pending;
   int64_t n_rcs() const { return 6 * S.nf; }
-  double* vsum() { return Sd.p + n_rcs() * n_rcs(); }  // tail of the dense RCS buffer: one collective covers both
+  // rhs correction (sum of v_i per camera) lives at the tail of the RCS value buffer: one collective covers both
+  double* vsum() { return solver == BA_RCS_PCG ? Sb.p + (int64_t)R.nd * 36 : Sd.p + n_rcs() * n_rcs(); }
 };
 
 namespace {
@@ -189,6 +199,47 @@ int allreduce(ba_cuda_problem* p, double* buf, size_t count, int op) {
   const int rc = nccl().AllReduce(buf, buf, count, kNcclFloat64, op, p->comm, p->st);
   if (rc != 0) return fail(BA_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
   return BA_OK;
+}
+
+// Multi-GPU: every rank only knows the destination blocks its own shard couples; the stored pattern has to be
+// the union, identical on all ranks, so that one ncclAllReduce sums the block values in place.
+int build_global_pattern(ba_cuda_problem* p) {
+  const Structure& S = p->S;
+  if (!nccl().AllGather) return fail(BA_ERR_NCCL, "ncclAllGather is not available");
+  // 1. counts
+  DVec<int64_t> cnt;
+  BA_TRY(cnt.alloc(p->world));
+  const int64_t mine = S.ndest;
+  BA_CUDA_TRY(cudaMemcpyAsync(cnt.p + p->rank, &mine, sizeof(int64_t), cudaMemcpyHostToDevice, p->st));
+  int rc = nccl().AllGather(cnt.p + p->rank, cnt.p, 1, kNcclInt64, p->comm, p->st);
+  if (rc != 0) return fail(BA_ERR_NCCL, "ncclAllGather failed (%d)", rc);
+  std::vector<int64_t> h(p->world);
+  BA_CUDA_TRY(cudaMemcpyAsync(h.data(), cnt.p, sizeof(int64_t) * p->world, cudaMemcpyDeviceToHost, p->st));
+  BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  int64_t mx = 0;
+  for (int64_t v : h) mx = std::max(mx, v);
+  if (mx * p->world >= (int64_t)INT32_MAX) return fail(BA_ERR_UNSUPPORTED, "reduced camera system pattern too large");
+  // 2. keys, padded with ~0 to the largest count
+  DVec<uint64_t> all, sorted, uniq;
+  DVec<int> nuniq;
+  BA_TRY(all.alloc((size_t)mx * p->world)); BA_TRY(sorted.alloc((size_t)mx * p->world)); BA_TRY(uniq.alloc((size_t)mx * p->world));
+  BA_TRY(nuniq.alloc(1));
+  uint64_t* my = all.p + (size_t)mx * p->rank;
+  BA_CUDA_TRY(cudaMemsetAsync(my, 0xff, sizeof(uint64_t) * mx, p->st));
+  BA_CUDA_TRY(cudaMemcpyAsync(my, S.dest_keys.p, sizeof(uint64_t) * S.ndest, cudaMemcpyDeviceToDevice, p->st));
+  rc = nccl().AllGather(my, all.p, (size_t)mx, kNcclUint64, p->comm, p->st);
+  if (rc != 0) return fail(BA_ERR_NCCL, "ncclAllGather failed (%d)", rc);
+  const int total = (int)(mx * p->world);
+  BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, all.p, sorted.p, total, 0, 64, p->st); }));
+  BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceSelect::Unique(t, b, sorted.p, uniq.p, nuniq.p, total, p->st); }));
+  int nu = 0;
+  uint64_t last = 0;
+  BA_CUDA_TRY(cudaMemcpyAsync(&nu, nuniq.p, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  BA_CUDA_TRY(cudaMemcpyAsync(&last, uniq.p + (nu - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, p->st));
+  BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  if (last == ~0ull) --nu;
+  return build_rcs_pattern(p->R, uniq.p, nu, S.nf, p->st);
 }
 
 int build_tables(ba_cuda_problem* p, bool candidate) {
@@ -330,7 +381,9 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   else
     BA_LAUNCH(p, KT_INCY, (k_inc_Y<RD, DE, false>), grid_for(S.ninc, 128), 128, 0, S.ninc, S.inc_e, nullptr, nullptr, p->Wt.p, p->Lb.p,
               p->zb.p, p->Yt.p, p->vb.p);
-  BA_CUDA_TRY(cudaMemsetAsync(p->Sd.p, 0, sizeof(double) * (n * n + n), p->st));
+  const bool pcg = p->solver == BA_RCS_PCG;
+  if (pcg) { if (p->world > 1) BA_CUDA_TRY(cudaMemsetAsync(p->Sb.p, 0, p->Sb.bytes(), p->st)); }
+  else BA_CUDA_TRY(cudaMemsetAsync(p->Sd.p, 0, sizeof(double) * (n * n + n), p->st));
   if (S.ch_finc.n > 0)
     BA_LAUNCH(p, KT_FINC, k_finc_partial, grid_for(S.ch_finc.n, 4), 128, 0, S.ch_finc.n, S.ch_finc.ch, S.ch_finc.seg.p, S.ch_finc.begin.p,
               S.finc_ptr.p, S.finc.p, p->vb.p, p->part_finc.p);
@@ -338,19 +391,33 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   BA_LAUNCH(p, KT_PAIRS, (k_pairs_partial<DE>), grid_for(S.ch_pairs.n, 4), 128, 0, S.ch_pairs.n, S.ch_pairs.ch, S.ch_pairs.seg.p,
             S.ch_pairs.begin.p, S.dpair_ptr.p, S.pairs.p, p->Yt.p, p->part_pairs.p);
   BA_LAUNCH(p, KT_SEGFIN, (k_seg_final<36>), grid_for(S.ndest, 4), 128, 0, S.ndest, S.ch_pairs.seg_first.p, p->part_pairs.p, p->Pacc.p);
-  BA_LAUNCH(p, KT_ASSEMBLE, k_assemble_dense, grid_for((int64_t)S.ndest * 36, 256), 256, 0, S.ndest, S.dest_fa.p, S.dest_fb.p, p->Pacc.p,
-            p->model == 1 ? p->Qacc.p : nullptr, n, p->Sd.p);
+  if (pcg)
+    BA_LAUNCH(p, KT_ASSEMBLE, k_assemble_bsr, grid_for((int64_t)S.ndest * 36, 256), 256, 0, S.ndest, p->R.l2g.p, p->Pacc.p,
+              p->model == 1 ? p->Qacc.p : nullptr, p->Sb.p);
+  else
+    BA_LAUNCH(p, KT_ASSEMBLE, k_assemble_dense, grid_for((int64_t)S.ndest * 36, 256), 256, 0, S.ndest, S.dest_fa.p, S.dest_fb.p, p->Pacc.p,
+              p->model == 1 ? p->Qacc.p : nullptr, n, p->Sd.p);
   BA_CUDA_TRY(cudaGetLastError());
   fam_end(p, F_SCHUR);
   if (p->world > 1) {
     fam_begin(p, F_COLL);
-    BA_TRY(allreduce(p, p->Sd.p, n * n + n, kNcclSum));  // partial RCS and the partial rhs correction in one call
+    // partial RCS and the partial rhs correction in one call
+    if (pcg) BA_TRY(allreduce(p, p->Sb.p, p->Sb.n, kNcclSum));
+    else BA_TRY(allreduce(p, p->Sd.p, n * n + n, kNcclSum));
     fam_end(p, F_COLL);
   }
   fam_begin(p, F_SOLVE);
-  BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_dense, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->HG.p, p->vsum(), radius, opt.min_lm_diagonal,
-            opt.max_lm_diagonal, n, p->Sd.p, p->rhs.p);
-  {
+  if (pcg) {
+    BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_bsr, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->R.diag.p, p->HG.p, p->vsum(), radius,
+              opt.min_lm_diagonal, opt.max_lm_diagonal, p->Sb.p, p->rhs.p);
+    {
+      LaunchScope scope(p, KT_RCS);
+      BA_TRY(launch_pcg(p->pcg, p->R, p->Sb.p, p->rhs.p, p->yf.p, p->status.p, opt, p->st));
+    }
+    BA_CUDA_TRY(cudaMemcpyAsync(&p->h_pcg_iters, p->pcg.iters.p, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  } else {
+    BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_dense, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->HG.p, p->vsum(), radius, opt.min_lm_diagonal,
+              opt.max_lm_diagonal, n, p->Sd.p, p->rhs.p);
     LaunchScope scope(p, KT_RCS);
     BA_TRY(launch_chol_solve((int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p, p->st));
   }
@@ -375,6 +442,36 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   BA_TRY(run_cost_candidate(p));
   fam_end(p, F_COST);
   if (p->world > 1) BA_TRY(allreduce(p, p->scal.p + S_CAND, 4, kNcclSum));  // S_CAND, S_MCC, S_XE2, S_DE2
+  return BA_OK;
+}
+
+// Resolves options.rcs_solver for this problem and makes sure the matching RCS storage exists.
+// BA_RCS_AUTO: dense Cholesky while the system is rig sized (Ceres DENSE_SCHUR, what the reference asks for),
+// block-sparse PCG above.
+constexpr int64_t kDenseAutoMaxN = 768;
+int prepare_solver(ba_cuda_problem* p, const ba_cuda_options& opt) {
+  const Structure& S = p->S;
+  const int64_t n = p->n_rcs();
+  int want = opt.rcs_solver;
+  if (want == BA_RCS_AUTO) want = n <= kDenseAutoMaxN ? BA_RCS_DENSE_CHOLESKY : BA_RCS_PCG;
+  if (want != BA_RCS_DENSE_CHOLESKY && want != BA_RCS_PCG) return fail(BA_ERR_INVALID_ARGUMENT, "unknown rcs_solver %d", opt.rcs_solver);
+  if (want == BA_RCS_DENSE_CHOLESKY) {
+    if (2 * (size_t)n * sizeof(double) > 200 * 1024)
+      return fail(BA_ERR_UNSUPPORTED, "dense RCS of dimension %lld is too large for the single-CTA Cholesky; use BA_RCS_PCG", (long long)n);
+    if (p->Sd.n != (size_t)(n * n + n)) BA_TRY(p->Sd.alloc(n * n + n));
+  } else {
+    if (p->R.nd == 0 || p->R.nf != S.nf) {
+      if (p->world > 1) BA_TRY(build_global_pattern(p));
+      else BA_TRY(build_rcs_pattern(p->R, S.dest_keys.p, S.ndest, S.nf, p->st));
+      BA_TRY(p->R.l2g.alloc(S.ndest));
+      k_map_keys<<<grid_for(S.ndest, 256), 256, 0, p->st>>>(S.dest_keys.p, S.ndest, p->R.keys.p, p->R.nd, p->R.l2g.p);
+      BA_CUDA_TRY(cudaGetLastError());
+      BA_TRY(p->Sb.alloc((size_t)p->R.nd * 36 + (size_t)S.nf * 6));
+      BA_TRY(pcg_prepare(p->pcg, S.nf, p->device));
+      BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+    }
+  }
+  p->solver = want;
   return BA_OK;
 }
 
@@ -426,7 +523,7 @@ int lm_begin(ba_cuda_problem* p, const ba_cuda_options& opt) {
   p->profile = opt.profile_kernels != 0;
   for (int f = 0; f < F_COUNT; ++f) { p->fam_ms[f] = 0.0; p->fam_open[f] = false; }
   L.Z.num_residuals = S.nb * RD;
-  L.Z.rcs_solver_used = BA_RCS_DENSE_CHOLESKY;
+  L.Z.rcs_solver_used = p->solver;
   L.radius = opt.initial_trust_region_radius;
   L.decrease_factor = 2.0;
   L.began = true;
@@ -465,6 +562,7 @@ int lm_iterate(ba_cuda_problem* p, int32_t max_new) {
     Z.num_linear_solves++;
     Z.num_cost_evaluations++;
     BA_TRY(fetch_scalars(p));
+    row.linear_solver_iterations = p->solver == BA_RCS_PCG ? p->h_pcg_iters : 0;
     int status = *p->h_status;
     if (p->world > 1) {  // a failed block factorisation on any rank invalidates the step everywhere
       double flag = status ? 1.0 : 0.0, *d = p->scal.p + S_COUNT - 1;
@@ -553,7 +651,6 @@ int count_active(ba_cuda_problem* p, const DVec<int64_t>& ptr, int64_t nblk, int
 int alloc_workspace(ba_cuda_problem* p, int RD, int DE) {
   const Structure& S = p->S;
   const int64_t n = p->n_rcs();
-  if (n > 2048) return fail(BA_ERR_UNSUPPORTED, "reduced camera system of dimension %lld needs the PCG solver (not in this build yet)", (long long)n);
   cudaStream_t st = p->st;
   BA_TRY(p->xf.alloc_zero(S.nf * 6, st)); BA_TRY(p->xf_c.alloc_zero(S.nf * 6, st));
   BA_TRY(p->xe.alloc_zero(S.ne * DE, st)); BA_TRY(p->xe_c.alloc_zero(S.ne * DE, st));
@@ -569,7 +666,8 @@ int alloc_workspace(ba_cuda_problem* p, int RD, int DE) {
   BA_TRY(p->Lb.alloc(S.ne * DE * DE)); BA_TRY(p->zb.alloc(S.ne * DE));
   BA_TRY(p->Yt.alloc(S.ninc * DE * 6)); BA_TRY(p->vb.alloc(S.ninc * 6));
   BA_TRY(p->Pacc.alloc((int64_t)S.ndest * 36)); BA_TRY(p->Qacc.alloc(p->model == 1 ? (int64_t)S.ndest * 36 : 0));
-  BA_TRY(p->Sd.alloc(n * n + n)); BA_TRY(p->rhs.alloc(n)); BA_TRY(p->yf.alloc_zero(n, st)); BA_TRY(p->ye.alloc_zero(S.ne * DE, st));
+  p->Sd.release(); p->Sb.release(); p->solver = 0;
+  BA_TRY(p->rhs.alloc(n)); BA_TRY(p->yf.alloc_zero(n, st)); BA_TRY(p->ye.alloc_zero(S.ne * DE, st));
   BA_TRY(p->part_fobs.alloc((int64_t)S.ch_fobs.n * NV_F)); BA_TRY(p->part_finc.alloc((int64_t)S.ch_finc.n * 6));
   BA_TRY(p->part_pairs.alloc((int64_t)S.ch_pairs.n * 36));
   BA_TRY(p->part_dobs.alloc(p->model == 1 ? (int64_t)S.ch_dobs.n * 36 : 0));
@@ -670,6 +768,8 @@ void reset_problem(ba_cuda_problem* p) {
   p->params_set = false;
   p->rows.clear();
   p->xf_s.release(); p->xe_s.release();
+  p->R.~RcsPattern();
+  new (&p->R) RcsPattern();
   p->lm.began = false;
   p->S.~Structure();
   new (&p->S) Structure();
@@ -922,7 +1022,7 @@ int ba_cuda_solve_begin(ba_cuda_problem* p, const ba_cuda_options* options) {
   BA_TRY(use_device(p));
   ba_cuda_options opt;
   if (options) opt = *options; else ba_cuda_options_init(&opt);
-  if (opt.rcs_solver == BA_RCS_PCG) return fail(BA_ERR_UNSUPPORTED, "PCG reduced-system solver is not in this build yet");
+  BA_TRY(prepare_solver(p, opt));
   return p->model == 0 ? lm_begin<2, 3, 1, 1>(p, opt) : lm_begin<8, 6, 32, 2>(p, opt);
 }
 

@@ -41,6 +41,7 @@ struct Structure {
   DVec<int64_t> finc_ptr, fobs_ptr;
   DVec<int32_t> finc, fobs;  // fobs entries are (obs << 1 | slot)
   DVec<int32_t> dest_fa, dest_fb, diag_dest;
+  DVec<uint64_t> dest_keys;  // fa * nf + fb, ascending (the RCS pattern of this rank's shard)
   DVec<int64_t> dpair_ptr;
   DVec<int2> pairs;
   DVec<int64_t> dobs_ptr;  // nslots == 2 only: dest -> obs having (f0,f1) == (fa,fb)
@@ -294,7 +295,7 @@ inline int build_structure(Structure& S, int64_t nb, int64_t ne, int64_t nf, con
   }
 
   // 4. destination blocks of the reduced system and their incidence-pair lists
-  DVec<uint64_t> dest_keys;
+  DVec<uint64_t>& dest_keys = S.dest_keys;
   {
     DVec<int64_t> cnt, off;
     BA_TRY(cnt.alloc(ne + 1)); BA_TRY(off.alloc(ne + 1));
@@ -345,7 +346,13 @@ inline int build_structure(Structure& S, int64_t nb, int64_t ne, int64_t nf, con
     k_dobs_ptr<<<grid_for(S.ndest + 1, B), B, 0, st>>>(ks.p, nb, dest_keys.p, S.ndest, S.dobs_ptr.p);
     BA_CUDA_TRY(cudaStreamSynchronize(st));
   }
-  dest_keys.release();
+  {  // keep exactly ndest keys
+    DVec<uint64_t> exact;
+    BA_TRY(exact.alloc(S.ndest));
+    BA_CUDA_TRY(cudaMemcpyAsync(exact.p, dest_keys.p, sizeof(uint64_t) * S.ndest, cudaMemcpyDeviceToDevice, st));
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+    dest_keys.swap(exact);
+  }
   // 6. chunk tables of the gather reductions
   BA_TRY(build_chunks(S.ch_fobs, S.fobs_ptr.p, (int)nf, 256, st));
   BA_TRY(build_chunks(S.ch_finc, S.finc_ptr.p, (int)nf, 512, st));

@@ -190,6 +190,58 @@ def test_rejected_steps_follow_the_same_schedule(gpu, oracle, seed, perturb):
     assert np.abs(x - xo).max() < POSE_ATOL
 
 
+# ---- K3b: block-sparse PCG on the reduced camera system ------------------------------------------
+@pytest.mark.parametrize("name", ["balA", "chain"])
+def test_pcg_matches_oracle_pcg(gpu, oracle, name):
+    # same truncated-CG rule on both sides (Ceres' ITERATIVE_SCHUR + SCHUR_JACOBI): same LM schedule, same
+    # number of CG iterations per linear solve (the inexact steps are part of the algorithm's definition)
+    pr = S.bal_like(60, 5000, 6, 16, 13, variable_degree=True) if name == "balA" else S.bal_like(300, 20000, 5, 20, 17)
+    opt_g, opt_o = cuda.default_options(), oracle.default_options()
+    for o in (opt_g, opt_o):
+        o.rcs_solver = abi.RCS_PCG
+        o.max_num_iterations = 6
+    gpu.set_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr)
+    gpu.set_parameters(pr.params)
+    s, rows = gpu.solve(opt_g)
+    x = gpu.get_parameters()
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o,
+                                          linear_solver=oracle.SCHUR_PCG, n_threads=4)
+    assert s.rcs_solver_used == abi.RCS_PCG
+    assert len(rows) == len(rows_o)
+    # The Q-based stopping test (zeta < eta) can flip by one CG iteration on round-off: from the first row where the
+    # counts differ, the two runs take (slightly) different inexact steps and only the looser bound applies.
+    same = True
+    for a, b in zip(rows, rows_o):
+        assert a["step_is_successful"] == b["step_is_successful"]
+        ia, ib = a["linear_solver_iterations"], b["linear_solver_iterations"]
+        assert abs(ia - ib) <= max(2, 0.1 * ib), (a, b)
+        same = same and ia == ib
+        assert H.rel(a["cost"], b["cost"]) <= (1e-9 if same else 1e-3), (a, b)
+        assert H.rel(a["trust_region_radius"], b["trust_region_radius"]) <= (1e-7 if same else 0.5)
+    assert np.abs(x - xo).max() < (1e-6 if same else 1e-2)
+    assert rows[1]["linear_solver_iterations"] == rows_o[1]["linear_solver_iterations"] > 0
+
+
+def test_pcg_converges_to_the_dense_solution(gpu):
+    # with a tight CG tolerance the PCG step is the exact step: the LM trace must then equal the dense-Cholesky trace
+    pr = S.bal_like(40, 3000, 6, 12, 3)
+    traces = []
+    for solver in (abi.RCS_DENSE_CHOLESKY, abi.RCS_PCG):
+        opt = cuda.default_options()
+        opt.rcs_solver = solver
+        opt.pcg_eta = 1e-14
+        opt.pcg_max_iterations = 2000
+        gpu.set_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr)
+        gpu.set_parameters(pr.params)
+        s, rows = gpu.solve(opt)
+        traces.append((s, rows, gpu.get_parameters()))
+    (s0, r0, x0), (s1, r1, x1) = traces
+    assert s0.num_iterations == s1.num_iterations and s0.termination_reason == s1.termination_reason
+    for a, b in zip(r0, r1):
+        assert H.rel(a["cost"], b["cost"]) <= 1e-8
+    assert np.abs(x0 - x1).max() < 1e-6
+
+
 def test_max_iterations_and_determinism(gpu):
     pr = S.bal_like(30, 2000, 5, 12, 5)
     opt = cuda.default_options()
