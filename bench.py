@@ -50,7 +50,7 @@ WORKLOADS = {
     "small": dict(desc="smoke-sized BAL-shaped synthetic: 50 cameras x 20k points x 100k observations",
                   kind="bal", args=(50, 20000, 5, 12, 0xBA00)),
 }
-DEFAULT_WORKLOAD = "cfg3a"
+DEFAULT_WORKLOAD = "cfg4"
 
 
 def make_workload(name):
