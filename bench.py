@@ -64,16 +64,9 @@ def make_workload(name):
 def shard_model_a(pr, rank, world):
     """Points (with all their observations) are block-distributed over ranks, balanced by observation count;
     cameras are replicated.  Returns the rank-local arrays."""
-    from realsensecalibration_b200 import cuda
-    if world == 1:
-        return pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.params
-    deg = np.bincount(pr.pt_idx, minlength=pr.n_pt).astype(np.int64)
-    rng = cuda.shard_blocks(deg, world)
-    lo, hi = int(rng[rank]), int(rng[rank + 1])
-    sel = (pr.pt_idx >= lo) & (pr.pt_idx < hi)
-    cams = pr.params[:6 * pr.n_cam]
-    pts = pr.params[6 * pr.n_cam:].reshape(-1, 3)[lo:hi]
-    return hi - lo, pr.cam_idx[sel], (pr.pt_idx[sel] - lo).astype(np.int32), pr.obs_xy[sel], np.concatenate([cams, pts.ravel()])
+    from realsensecalibration_b200 import sharding
+    sh = sharding.shard_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.params, rank, world)
+    return sh.n_pt, sh.cam_idx, sh.pt_idx, sh.obs_xy, sh.params
 
 
 class ClockSampler:

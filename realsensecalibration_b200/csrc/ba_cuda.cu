@@ -34,7 +34,7 @@ struct Nccl {
   const char* (*GetErrorString)(int) = nullptr;
   bool ok() const { return handle != nullptr; }
 };
-constexpr int kNcclFloat64 = 8, kNcclInt64 = 4, kNcclUint64 = 5, kNcclSum = 0, kNcclMax = 2;
+constexpr int kNcclFloat64 = 8, kNcclInt32 = 2, kNcclInt64 = 4, kNcclUint64 = 5, kNcclSum = 0, kNcclMax = 2;
 Nccl& nccl() {
   static Nccl n;
   static bool tried = false;
@@ -99,6 +99,8 @@ struct ba_cuda_problem {
   DVec<double> RES, JE, JF0, JF1, ME, HG, Wt, Lb, zb, Yt, vb, Pacc, Qacc, Sd, rhs, yf, ye;
   DVec<double> part_fobs, part_finc, part_pairs, part_dobs, bp0, bp1, scal;
   DVec<int> status;
+  DVec<int64_t> f_act_ptr;   // exclusive scan of the kept blocks' GLOBAL activity: active iff ptr[f + 1] > ptr[f]
+  int64_t n_active_e_global = 0, n_active_f_global = 0, nb_global = 0;
   // reduced camera system: block-sparse pattern (shared by all ranks), values, PCG workspace
   RcsPattern R;
   PcgWork pcg;
@@ -194,9 +196,9 @@ int fold(ba_cuda_problem* p, const double* partial, int n, int slot, bool is_max
   return BA_OK;
 }
 
-int allreduce(ba_cuda_problem* p, double* buf, size_t count, int op) {
+int allreduce(ba_cuda_problem* p, void* buf, size_t count, int op, int dtype = kNcclFloat64) {
   if (p->world <= 1) return BA_OK;
-  const int rc = nccl().AllReduce(buf, buf, count, kNcclFloat64, op, p->comm, p->st);
+  const int rc = nccl().AllReduce(buf, buf, count, dtype, op, p->comm, p->st);
   if (rc != 0) return fail(BA_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
   return BA_OK;
 }
@@ -321,7 +323,7 @@ int run_gradient_norms(ba_cuda_problem* p) {
   BA_LAUNCH(p, KT_GRADNORM, (k_gradient_norm<DE, NU + DE, NU>), ge, 256, 0, S.ne, S.e_ptr.p, p->xe.p, p->se.p, p->ME.p, p->bp0.p, p->bp1.p);
   BA_TRY(fold(p, p->bp0.p, ge, S_GMAXE, true));
   BA_TRY(fold(p, p->bp1.p, ge, S_G2E));
-  BA_LAUNCH(p, KT_GRADNORM, (k_gradient_norm<6, NV_F, 21>), gf, 256, 0, S.nf, S.fobs_ptr.p, p->xf.p, p->sf.p, p->HG.p, p->bp0.p, p->bp1.p);
+  BA_LAUNCH(p, KT_GRADNORM, (k_gradient_norm<6, NV_F, 21>), gf, 256, 0, S.nf, p->f_act_ptr.p, p->xf.p, p->sf.p, p->HG.p, p->bp0.p, p->bp1.p);
   BA_TRY(fold(p, p->bp0.p, gf, S_GMAXF, true));
   BA_TRY(fold(p, p->bp1.p, gf, S_G2F));
   BA_CUDA_TRY(cudaGetLastError());
@@ -433,7 +435,7 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   BA_LAUNCH(p, KT_CANDIDATE, (k_candidate<DE>), gce, 256, 0, S.ne, S.e_ptr.p, p->xe.p, p->se.p, p->ye.p, p->xe_c.p, p->bp0.p, p->bp1.p);
   BA_TRY(fold(p, p->bp0.p, gce, S_XE2));
   BA_TRY(fold(p, p->bp1.p, gce, S_DE2));
-  BA_LAUNCH(p, KT_CANDIDATE, (k_candidate<6>), gcf, 256, 0, S.nf, S.fobs_ptr.p, p->xf.p, p->sf.p, p->yf.p, p->xf_c.p, p->bp0.p, p->bp1.p);
+  BA_LAUNCH(p, KT_CANDIDATE, (k_candidate<6>), gcf, 256, 0, S.nf, p->f_act_ptr.p, p->xf.p, p->sf.p, p->yf.p, p->xf_c.p, p->bp0.p, p->bp1.p);
   BA_TRY(fold(p, p->bp0.p, gcf, S_XF2));
   BA_TRY(fold(p, p->bp1.p, gcf, S_DF2));
   BA_CUDA_TRY(cudaGetLastError());
@@ -522,7 +524,7 @@ int lm_begin(ba_cuda_problem* p, const ba_cuda_options& opt) {
   p->rows.clear();
   p->profile = opt.profile_kernels != 0;
   for (int f = 0; f < F_COUNT; ++f) { p->fam_ms[f] = 0.0; p->fam_open[f] = false; }
-  L.Z.num_residuals = S.nb * RD;
+  L.Z.num_residuals = p->nb_global * RD;
   L.Z.rcs_solver_used = p->solver;
   L.radius = opt.initial_trust_region_radius;
   L.decrease_factor = 2.0;
@@ -645,6 +647,41 @@ int count_active(ba_cuda_problem* p, const DVec<int64_t>& ptr, int64_t nblk, int
   int64_t c = 0;
   for (int64_t i = 0; i < nblk; ++i) c += h[i + 1] > h[i] ? 1 : 0;
   *out = c;
+  return BA_OK;
+}
+
+__global__ void k_active_flags(const int64_t* __restrict__ ptr, int64_t n, int32_t* __restrict__ flag) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i <= n) flag[i] = (i < n && ptr[i + 1] > ptr[i]) ? 1 : 0;
+}
+__global__ void k_widen(const int32_t* __restrict__ a, int64_t n, int64_t* __restrict__ b) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) b[i] = a[i];
+}
+
+// Which kept blocks take part in the problem is a GLOBAL property (a camera may have no observation in this
+// rank's shard); the eliminated blocks are owned by exactly one rank, so only their count is summed.
+int build_activity(ba_cuda_problem* p) {
+  const Structure& S = p->S;
+  DVec<int32_t> flag;
+  DVec<int64_t> wide;
+  BA_TRY(flag.alloc(S.nf + 1)); BA_TRY(wide.alloc(S.nf + 1)); BA_TRY(p->f_act_ptr.alloc(S.nf + 1));
+  k_active_flags<<<grid_for(S.nf + 1, 256), 256, 0, p->st>>>(S.fobs_ptr.p, S.nf, flag.p);
+  BA_TRY(allreduce(p, flag.p, S.nf + 1, kNcclMax, kNcclInt32));
+  k_widen<<<grid_for(S.nf + 1, 256), 256, 0, p->st>>>(flag.p, S.nf + 1, wide.p);
+  BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, wide.p, p->f_act_ptr.p, (int)(S.nf + 1), p->st); }));
+  BA_CUDA_TRY(cudaMemcpyAsync(&p->n_active_f_global, p->f_act_ptr.p + S.nf, sizeof(int64_t), cudaMemcpyDeviceToHost, p->st));
+  int64_t cnt[2] = {0, S.nb};
+  BA_TRY(count_active(p, S.e_ptr, S.ne, &cnt[0]));  // synchronises
+  if (p->world > 1) {
+    DVec<int64_t> t;
+    BA_TRY(t.upload(cnt, 2, p->st));
+    BA_TRY(allreduce(p, t.p, 2, kNcclSum, kNcclInt64));
+    BA_CUDA_TRY(cudaMemcpyAsync(cnt, t.p, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, p->st));
+    BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  }
+  p->n_active_e_global = cnt[0];
+  p->nb_global = cnt[1];
   return BA_OK;
 }
 
@@ -908,7 +945,7 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
   p->h_perm.resize(n_obs);
   BA_CUDA_TRY(cudaMemcpy(p->h_perm.data(), p->S.perm.p, sizeof(int32_t) * n_obs, cudaMemcpyDeviceToHost));
   BA_TRY(alloc_workspace(p, 2, 3));
-  return BA_OK;
+  return build_activity(p);
 }
 
 int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32_t n_marker, int64_t n_mobs,
@@ -951,7 +988,7 @@ int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32
   p->h_perm.resize(n_mobs);
   BA_CUDA_TRY(cudaMemcpy(p->h_perm.data(), p->S.perm.p, sizeof(int32_t) * n_mobs, cudaMemcpyDeviceToHost));
   BA_TRY(alloc_workspace(p, 8, 6));
-  return BA_OK;
+  return build_activity(p);
 }
 
 int64_t ba_cuda_num_parameters(const ba_cuda_problem* p) { return p ? p->n_params : 0; }
@@ -1041,9 +1078,7 @@ int ba_cuda_solve_end(ba_cuda_problem* p, ba_cuda_summary* summary) {
   BA_TRY(use_device(p));
   lm_end(p, summary);
   if (summary) {
-    int64_t ae = 0, af = 0;
-    BA_TRY(count_active(p, p->S.e_ptr, p->S.ne, &ae));
-    BA_TRY(count_active(p, p->S.fobs_ptr, p->S.nf, &af));
+    const int64_t ae = p->n_active_e_global, af = p->n_active_f_global;
     summary->num_free_parameters = ae * (p->model == 0 ? 3 : 6) + af * 6;
     summary->rcs_dim = (int32_t)(6 * af);
   }
@@ -1178,7 +1213,7 @@ int ba_cuda_reprojection_error(ba_cuda_problem* p, double* sum_half_sq, double* 
   BA_TRY(fetch_scalars(p));
   BA_CUDA_TRY(cudaEventElapsedTime(&p->last_kernel_ms, p->k0, p->k1));
   const double err = 0.5 * p->h_scal[S_CAND];
-  const double n_points = (double)(p->model == 0 ? p->S.nb : 4 * p->S.nb) * p->world;  // exact for equal shards only
+  const double n_points = (double)(p->model == 0 ? p->nb_global : 4 * p->nb_global);
   if (sum_half_sq) *sum_half_sq = err;
   if (rms_per_coord) *rms_per_coord = std::pow((err * 2.0) / (n_points * 2.0), 0.5);
   return BA_OK;
