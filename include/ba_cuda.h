@@ -258,6 +258,13 @@ int ba_cuda_project_points_error(ba_cuda_problem* p, int64_t n_points, const dou
                                  const float* image_xy, double* sum_half_sq,
                                  double* rms_per_coord, double* reprojected_xy /* opt */);
 
+/* Same, with the rotations given as 3x3 matrices (row-major) the way Main_Calibration's Camera_Transform.xml
+ * stores them (bundle_adjustment_manager.cpp:130; read back at reprojection_check.cpp:65). */
+int ba_cuda_project_points_error_rt(ba_cuda_problem* p, int64_t n_points, const double* xyz,
+                                    const int32_t* cam_of_point, int32_t n_cam, const double* rot9,
+                                    const double* tvec3, const double* intr4, const float* image_xy,
+                                    double* sum_half_sq, double* rms_per_coord, double* reprojected_xy /* opt */);
+
 /* Post-BA outputs of BAManager::Write (bundle_adjustment_manager.cpp:121,135-149)
  * and BALProblem::getPoint3dCoordinates (bundle_adjustment.cpp:89-130), Model B:
  *   rot9    n_cam x 9  Rodrigues(rvec) row-major

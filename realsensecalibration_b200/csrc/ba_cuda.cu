@@ -758,7 +758,7 @@ __global__ void k_rodrigues_cv(const double* __restrict__ rt6, int n, double* __
 // cv::projectPoints with zero distortion, then ((x^ - x)^2 + (y^ - y)^2) / 2 (reprojection_check.cpp:81)
 __global__ void __launch_bounds__(256)
 k_project_error(int64_t n, const double* __restrict__ xyz, const int32_t* __restrict__ cam, const double* __restrict__ R9,
-                const double* __restrict__ rt6, const double* __restrict__ K4, const float* __restrict__ img,
+                const double* __restrict__ t3, const double* __restrict__ K4, const float* __restrict__ img,
                 double* __restrict__ rep, double* __restrict__ partial) {
   __shared__ double sm[32];
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -766,7 +766,7 @@ k_project_error(int64_t n, const double* __restrict__ xyz, const int32_t* __rest
   if (i < n) {
     const int c = cam[i];
     const double* R = R9 + 9 * c;
-    const double* t = rt6 + 6 * c + 3;
+    const double* t = t3 + 3 * c;
     const double X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
     const double x = R[0] * X + R[1] * Y + R[2] * Z + t[0];
     const double y = R[3] * X + R[4] * Y + R[5] * Z + t[1];
@@ -1219,27 +1219,37 @@ int ba_cuda_reprojection_error(ba_cuda_problem* p, double* sum_half_sq, double* 
   return BA_OK;
 }
 
-int ba_cuda_project_points_error(ba_cuda_problem* p, int64_t n_points, const double* xyz, const int32_t* cam_of_point,
-                                 int32_t n_cam, const double* rvec_tvec6, const double* intr4, const float* image_xy,
-                                 double* sum_half_sq, double* rms_per_coord, double* reprojected_xy) {
-  if (!p || n_points < 0 || n_cam < 1 || !rvec_tvec6 || !intr4 || (n_points > 0 && (!xyz || !cam_of_point || !image_xy)))
-    return fail(BA_ERR_INVALID_ARGUMENT, "ba_cuda_project_points_error: bad arguments");
+// shared body: rotations either from rvecs (Rodrigues on the device) or given as matrices
+static int project_points_impl(ba_cuda_problem* p, int64_t n_points, const double* xyz, const int32_t* cam_of_point, int32_t n_cam,
+                               const double* rvec3 /* n_cam x 3 or NULL */, const double* rot9 /* n_cam x 9 or NULL */,
+                               const double* tvec3 /* n_cam x 3 */, const double* intr4, const float* image_xy, double* sum_half_sq,
+                               double* rms_per_coord, double* reprojected_xy) {
   for (int64_t i = 0; i < n_points; ++i)
     if (cam_of_point[i] < 0 || cam_of_point[i] >= n_cam) return fail(BA_ERR_INVALID_ARGUMENT, "point %lld: camera out of range", (long long)i);
   BA_TRY(use_device(p));
   cudaStream_t st = p->st;
-  DVec<double> d_xyz, d_rt, d_K, d_R, d_rep, d_part, d_out;
+  DVec<double> d_xyz, d_rt, d_t, d_K, d_R, d_rep, d_part, d_out;
   DVec<int32_t> d_cam;
   DVec<float> d_img;
   BA_TRY(d_xyz.upload(xyz, 3 * n_points, st)); BA_TRY(d_cam.upload(cam_of_point, n_points, st));
-  BA_TRY(d_img.upload(image_xy, 2 * n_points, st)); BA_TRY(d_rt.upload(rvec_tvec6, 6 * (size_t)n_cam, st));
-  BA_TRY(d_K.upload(intr4, 4 * (size_t)n_cam, st)); BA_TRY(d_R.alloc(9 * (size_t)n_cam));
+  BA_TRY(d_img.upload(image_xy, 2 * n_points, st)); BA_TRY(d_t.upload(tvec3, 3 * (size_t)n_cam, st));
+  BA_TRY(d_K.upload(intr4, 4 * (size_t)n_cam, st));
+  if (rot9) {
+    BA_TRY(d_R.upload(rot9, 9 * (size_t)n_cam, st));
+  } else {
+    std::vector<double> rt(6 * (size_t)n_cam, 0.0);
+    for (int32_t c = 0; c < n_cam; ++c) std::memcpy(&rt[6 * (size_t)c], rvec3 + 3 * (size_t)c, sizeof(double) * 3);
+    BA_TRY(d_rt.upload(rt.data(), rt.size(), st));
+    BA_TRY(d_R.alloc(9 * (size_t)n_cam));
+    BA_LAUNCH(p, KT_MISC, k_rodrigues_cv, grid_for(n_cam, 64), 64, 0, d_rt.p, n_cam, d_R.p, nullptr);
+    BA_CUDA_TRY(cudaStreamSynchronize(st));  // rt (host staging) must outlive the copy
+  }
   const int grid = (int)grid_for(n_points, 256);
   BA_TRY(d_rep.alloc(reprojected_xy ? 2 * n_points : 0)); BA_TRY(d_part.alloc(grid)); BA_TRY(d_out.alloc(1));
-  k_rodrigues_cv<<<grid_for(n_cam, 64), 64, 0, st>>>(d_rt.p, n_cam, d_R.p, nullptr);
   BA_CUDA_TRY(cudaEventRecord(p->k0, st));
-  k_project_error<<<grid, 256, 0, st>>>(n_points, d_xyz.p, d_cam.p, d_R.p, d_rt.p, d_K.p, d_img.p, reprojected_xy ? d_rep.p : nullptr, d_part.p);
-  k_fold_partials<<<1, 1024, 0, st>>>(d_part.p, grid, d_out.p, 0, 0);
+  BA_LAUNCH(p, KT_COST, k_project_error, grid, 256, 0, n_points, d_xyz.p, d_cam.p, d_R.p, d_t.p, d_K.p, d_img.p,
+            reprojected_xy ? d_rep.p : nullptr, d_part.p);
+  BA_LAUNCH(p, KT_FOLD, k_fold_partials, 1, 1024, 0, d_part.p, grid, d_out.p, 0, 0);
   BA_CUDA_TRY(cudaEventRecord(p->k1, st));
   BA_CUDA_TRY(cudaGetLastError());
   double err = 0.0;
@@ -1251,6 +1261,27 @@ int ba_cuda_project_points_error(ba_cuda_problem* p, int64_t n_points, const dou
   if (sum_half_sq) *sum_half_sq = err;
   if (rms_per_coord) *rms_per_coord = std::pow((err * 2.0) / (n_points * 2.0), 0.5);
   return BA_OK;
+}
+
+int ba_cuda_project_points_error(ba_cuda_problem* p, int64_t n_points, const double* xyz, const int32_t* cam_of_point,
+                                 int32_t n_cam, const double* rvec_tvec6, const double* intr4, const float* image_xy,
+                                 double* sum_half_sq, double* rms_per_coord, double* reprojected_xy) {
+  if (!p || n_points < 0 || n_cam < 1 || !rvec_tvec6 || !intr4 || (n_points > 0 && (!xyz || !cam_of_point || !image_xy)))
+    return fail(BA_ERR_INVALID_ARGUMENT, "ba_cuda_project_points_error: bad arguments");
+  std::vector<double> r(3 * (size_t)n_cam), t(3 * (size_t)n_cam);
+  for (int32_t c = 0; c < n_cam; ++c)
+    for (int k = 0; k < 3; ++k) { r[3 * (size_t)c + k] = rvec_tvec6[6 * (size_t)c + k]; t[3 * (size_t)c + k] = rvec_tvec6[6 * (size_t)c + 3 + k]; }
+  return project_points_impl(p, n_points, xyz, cam_of_point, n_cam, r.data(), nullptr, t.data(), intr4, image_xy, sum_half_sq,
+                             rms_per_coord, reprojected_xy);
+}
+
+int ba_cuda_project_points_error_rt(ba_cuda_problem* p, int64_t n_points, const double* xyz, const int32_t* cam_of_point,
+                                    int32_t n_cam, const double* rot9, const double* tvec3, const double* intr4,
+                                    const float* image_xy, double* sum_half_sq, double* rms_per_coord, double* reprojected_xy) {
+  if (!p || n_points < 0 || n_cam < 1 || !rot9 || !tvec3 || !intr4 || (n_points > 0 && (!xyz || !cam_of_point || !image_xy)))
+    return fail(BA_ERR_INVALID_ARGUMENT, "ba_cuda_project_points_error_rt: bad arguments");
+  return project_points_impl(p, n_points, xyz, cam_of_point, n_cam, nullptr, rot9, tvec3, intr4, image_xy, sum_half_sq, rms_per_coord,
+                             reprojected_xy);
 }
 
 int ba_cuda_model_b_outputs(ba_cuda_problem* p, double* rot9, double* inv12, double* corners) {

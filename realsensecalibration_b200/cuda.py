@@ -23,7 +23,7 @@ EXPORTS = [
     "ba_cuda_get_iterations", "ba_cuda_eval", "ba_cuda_last_kernel_ms", "ba_cuda_reprojection_error",
     "ba_cuda_project_points_error", "ba_cuda_model_b_outputs", "ba_cuda_solve_begin", "ba_cuda_solve_iterate",
     "ba_cuda_solve_end", "ba_cuda_set_stream", "ba_cuda_get_kernel_stats", "ba_cuda_num_launches", "ba_cuda_reset_stats",
-    "ba_cuda_save_parameters", "ba_cuda_restore_parameters",
+    "ba_cuda_save_parameters", "ba_cuda_restore_parameters", "ba_cuda_project_points_error_rt",
 ]
 
 
