@@ -91,7 +91,8 @@ typedef struct ba_cuda_options {
   int32_t minimizer_progress_to_stdout;      /* 0 */
   int32_t profile_kernels;                   /* 0; 1 = CUDA-event timing of every kernel family member
                                                 (ba_cuda_get_kernel_stats), costs ~2 us of host time per launch */
-  int32_t reserved0;                         /* 0 */
+  int32_t force_generic_path;                /* 0; 1 = Model A through the generic materialised-Jacobian pipeline
+                                                (the one Model B uses) instead of the fused tile kernels: A/B testing */
   double initial_trust_region_radius;        /* 1e4 */
   double max_trust_region_radius;            /* 1e16 */
   double min_trust_region_radius;            /* 1e-32 */

@@ -21,7 +21,7 @@ class Options(C.Structure):
         ("pcg_residual_reset_period", C.c_int32),
         ("minimizer_progress_to_stdout", C.c_int32),
         ("profile_kernels", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("force_generic_path", C.c_int32),
         ("initial_trust_region_radius", C.c_double),
         ("max_trust_region_radius", C.c_double),
         ("min_trust_region_radius", C.c_double),

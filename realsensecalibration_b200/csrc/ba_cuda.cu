@@ -17,6 +17,7 @@
 #include "ba_kernels.cuh"
 #include "ba_structure.cuh"
 #include "ba_rcs.cuh"
+#include "ba_fused_a.cuh"
 
 using namespace ba;
 
@@ -64,12 +65,13 @@ enum Family { F_JAC = 0, F_SCHUR, F_SOLVE, F_UPDATE, F_COST, F_COLL, F_COUNT };
 // one entry per kernel (family member) of the solve path; names are what ba_cuda_get_kernel_stats() reports
 enum KT {
   KT_TABLES = 0, KT_JAC, KT_COST, KT_FOBS, KT_EM, KT_INCW, KT_DOBS, KT_ECHOL, KT_INCY, KT_FINC, KT_PAIRS, KT_SEGFIN,
-  KT_ASSEMBLE, KT_RCS, KT_BACKSUB, KT_MODELCOST, KT_CANDIDATE, KT_GRADNORM, KT_FOLD, KT_MISC, KT_COUNT
+  KT_ASSEMBLE, KT_RCS, KT_BACKSUB, KT_MODELCOST, KT_CANDIDATE, KT_GRADNORM, KT_FOLD, KT_MISC, KT_FA_P1, KT_FA_RED, KT_FA_P2, KT_COUNT
 };
 const char* const kKtName[KT_COUNT] = {
   "k1_tables", "k1_residual_jacobian", "k5_cost", "k2_fobs_partial", "k2_e_normal", "k2_inc_w", "k2_dobs_partial",
   "k2_e_cholesky", "k2_inc_y", "k2_finc_partial", "k2_pairs_partial", "k2_seg_final", "k2_assemble", "k3_rcs_solve",
-  "k4_backsub", "k4_model_cost", "k4_candidate", "k4_gradient_norm", "fold_partials", "misc"};
+  "k4_backsub", "k4_model_cost", "k4_candidate", "k4_gradient_norm", "fold_partials", "misc",
+  "k1k2_fused_pass1", "k2_reduce_items", "k4k5_fused_pass2"};
 }  // namespace
 
 struct LmState {  // TrustRegionMinimizer's loop variables, kept between ba_cuda_solve_iterate() calls
@@ -78,6 +80,7 @@ struct LmState {  // TrustRegionMinimizer's loop variables, kept between ba_cuda
   double radius = 0.0, decrease_factor = 2.0, x_cost = 0.0, gmax = 0.0, gnorm = 0.0, t_start = 0.0;
   int num_invalid = 0;
   bool began = false, go = false;
+  bool need_linearize = false;  // fused Model A path: the Schur system must be re-formed (new radius after a rejection)
 };
 
 struct ba_cuda_problem {
@@ -106,6 +109,9 @@ struct ba_cuda_problem {
   PcgWork pcg;
   DVec<double> Sb;           // R.nd * 36 block values | nf * 6 rhs correction (one collective covers both)
   int solver = 0;            // ba_rcs_solver resolved for the current solve
+  FusedA FA;                 // Model A: tile structure of the fused two-pass pipeline
+  bool use_fused = false, generic_ws = false;
+  DVec<double> fa_part;      // 7 per-tile partial arrays (cost, g2, gmax, mcc, x2, d2, cand)
   int h_pcg_iters = 0;
   double* h_scal = nullptr;  // pinned
   int* h_status = nullptr;   // pinned
@@ -410,7 +416,7 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   }
   fam_begin(p, F_SOLVE);
   if (pcg) {
-    BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_bsr, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->R.diag.p, p->HG.p, p->vsum(), radius,
+    BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_bsr, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->R.diag.p, p->HG.p, NV_F, p->vsum(), 6, radius,
               opt.min_lm_diagonal, opt.max_lm_diagonal, p->Sb.p, p->rhs.p);
     {
       LaunchScope scope(p, KT_RCS);
@@ -418,7 +424,7 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
     }
     BA_CUDA_TRY(cudaMemcpyAsync(&p->h_pcg_iters, p->pcg.iters.p, sizeof(int), cudaMemcpyDeviceToHost, p->st));
   } else {
-    BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_dense, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->HG.p, p->vsum(), radius, opt.min_lm_diagonal,
+    BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_dense, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->HG.p, NV_F, p->vsum(), 6, radius, opt.min_lm_diagonal,
               opt.max_lm_diagonal, n, p->Sd.p, p->rhs.p);
     LaunchScope scope(p, KT_RCS);
     BA_TRY(launch_chol_solve((int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p, p->st));
@@ -446,6 +452,172 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   if (p->world > 1) BA_TRY(allreduce(p, p->scal.p + S_CAND, 4, kNcclSum));  // S_CAND, S_MCC, S_XE2, S_DE2
   return BA_OK;
 }
+
+// ---- fused Model A path (ba_fused_a.cuh) -------------------------------------------------------------
+FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt) {
+  const Structure& S = p->S;
+  FusedA& F = p->FA;
+  const size_t nt = (size_t)F.n_tiles;
+  FaParams P;
+  P.tile_pt_ptr = F.tile_pt_ptr.p; P.e_ptr = S.e_ptr.p; P.ob_e = S.ob_e.p; P.ob_f = S.ob_f0.p; P.uv = p->uv.p;
+  P.tile_pitem_ptr = F.pairs.tile_item_ptr.p; P.pitem_begin = F.pairs.item_begin.p; P.pitem_end = F.pairs.item_end.p; P.pent = F.pairs.ent.p;
+  P.tile_citem_ptr = F.cams.tile_item_ptr.p; P.citem_begin = F.cams.item_begin.p; P.citem_end = F.cams.item_end.p; P.cent = F.cams.ent.p;
+  P.xe = p->xe.p; P.se = p->se.p; P.tab_f = p->tab_f.p; P.radius = p->scal.p + S_RADIUS;
+  P.min_diag = opt.min_lm_diagonal; P.max_diag = opt.max_lm_diagonal;
+  P.partP = F.partP.p; P.partC = F.partC.p; P.Lz = F.Lz.p; P.se_out = p->se.p;
+  P.cost_partial = p->fa_part.p; P.g2_partial = p->fa_part.p + nt; P.gmax_partial = p->fa_part.p + 2 * nt;
+  P.yf = p->yf.p; P.tabc_f = p->tabc_f.p; P.xe_c = p->xe_c.p;
+  P.mcc_partial = p->fa_part.p + 3 * nt; P.x2_partial = p->fa_part.p + 4 * nt; P.d2_partial = p->fa_part.p + 5 * nt;
+  P.cand_partial = p->fa_part.p + 6 * nt;
+  P.status = p->status.p;
+  return P;
+}
+
+int fa_set_smem_attr() {
+  static bool done = false;
+  if (!done) {
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_CAP * FA_REC * 8));
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_CAP * FA_REC * 8));
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (FA_CAP * FA_REC2 + FA_TPTS * 3) * 8));
+    done = true;
+  }
+  return BA_OK;
+}
+
+int fa_reduce(ba_cuda_problem* p, bool cams, bool pairs) {
+  const Structure& S = p->S;
+  FusedA& F = p->FA;
+  if (cams) {
+    const ItemSet& I = F.cams;
+    if (I.red_ch.n > 0)
+      BA_LAUNCH(p, KT_FA_RED, (k_reduce_items<FA_NVC>), grid_for(I.red_ch.n, 4), 128, 0, I.red_ch.n, I.red_ch.ch, I.red_ch.seg.p, I.red_ch.begin.p,
+                I.tgt_ptr.p, I.red_items.p, F.partC.p, F.red1C.p);
+    BA_LAUNCH(p, KT_FA_RED, (k_reduce_final<FA_NVC>), grid_for(S.nf, 4), 128, 0, (int)S.nf, I.red_ch.seg_first.p, F.red1C.p, F.camacc.p);
+  }
+  if (pairs) {
+    const ItemSet& I = F.pairs;
+    if (I.red_ch.n > 0)
+      BA_LAUNCH(p, KT_FA_RED, (k_reduce_items<36>), grid_for(I.red_ch.n, 4), 128, 0, I.red_ch.n, I.red_ch.ch, I.red_ch.seg.p, I.red_ch.begin.p,
+                I.tgt_ptr.p, I.red_items.p, F.partP.p, F.red1P.p);
+    BA_LAUNCH(p, KT_FA_RED, (k_reduce_final<36>), grid_for(S.ndest, 4), 128, 0, S.ndest, I.red_ch.seg_first.p, F.red1P.p, p->Pacc.p);
+  }
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
+// r, J, cost, gradient norms at x AND the eliminated Schur system for the radius in scal[S_RADIUS]
+// (TrustRegionMinimizer::EvaluateGradientAndJacobian + SchurEliminator::Eliminate in one pass).
+// norms = true: iteration 0, computes the Jacobi scaling only.
+int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms) {
+  const Structure& S = p->S;
+  FusedA& F = p->FA;
+  BA_TRY(fa_set_smem_attr());
+  fam_begin(p, F_JAC);
+  if (norms) {
+    BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.nf * 6, 256), 256, 0, p->sf.p, S.nf * 6, 1.0);
+    BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.ne * 3, 256), 256, 0, p->se.p, S.ne * 3, 1.0);
+  }
+  BA_TRY(build_tables(p, false));
+  const FaParams P = fa_params(p, opt);
+  const int nt = F.n_tiles;
+  if (norms) {
+    BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<true>), nt, FA_THREADS, FA_CAP * FA_REC * 8, P);
+    BA_TRY(fa_reduce(p, true, false));
+    BA_TRY(allreduce(p, F.camacc.p, F.camacc.n, kNcclSum));
+    BA_LAUNCH(p, KT_MISC, (k_jacobi_scale<6, FA_NVC>), grid_for(S.nf * 6, 256), 256, 0, S.nf, F.camacc.p, p->sf.p);
+    BA_CUDA_TRY(cudaGetLastError());
+    fam_end(p, F_JAC);
+    return BA_OK;
+  }
+  BA_CUDA_TRY(cudaMemsetAsync(p->status.p, 0, sizeof(int), p->st));
+  BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<false>), nt, FA_THREADS, FA_CAP * FA_REC * 8, P);
+  {
+    FoldJob J = {{P.cost_partial, P.g2_partial, P.gmax_partial, nullptr}, {S_COST, S_G2E, S_GMAXE, 0}, {0, 0, 1, 0}};
+    BA_LAUNCH(p, KT_FOLD, k_fold_multi, 3, 1024, 0, J, nt, p->scal.p);
+  }
+  fam_end(p, F_JAC);
+  fam_begin(p, F_SCHUR);
+  BA_TRY(fa_reduce(p, true, true));
+  fam_end(p, F_SCHUR);
+  if (p->world > 1) {
+    fam_begin(p, F_COLL);
+    BA_TRY(allreduce(p, F.camacc.p, F.camacc.n, kNcclSum));
+    fam_end(p, F_COLL);
+  }
+  const int gf = (int)grid_for(S.nf * 6, 256);
+  BA_LAUNCH(p, KT_GRADNORM, (k_gradient_norm<6, FA_NVC, 21>), gf, 256, 0, S.nf, p->f_act_ptr.p, p->xf.p, p->sf.p, F.camacc.p, p->bp0.p, p->bp1.p);
+  {
+    FoldJob J = {{p->bp0.p, p->bp1.p, nullptr, nullptr}, {S_GMAXF, S_G2F, 0, 0}, {1, 0, 0, 0}};
+    BA_LAUNCH(p, KT_FOLD, k_fold_multi, 2, 1024, 0, J, gf, p->scal.p);
+  }
+  if (p->world > 1) {
+    BA_TRY(allreduce(p, p->scal.p + S_COST, 2, kNcclSum));  // S_COST, S_G2E
+    BA_TRY(allreduce(p, p->scal.p + S_GMAXE, 1, kNcclMax));
+  }
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
+// RCS assembly + solve + (pass 2) back-substitution, model cost change, candidate and its cost
+int fa_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
+  const Structure& S = p->S;
+  FusedA& F = p->FA;
+  const int64_t n = p->n_rcs();
+  const double* radius = p->scal.p + S_RADIUS;
+  const bool pcg = p->solver == BA_RCS_PCG;
+  fam_begin(p, F_SCHUR);
+  if (pcg) {
+    if (p->world > 1) BA_CUDA_TRY(cudaMemsetAsync(p->Sb.p, 0, p->Sb.bytes(), p->st));
+    BA_LAUNCH(p, KT_ASSEMBLE, k_assemble_bsr, grid_for((int64_t)S.ndest * 36, 256), 256, 0, S.ndest, p->R.l2g.p, p->Pacc.p, nullptr, p->Sb.p);
+  } else {
+    BA_CUDA_TRY(cudaMemsetAsync(p->Sd.p, 0, sizeof(double) * n * n, p->st));
+    BA_LAUNCH(p, KT_ASSEMBLE, k_assemble_dense, grid_for((int64_t)S.ndest * 36, 256), 256, 0, S.ndest, S.dest_fa.p, S.dest_fb.p, p->Pacc.p,
+              nullptr, n, p->Sd.p);
+  }
+  fam_end(p, F_SCHUR);
+  if (p->world > 1) {
+    fam_begin(p, F_COLL);
+    if (pcg) BA_TRY(allreduce(p, p->Sb.p, (size_t)p->R.nd * 36, kNcclSum));
+    else BA_TRY(allreduce(p, p->Sd.p, n * n, kNcclSum));
+    fam_end(p, F_COLL);
+  }
+  fam_begin(p, F_SOLVE);
+  if (pcg) {
+    BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_bsr, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->R.diag.p, F.camacc.p, FA_NVC, F.camacc.p + 27, FA_NVC,
+              radius, opt.min_lm_diagonal, opt.max_lm_diagonal, p->Sb.p, p->rhs.p);
+    {
+      LaunchScope scope(p, KT_RCS);
+      BA_TRY(launch_pcg(p->pcg, p->R, p->Sb.p, p->rhs.p, p->yf.p, p->status.p, opt, p->st));
+    }
+    BA_CUDA_TRY(cudaMemcpyAsync(&p->h_pcg_iters, p->pcg.iters.p, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  } else {
+    BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_dense, grid_for(S.nf * 6, 128), 128, 0, S.nf, F.camacc.p, FA_NVC, F.camacc.p + 27, FA_NVC, radius,
+              opt.min_lm_diagonal, opt.max_lm_diagonal, n, p->Sd.p, p->rhs.p);
+    LaunchScope scope(p, KT_RCS);
+    BA_TRY(launch_chol_solve((int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p, p->st));
+  }
+  fam_end(p, F_SOLVE);
+  fam_begin(p, F_UPDATE);
+  const int gcf = (int)grid_for(S.nf * 6, 256);
+  BA_LAUNCH(p, KT_CANDIDATE, (k_candidate<6>), gcf, 256, 0, S.nf, p->f_act_ptr.p, p->xf.p, p->sf.p, p->yf.p, p->xf_c.p, p->bp0.p, p->bp1.p);
+  {
+    FoldJob J = {{p->bp0.p, p->bp1.p, nullptr, nullptr}, {S_XF2, S_DF2, 0, 0}, {0, 0, 0, 0}};
+    BA_LAUNCH(p, KT_FOLD, k_fold_multi, 2, 1024, 0, J, gcf, p->scal.p);
+  }
+  BA_TRY(build_tables(p, true));
+  const FaParams P = fa_params(p, opt);
+  BA_LAUNCH(p, KT_FA_P2, k_fa_pass2, F.n_tiles, FA_THREADS, (FA_CAP * FA_REC2 + FA_TPTS * 3) * 8, P);
+  {
+    FoldJob J = {{P.mcc_partial, P.x2_partial, P.d2_partial, P.cand_partial}, {S_MCC, S_XE2, S_DE2, S_CAND}, {0, 0, 0, 0}};
+    BA_LAUNCH(p, KT_FOLD, k_fold_multi, 4, 1024, 0, J, F.n_tiles, p->scal.p);
+  }
+  BA_CUDA_TRY(cudaGetLastError());
+  fam_end(p, F_UPDATE);
+  if (p->world > 1) BA_TRY(allreduce(p, p->scal.p + S_CAND, 4, kNcclSum));  // S_CAND, S_MCC, S_XE2, S_DE2
+  return BA_OK;
+}
+
+bool lm_fused(const ba_cuda_problem* p) { return p->model == 0 && p->use_fused && !p->lm.opt.force_generic_path; }
 
 // Resolves options.rcs_solver for this problem and makes sure the matching RCS storage exists.
 // BA_RCS_AUTO: dense Cholesky while the system is rig sized (Ceres DENSE_SCHUR, what the reference asks for),
@@ -530,7 +702,13 @@ int lm_begin(ba_cuda_problem* p, const ba_cuda_options& opt) {
   L.decrease_factor = 2.0;
   L.began = true;
   const double iter_t0 = now_s();
-  BA_TRY((eval_gradient_and_jacobian<RD, DE, GE>(p, true, opt.jacobi_scaling != 0)));
+  if (lm_fused(p)) {
+    if (opt.jacobi_scaling) BA_TRY(fa_linearize(p, opt, true));
+    BA_CUDA_TRY(cudaMemcpyAsync(p->scal.p + S_RADIUS, &L.radius, sizeof(double), cudaMemcpyHostToDevice, p->st));
+    BA_TRY(fa_linearize(p, opt, false));
+  } else {
+    BA_TRY((eval_gradient_and_jacobian<RD, DE, GE>(p, true, opt.jacobi_scaling != 0)));
+  }
   L.Z.num_jacobian_evaluations++;
   BA_TRY(fetch_scalars(p));
   lm_read_gradient(p);
@@ -559,8 +737,14 @@ int lm_iterate(ba_cuda_problem* p, int32_t max_new) {
     const double iter_t0 = now_s();
     std::memset(&row, 0, sizeof(row));
     row.iteration = p->rows.back().iteration + 1;
+    const bool fused = lm_fused(p);
     BA_CUDA_TRY(cudaMemcpyAsync(p->scal.p + S_RADIUS, &L.radius, sizeof(double), cudaMemcpyHostToDevice, p->st));
-    BA_TRY((compute_step<RD, DE, GE, NSLOT>(p, opt)));
+    if (fused) {
+      if (L.need_linearize) { BA_TRY(fa_linearize(p, opt, false)); L.need_linearize = false; }  // same x, new radius
+      BA_TRY(fa_step(p, opt));
+    } else {
+      BA_TRY((compute_step<RD, DE, GE, NSLOT>(p, opt)));
+    }
     Z.num_linear_solves++;
     Z.num_cost_evaluations++;
     BA_TRY(fetch_scalars(p));
@@ -584,6 +768,7 @@ int lm_iterate(ba_cuda_problem* p, int32_t max_new) {
         break;
       }
       L.radius = L.radius / L.decrease_factor; L.decrease_factor *= 2.0;
+      L.need_linearize = true;
       row.cost = L.x_cost; row.cost_change = 0.0;
       row.gradient_max_norm = p->rows.back().gradient_max_norm; row.gradient_norm = p->rows.back().gradient_norm;
       L.go = lm_finalize(p, row, iter_t0);
@@ -610,17 +795,23 @@ int lm_iterate(ba_cuda_problem* p, int32_t max_new) {
     if (row.relative_decrease > opt.min_relative_decrease) {  // HandleSuccessfulStep
       p->xe.swap(p->xe_c);
       p->xf.swap(p->xf_c);
-      BA_TRY((eval_gradient_and_jacobian<RD, DE, GE>(p, false, opt.jacobi_scaling != 0)));
+      L.radius = L.radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * row.relative_decrease - 1.0, 3));
+      L.radius = std::min(opt.max_trust_region_radius, L.radius);
+      L.decrease_factor = 2.0;
+      if (fused) {  // the next step's radius is known: linearize and eliminate in the same pass
+        BA_CUDA_TRY(cudaMemcpyAsync(p->scal.p + S_RADIUS, &L.radius, sizeof(double), cudaMemcpyHostToDevice, p->st));
+        BA_TRY(fa_linearize(p, opt, false));
+      } else {
+        BA_TRY((eval_gradient_and_jacobian<RD, DE, GE>(p, false, opt.jacobi_scaling != 0)));
+      }
       Z.num_jacobian_evaluations++;
       BA_TRY(fetch_scalars(p));
       lm_read_gradient(p);
       row.step_is_successful = 1;
-      L.radius = L.radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * row.relative_decrease - 1.0, 3));
-      L.radius = std::min(opt.max_trust_region_radius, L.radius);
-      L.decrease_factor = 2.0;
       row.cost = L.x_cost; row.gradient_max_norm = L.gmax; row.gradient_norm = L.gnorm;
     } else {  // HandleUnsuccessfulStep
       L.radius = L.radius / L.decrease_factor; L.decrease_factor *= 2.0;
+      L.need_linearize = true;
       row.cost = cand_cost;
     }
     L.go = lm_finalize(p, row, iter_t0);
@@ -685,6 +876,7 @@ int build_activity(ba_cuda_problem* p) {
   return BA_OK;
 }
 
+// buffers every path needs
 int alloc_workspace(ba_cuda_problem* p, int RD, int DE) {
   const Structure& S = p->S;
   const int64_t n = p->n_rcs();
@@ -696,23 +888,34 @@ int alloc_workspace(ba_cuda_problem* p, int RD, int DE) {
   k_fill<<<grid_for(S.ne * DE, 256), 256, 0, st>>>(p->se.p, S.ne * DE, 1.0);
   BA_TRY(p->tab_f.alloc(S.nf * TAB)); BA_TRY(p->tabc_f.alloc(S.nf * TAB));
   if (p->model == 1) { BA_TRY(p->tab_e.alloc(S.ne * TAB)); BA_TRY(p->tabc_e.alloc(S.ne * TAB)); }
+  BA_TRY(p->Pacc.alloc((int64_t)S.ndest * 36)); BA_TRY(p->Qacc.alloc(p->model == 1 ? (int64_t)S.ndest * 36 : 0));
+  p->Sd.release(); p->Sb.release(); p->solver = 0;
+  BA_TRY(p->rhs.alloc(n)); BA_TRY(p->yf.alloc_zero(n, st)); BA_TRY(p->ye.alloc_zero(S.ne * DE, st));
+  const int64_t maxgrid = std::max<int64_t>({(int64_t)grid_for(S.nb * 4, 128), (int64_t)grid_for(S.ne * DE, 256), (int64_t)grid_for(S.nf * 6, 256)}) + 1;
+  BA_TRY(p->bp0.alloc(maxgrid)); BA_TRY(p->bp1.alloc(maxgrid));
+  BA_TRY(p->scal.alloc_zero(S_COUNT, st)); BA_TRY(p->status.alloc_zero(1, st));
+  p->generic_ws = false;
+  BA_CUDA_TRY(cudaStreamSynchronize(st));
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
+// the materialised residual / Jacobian / Schur buffers of the generic pipeline (Model B always; Model A only when the
+// fused path is not used, and for the ba_cuda_eval test hook)
+int ensure_generic_workspace(ba_cuda_problem* p) {
+  if (p->generic_ws) return BA_OK;
+  const Structure& S = p->S;
+  const int RD = p->model == 0 ? 2 : 8, DE = p->model == 0 ? 3 : 6;
   BA_TRY(p->RES.alloc(S.nb * RD)); BA_TRY(p->JE.alloc(S.nb * RD * DE)); BA_TRY(p->JF0.alloc(S.nb * RD * 6));
   BA_TRY(p->JF1.alloc(p->model == 1 ? S.nb * RD * 6 : 0));
   BA_TRY(p->ME.alloc(S.ne * (DE * (DE + 1) / 2 + DE))); BA_TRY(p->HG.alloc(S.nf * NV_F));
   BA_TRY(p->Wt.alloc(p->model == 1 ? S.ninc * 36 : 0));
   BA_TRY(p->Lb.alloc(S.ne * DE * DE)); BA_TRY(p->zb.alloc(S.ne * DE));
   BA_TRY(p->Yt.alloc(S.ninc * DE * 6)); BA_TRY(p->vb.alloc(S.ninc * 6));
-  BA_TRY(p->Pacc.alloc((int64_t)S.ndest * 36)); BA_TRY(p->Qacc.alloc(p->model == 1 ? (int64_t)S.ndest * 36 : 0));
-  p->Sd.release(); p->Sb.release(); p->solver = 0;
-  BA_TRY(p->rhs.alloc(n)); BA_TRY(p->yf.alloc_zero(n, st)); BA_TRY(p->ye.alloc_zero(S.ne * DE, st));
   BA_TRY(p->part_fobs.alloc((int64_t)S.ch_fobs.n * NV_F)); BA_TRY(p->part_finc.alloc((int64_t)S.ch_finc.n * 6));
   BA_TRY(p->part_pairs.alloc((int64_t)S.ch_pairs.n * 36));
   BA_TRY(p->part_dobs.alloc(p->model == 1 ? (int64_t)S.ch_dobs.n * 36 : 0));
-  const int64_t maxgrid = std::max<int64_t>({(int64_t)grid_for(S.nb * 4, 128), (int64_t)grid_for(S.ne * DE, 256), (int64_t)grid_for(S.nf * 6, 256)}) + 1;
-  BA_TRY(p->bp0.alloc(maxgrid)); BA_TRY(p->bp1.alloc(maxgrid));
-  BA_TRY(p->scal.alloc_zero(S_COUNT, st)); BA_TRY(p->status.alloc_zero(1, st));
-  BA_CUDA_TRY(cudaStreamSynchronize(st));
-  BA_CUDA_TRY(cudaGetLastError());
+  p->generic_ws = true;
   return BA_OK;
 }
 
@@ -807,6 +1010,9 @@ void reset_problem(ba_cuda_problem* p) {
   p->xf_s.release(); p->xe_s.release();
   p->R.~RcsPattern();
   new (&p->R) RcsPattern();
+  p->FA.~FusedA();
+  new (&p->FA) FusedA();
+  p->use_fused = false; p->generic_ws = false;
   p->lm.began = false;
   p->S.~Structure();
   new (&p->S) Structure();
@@ -945,6 +1151,13 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
   p->h_perm.resize(n_obs);
   BA_CUDA_TRY(cudaMemcpy(p->h_perm.data(), p->S.perm.p, sizeof(int32_t) * n_obs, cudaMemcpyDeviceToHost));
   BA_TRY(alloc_workspace(p, 2, 3));
+  {  // fused two-pass pipeline when every point has <= FA_KMAX observations, else the generic one
+    const int rc = build_fused_a(p->FA, p->S, p->st);
+    if (rc != BA_OK && rc != BA_ERR_UNSUPPORTED) return rc;
+    p->use_fused = rc == BA_OK;
+    if (p->use_fused) BA_TRY(p->fa_part.alloc((size_t)7 * p->FA.n_tiles));
+    else BA_TRY(ensure_generic_workspace(p));
+  }
   return build_activity(p);
 }
 
@@ -988,6 +1201,8 @@ int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32
   p->h_perm.resize(n_mobs);
   BA_CUDA_TRY(cudaMemcpy(p->h_perm.data(), p->S.perm.p, sizeof(int32_t) * n_mobs, cudaMemcpyDeviceToHost));
   BA_TRY(alloc_workspace(p, 8, 6));
+  p->use_fused = false;
+  BA_TRY(ensure_generic_workspace(p));
   return build_activity(p);
 }
 
@@ -1060,6 +1275,7 @@ int ba_cuda_solve_begin(ba_cuda_problem* p, const ba_cuda_options* options) {
   ba_cuda_options opt;
   if (options) opt = *options; else ba_cuda_options_init(&opt);
   BA_TRY(prepare_solver(p, opt));
+  if (p->model == 0 && (opt.force_generic_path || !p->use_fused)) BA_TRY(ensure_generic_workspace(p));
   return p->model == 0 ? lm_begin<2, 3, 1, 1>(p, opt) : lm_begin<8, 6, 32, 2>(p, opt);
 }
 
@@ -1162,6 +1378,7 @@ int ba_cuda_eval(ba_cuda_problem* p, double* cost, double* residuals, double* ja
   BA_TRY(use_device(p));
   const Structure& S = p->S;
   const int RD = p->model == 0 ? 2 : 8, DE = p->model == 0 ? 3 : 6;
+  BA_TRY(ensure_generic_workspace(p));
   BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.ne * DE, 256), 256, 0, p->se.p, S.ne * DE, 1.0);
   BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.nf * 6, 256), 256, 0, p->sf.p, S.nf * 6, 1.0);
   BA_TRY(build_tables(p, false));  // warm the tables outside the timed kernel

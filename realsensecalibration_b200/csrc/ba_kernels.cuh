@@ -665,21 +665,21 @@ __global__ void k_assemble_dense(int ndest, const int32_t* __restrict__ dest_fa,
 }
 
 // After the (optional) cross-GPU sum: add F^T F diagonal blocks and the LM diagonal D_f^2, form the rhs.
-__global__ void k_diag_rhs_dense(int64_t nf, const double* __restrict__ HG, const double* __restrict__ vsum,
-                                 const double* __restrict__ radius_p, double min_diag, double max_diag, int64_t n,
+__global__ void k_diag_rhs_dense(int64_t nf, const double* __restrict__ HG, int hg_stride, const double* __restrict__ vsum,
+                                 int v_stride, const double* __restrict__ radius_p, double min_diag, double max_diag, int64_t n,
                                  double* __restrict__ S, double* __restrict__ rhs) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= nf * 6) return;
   const int64_t f = t / 6;
   const int a = (int)(t % 6);
-  const double* H = HG + f * NV_F;
+  const double* H = HG + f * hg_stride;
 #pragma unroll
   for (int b = 0; b < 6; ++b) {
     double h = H[a <= b ? sym_idx6(a, b) : sym_idx6(b, a)];
     if (a == b) { const double d = sqrt(fmin(fmax(h, min_diag), max_diag) / *radius_p); h += d * d; }
     S[(6 * f + a) * n + 6 * f + b] += h;
   }
-  rhs[t] = H[21 + a] - vsum[t];
+  rhs[t] = H[21 + a] - vsum[f * v_stride + a];
 }
 
 // ---------------------------------------------------------------------------------------

@@ -80,14 +80,14 @@ __global__ void k_assemble_bsr(int ndest, const int32_t* __restrict__ l2g, const
   Sb[(int64_t)l2g[d] * 36 + q] = (Q ? Q[t] : 0.0) - P[t];
 }
 
-__global__ void k_diag_rhs_bsr(int64_t nf, const int32_t* __restrict__ diag, const double* __restrict__ HG, const double* __restrict__ vsum,
-                               const double* __restrict__ radius_p, double min_diag, double max_diag, double* __restrict__ Sb,
+__global__ void k_diag_rhs_bsr(int64_t nf, const int32_t* __restrict__ diag, const double* __restrict__ HG, int hg_stride,
+                               const double* __restrict__ vsum, int v_stride, const double* __restrict__ radius_p, double min_diag, double max_diag, double* __restrict__ Sb,
                                double* __restrict__ rhs) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= nf * 6) return;
   const int64_t f = t / 6;
   const int a = (int)(t % 6);
-  const double* H = HG + f * NV_F;
+  const double* H = HG + f * hg_stride;
   double* B = Sb + (int64_t)diag[f] * 36;
 #pragma unroll
   for (int b = 0; b < 6; ++b) {
@@ -95,7 +95,7 @@ __global__ void k_diag_rhs_bsr(int64_t nf, const int32_t* __restrict__ diag, con
     if (a == b) { const double d = sqrt(fmin(fmax(h, min_diag), max_diag) / *radius_p); h += d * d; }
     B[a * 6 + b] += h;
   }
-  rhs[t] = H[21 + a] - vsum[t];
+  rhs[t] = H[21 + a] - vsum[f * v_stride + a];
 }
 
 struct PcgParams {
