@@ -459,7 +459,8 @@ FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt) {
   FusedA& F = p->FA;
   const size_t nt = (size_t)F.n_tiles;
   FaParams P;
-  P.tile_pt_ptr = F.tile_pt_ptr.p; P.e_ptr = S.e_ptr.p; P.ob_e = S.ob_e.p; P.ob_f = S.ob_f0.p; P.uv = p->uv.p;
+  P.tile_pt_ptr = F.tile_pt_ptr.p; P.e_ptr = S.e_ptr.p; P.ob_e = S.ob_e.p; P.ob_f = S.ob_f0.p; P.ob_slot = F.ob_slot.p; P.uv = p->uv.p;
+  P.tile_cam_ptr = F.cams.tile_group_ptr.p; P.tile_cams = F.cams.group_target.p; P.cap = F.cap;
   P.tile_pitem_ptr = F.pairs.tile_item_ptr.p; P.pitem_begin = F.pairs.item_begin.p; P.pitem_end = F.pairs.item_end.p; P.pent = F.pairs.ent.p;
   P.tile_citem_ptr = F.cams.tile_item_ptr.p; P.citem_begin = F.cams.item_begin.p; P.citem_end = F.cams.item_end.p; P.cent = F.cams.ent.p;
   P.xe = p->xe.p; P.se = p->se.p; P.tab_f = p->tab_f.p; P.radius = p->scal.p + S_RADIUS;
@@ -476,9 +477,10 @@ FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt) {
 int fa_set_smem_attr() {
   static bool done = false;
   if (!done) {
-    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_CAP * FA_REC * 8));
-    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_CAP * FA_REC * 8));
-    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (FA_CAP * FA_REC2 + FA_TPTS * 3) * 8));
+    const int kMax = 200 * 1024;  // dynamic part; the kernels also hold a little static shared memory
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     done = true;
   }
   return BA_OK;
@@ -521,7 +523,7 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms) {
   const FaParams P = fa_params(p, opt);
   const int nt = F.n_tiles;
   if (norms) {
-    BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<true>), nt, FA_THREADS, FA_CAP * FA_REC * 8, P);
+    BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<true>), nt, FA_THREADS, F.smem1(), P);
     BA_TRY(fa_reduce(p, true, false));
     BA_TRY(allreduce(p, F.camacc.p, F.camacc.n, kNcclSum));
     BA_LAUNCH(p, KT_MISC, (k_jacobi_scale<6, FA_NVC>), grid_for(S.nf * 6, 256), 256, 0, S.nf, F.camacc.p, p->sf.p);
@@ -530,7 +532,7 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms) {
     return BA_OK;
   }
   BA_CUDA_TRY(cudaMemsetAsync(p->status.p, 0, sizeof(int), p->st));
-  BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<false>), nt, FA_THREADS, FA_CAP * FA_REC * 8, P);
+  BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<false>), nt, FA_THREADS, F.smem1(), P);
   {
     FoldJob J = {{P.cost_partial, P.g2_partial, P.gmax_partial, nullptr}, {S_COST, S_G2E, S_GMAXE, 0}, {0, 0, 1, 0}};
     BA_LAUNCH(p, KT_FOLD, k_fold_multi, 3, 1024, 0, J, nt, p->scal.p);
@@ -606,7 +608,7 @@ int fa_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   }
   BA_TRY(build_tables(p, true));
   const FaParams P = fa_params(p, opt);
-  BA_LAUNCH(p, KT_FA_P2, k_fa_pass2, F.n_tiles, FA_THREADS, (FA_CAP * FA_REC2 + FA_TPTS * 3) * 8, P);
+  BA_LAUNCH(p, KT_FA_P2, k_fa_pass2, F.n_tiles, FA_THREADS, F.smem2(), P);
   {
     FoldJob J = {{P.mcc_partial, P.x2_partial, P.d2_partial, P.cand_partial}, {S_MCC, S_XE2, S_DE2, S_CAND}, {0, 0, 0, 0}};
     BA_LAUNCH(p, KT_FOLD, k_fold_multi, 4, 1024, 0, J, F.n_tiles, p->scal.p);
@@ -1333,6 +1335,11 @@ static double algorithmic_bytes(const ba_cuda_problem* p, int kt) {
     case KT_PAIRS: return (double)S.npairs * (8.0 + (A ? 288.0 : 576.0)) + (double)S.ndest * 288.0;
     case KT_BACKSUB: return A ? ninc * (144.0 + 4.0) + ne * 120.0 : ninc * (288.0 + 4.0) + ne * 384.0;
     case KT_MODELCOST: return A ? nb * (160.0 + 8.0) + ne * 24.0 : nb * (1216.0 + 12.0) + ne * 48.0;
+    // fused Model A passes, accounted with the bytes of the materialised layout they replace:
+    // pass 1 = K1 (184 B/obs) + K2 (168 B/obs read, 72 B/point, 336 B/camera, 288 B/stored block written)
+    case KT_FA_P1: return nb * (184.0 + 168.0) + ne * (24.0 + 72.0) + nf * (80.0 + 336.0) + (double)S.ndest * 288.0;
+    // pass 2 = K4 (152 B/obs + 72 B/point read, 24 B/point + 48 B/camera written) + cost-only evaluation (24 B/obs)
+    case KT_FA_P2: return nb * (152.0 + 24.0) + ne * (72.0 + 24.0 + 24.0) + nf * (48.0 + 80.0);
     default: return 0.0;
   }
 }

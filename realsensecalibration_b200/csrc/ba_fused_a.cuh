@@ -6,13 +6,16 @@
 // Jacobian of an observation (~150 flops) is cheaper than re-reading its 160 bytes, and the Schur complement's
 // pair products are the only heavy arithmetic.  So:
 //
-//   pass 1  k_fa_pass1   per tile of points (<= 448 observations, <= 256 points):
+//   pass 1  k_fa_pass1   per tile of points (a window of ~256 observations, <= 128 points):
+//             A0  the tile's camera tables -> shared memory (SoA, conflict free)
 //             A1  one thread per observation: r, J_e, J_f in registers -> shared memory
-//             A2  one thread per point: E^T E, E^T r, LM diagonal, 3x3 Cholesky in registers, z = L^-1 E^T r,
-//                 U_i = L^-1 J_e,i^T per observation (shared memory), L and z -> HBM (72 B / point)
+//             A2  one thread per point: E^T E, E^T r, LM diagonal, 3x3 Cholesky in registers, z = L^-1 E^T r
+//                 (L, 1/diag, z -> shared memory and HBM, 72 B / point); then one thread per observation:
+//                 U_i = L^-1 J_e,i^T, w_i = U_i^T z
 //             B   one thread per WORK ITEM (a fixed list of <= 16 observation pairs of one camera pair, or
-//                 <= 32 observations of one camera, all inside the tile): operands from shared memory, 36 resp.
-//                 33 accumulators in registers, one partial block -> HBM
+//                 <= 4 observations of one camera, all inside the tile; items sorted by length and dealt
+//                 boustrophedon so that the lanes of a warp run equally long loops): operands from shared
+//                 memory, 36 resp. 33 accumulators in registers, one partial block -> HBM
 //   reduce  k_reduce_items   fixed-order sum of the partial blocks per camera pair / camera (two levels)
 //   pass 2  k_fa_pass2   per tile: r, J again, back-substitution, Ceres' model cost change, candidate point,
 //                        candidate cost -- one pass instead of four
@@ -27,22 +30,23 @@
 
 namespace ba {
 
-constexpr int FA_TOBS = 384;                 // observation window of a tile
+constexpr int FA_TOBS_DEFAULT = 256;         // observation window of a tile (BA_FA_TOBS overrides, for tuning)
 constexpr int FA_KMAX = 64;                  // max observations of one point (fused path)
-constexpr int FA_CAP = FA_TOBS + FA_KMAX;    // shared-memory capacity in observations
-constexpr int FA_TPTS = 256;                 // max points of a tile
+constexpr int FA_TPTS = 128;                 // max points of a tile
+constexpr int FA_TCAM = 48;                  // camera tables staged in shared memory per tile (more: read from L2)
 constexpr int FA_CH_PAIR = 16;               // pairs per pair item
-constexpr int FA_CH_CAM = 32;                // observations per camera item
+constexpr int FA_CH_CAM = 4;                 // observations per camera item
 constexpr int FA_CH_RED = 64;                // partial blocks per first-level reduction chunk
 constexpr int FA_NVC = 33;                   // per camera: 21 packed upper F^T F | 6 F^T r | 6 sum of v_i
-constexpr int FA_THREADS = 128;               // 2 CTAs of 128 threads per SM: up to 255 registers for the 6x6 accumulators
-constexpr int FA_REC = 22;                    // doubles per observation record in shared memory (pass 1)
-constexpr int FA_REC2 = 10;                   // pass 2
+constexpr int FA_THREADS = 128;
+constexpr int FA_REC = 22;                   // doubles per observation record in shared memory (pass 1)
+constexpr int FA_REC2 = 10;                  // pass 2
+constexpr int FA_LS = 10;                    // per point in shared memory: L10 L20 L21 | 1/L00 1/L11 1/L22 | z (3) | pad
 
 // work items of one kind (pair items or camera items) and the static reduction lists over their partial blocks
 struct ItemSet {
   int64_t n_ent = 0;
-  int n_items = 0, n_targets = 0;
+  int n_items = 0, n_targets = 0, n_groups = 0;
   DVec<int32_t> ent;            // sorted entries (pair: li | lj << 16 ; camera: li)
   DVec<int64_t> item_begin;     // n_items
   DVec<int64_t> item_end;       // n_items
@@ -51,22 +55,29 @@ struct ItemSet {
   DVec<int32_t> red_items;      // item ids grouped by target (stable)
   DVec<int64_t> tgt_ptr;        // n_targets + 1 into red_items
   Chunks red_ch;                // chunks over tgt_ptr
+  // groups = distinct (tile, target)
+  DVec<int64_t> group_ptr;      // n_groups + 1 into ent
+  DVec<int32_t> group_target;   // n_groups
+  DVec<int64_t> tile_group_ptr; // n_tiles + 1
 };
 
 struct FusedA {
   bool ready = false;
-  int n_tiles = 0;
+  int n_tiles = 0, tobs = FA_TOBS_DEFAULT, kmax = 0, cap = 0;
   DVec<int64_t> tile_pt_ptr;    // n_tiles + 1
   ItemSet pairs, cams;
+  DVec<uint16_t> ob_slot;       // per observation: slot of its camera in the tile's camera list
   DVec<double> partP, partC, red1P, red1C, camacc, Lz;
+  size_t smem1() const { return ((size_t)cap * FA_REC + FA_TPTS * FA_LS + FA_TCAM * TAB) * 8 + (size_t)cap * 2; }
+  size_t smem2() const { return ((size_t)cap * FA_REC2 + FA_TPTS * 3 + FA_TCAM * (TAB + 16)) * 8; }
 };
 
-__global__ void k_fa_tile_flags(const int64_t* __restrict__ e_ptr, int64_t ne, int32_t* __restrict__ flag, int* __restrict__ too_wide) {
+__global__ void k_fa_tile_flags(const int64_t* __restrict__ e_ptr, int64_t ne, int tobs, int32_t* __restrict__ flag, int* __restrict__ kmax) {
   const int64_t pt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (pt >= ne) return;
-  if (e_ptr[pt + 1] - e_ptr[pt] > FA_KMAX) atomicOr(too_wide, 1);
+  atomicMax(kmax, (int)min(e_ptr[pt + 1] - e_ptr[pt], (int64_t)INT32_MAX));
   int f = 0;
-  if (pt > 0) f = (e_ptr[pt] / FA_TOBS != e_ptr[pt - 1] / FA_TOBS) || (pt / FA_TPTS != (pt - 1) / FA_TPTS);
+  if (pt > 0) f = (e_ptr[pt] / tobs != e_ptr[pt - 1] / tobs) || (pt / FA_TPTS != (pt - 1) / FA_TPTS);
   flag[pt] = f;
 }
 
@@ -97,24 +108,60 @@ __global__ void k_fa_cam_fill(const int32_t* __restrict__ ob_e, const int32_t* _
   keys[o] = (uint64_t)tile * (uint64_t)nf + (uint64_t)ob_f[o];
   vals[o] = (int32_t)(o - e_ptr[tile_pt_ptr[tile]]);
 }
+__global__ void k_fa_group_meta(int ng, const uint64_t* __restrict__ group_key, uint64_t n_targets, int32_t* __restrict__ group_target,
+                                int32_t* __restrict__ group_tile) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  group_target[g] = (int32_t)(group_key[g] % n_targets);
+  group_tile[g] = (int32_t)(group_key[g] / n_targets);
+}
+// per item: end, target, and the key (tile, descending length) the items are re-ordered by
 __global__ void k_fa_item_meta(int n_items, const int32_t* __restrict__ seg, const int64_t* __restrict__ begin, int ch,
-                               const int64_t* __restrict__ group_ptr, const uint64_t* __restrict__ group_key, uint64_t n_targets,
-                               int64_t* __restrict__ item_end, int32_t* __restrict__ item_target, int32_t* __restrict__ item_tile) {
+                               const int64_t* __restrict__ group_ptr, const int32_t* __restrict__ group_target,
+                               const int32_t* __restrict__ group_tile, int64_t* __restrict__ item_end, int32_t* __restrict__ item_target,
+                               uint64_t* __restrict__ sort_key) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_items) return;
   const int g = seg[i];
-  item_end[i] = min(begin[i] + ch, group_ptr[g + 1]);
-  item_target[i] = (int32_t)(group_key[g] % n_targets);
-  item_tile[i] = (int32_t)(group_key[g] / n_targets);
+  const int64_t end = min(begin[i] + ch, group_ptr[g + 1]);
+  item_end[i] = end;
+  item_target[i] = group_target[g];
+  sort_key[i] = (uint64_t)group_tile[g] * 64u + (uint64_t)(63 - min((int)(end - begin[i]), 63));
+}
+template <typename T>
+__global__ void k_fa_gather(const T* __restrict__ src, const int32_t* __restrict__ perm, int n, T* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[perm[i]];
+}
+__global__ void k_fa_key_tile(const uint64_t* __restrict__ key, int n, int32_t* __restrict__ tile) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tile[i] = (int32_t)(key[i] / 64u);
+}
+__global__ void k_fa_group_tile(int n_tiles, const int64_t* __restrict__ tile_group_ptr, int32_t* __restrict__ group_tile) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  for (int64_t g = tile_group_ptr[t]; g < tile_group_ptr[t + 1]; ++g) group_tile[g] = t;
+}
+// slot of every observation's camera inside its tile's camera list (= rank of its (tile, camera) group in the tile)
+__global__ void k_fa_ob_slot(int ng, const int64_t* __restrict__ group_ptr, const int32_t* __restrict__ group_tile,
+                             const int64_t* __restrict__ tile_group_ptr, const int32_t* __restrict__ ent, const int64_t* __restrict__ e_ptr,
+                             const int64_t* __restrict__ tile_pt_ptr, uint16_t* __restrict__ ob_slot) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  const int tile = group_tile[g];
+  const int64_t ob0 = e_ptr[tile_pt_ptr[tile]];
+  const uint16_t slot = (uint16_t)min((int64_t)65535, (int64_t)g - tile_group_ptr[tile]);
+  for (int64_t q = group_ptr[g]; q < group_ptr[g + 1]; ++q) ob_slot[ob0 + ent[q]] = slot;
 }
 
-// keys (tile * n_targets + target) with their entries -> sorted entries, items of <= ch entries, reduction lists
+// keys (tile * n_targets + target) with their entries -> sorted entries, groups, items of <= ch entries ordered by
+// (tile, descending length), reduction lists
 inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, int64_t n, int n_tiles, int64_t n_targets, int ch,
                        cudaStream_t st) {
   I.n_ent = n; I.n_targets = (int)n_targets;
   DVec<uint64_t> ks, gkey;
-  DVec<int64_t> gcnt, gptr;
-  DVec<int32_t> nruns;
+  DVec<int64_t> gcnt;
+  DVec<int32_t> nruns, group_tile;
   BA_TRY(ks.alloc(n)); BA_TRY(I.ent.alloc(n));
   if (n > 0)
     BA_TRY(cub_call([&](void* t, size_t& b) {
@@ -129,22 +176,36 @@ inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, in
     BA_CUDA_TRY(cudaStreamSynchronize(st));
   }
   ks.release();
-  BA_TRY(gptr.alloc(ng + 1));
+  I.n_groups = ng;
+  BA_TRY(I.group_ptr.alloc(ng + 1)); BA_TRY(I.group_target.alloc(ng)); BA_TRY(group_tile.alloc(ng));
   BA_CUDA_TRY(cudaMemsetAsync(gcnt.p + ng, 0, sizeof(int64_t), st));
-  BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, gcnt.p, gptr.p, ng + 1, st); }));
+  BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, gcnt.p, I.group_ptr.p, ng + 1, st); }));
+  k_fa_group_meta<<<grid_for(ng, 256), 256, 0, st>>>(ng, gkey.p, (uint64_t)n_targets, I.group_target.p, group_tile.p);
+  BA_TRY(I.tile_group_ptr.alloc((size_t)n_tiles + 1));
+  k_seg_ptr<int32_t><<<grid_for(ng > n_tiles + 1 ? ng : n_tiles + 1, 256), 256, 0, st>>>(group_tile.p, ng, n_tiles, I.tile_group_ptr.p);
   Chunks C;
-  BA_TRY(build_chunks(C, gptr.p, ng, ch, st));
-  I.n_items = C.n;
-  BA_TRY(I.item_end.alloc(C.n)); BA_TRY(I.item_target.alloc(C.n));
-  DVec<int32_t> item_tile, iota;
-  BA_TRY(item_tile.alloc(C.n)); BA_TRY(iota.alloc(C.n));
-  k_fa_item_meta<<<grid_for(C.n, 256), 256, 0, st>>>(C.n, C.seg.p, C.begin.p, ch, gptr.p, gkey.p, (uint64_t)n_targets, I.item_end.p,
-                                                     I.item_target.p, item_tile.p);
-  I.item_begin.swap(C.begin);
+  BA_TRY(build_chunks(C, I.group_ptr.p, ng, ch, st));
+  const int ni = C.n;
+  I.n_items = ni;
+  DVec<int64_t> end0;
+  DVec<int32_t> tgt0, perm, iota, item_tile;
+  DVec<uint64_t> skey, skey_sorted;
+  BA_TRY(end0.alloc(ni)); BA_TRY(tgt0.alloc(ni)); BA_TRY(skey.alloc(ni)); BA_TRY(skey_sorted.alloc(ni)); BA_TRY(perm.alloc(ni));
+  BA_TRY(iota.alloc(ni)); BA_TRY(item_tile.alloc(ni));
+  k_fa_item_meta<<<grid_for(ni, 256), 256, 0, st>>>(ni, C.seg.p, C.begin.p, ch, I.group_ptr.p, I.group_target.p, group_tile.p, end0.p, tgt0.p, skey.p);
+  k_iota<<<grid_for(ni, 256), 256, 0, st>>>(iota.p, ni, 0);
+  if (ni > 0)
+    BA_TRY(cub_call([&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, skey.p, skey_sorted.p, iota.p, perm.p, ni, 0, bits_for((uint64_t)n_tiles * 64u), st);
+    }));
+  BA_TRY(I.item_begin.alloc(ni)); BA_TRY(I.item_end.alloc(ni)); BA_TRY(I.item_target.alloc(ni));
+  k_fa_gather<int64_t><<<grid_for(ni, 256), 256, 0, st>>>(C.begin.p, perm.p, ni, I.item_begin.p);
+  k_fa_gather<int64_t><<<grid_for(ni, 256), 256, 0, st>>>(end0.p, perm.p, ni, I.item_end.p);
+  k_fa_gather<int32_t><<<grid_for(ni, 256), 256, 0, st>>>(tgt0.p, perm.p, ni, I.item_target.p);
+  k_fa_key_tile<<<grid_for(ni, 256), 256, 0, st>>>(skey_sorted.p, ni, item_tile.p);
   BA_TRY(I.tile_item_ptr.alloc((size_t)n_tiles + 1));
-  k_seg_ptr<int32_t><<<grid_for(C.n > n_tiles + 1 ? C.n : n_tiles + 1, 256), 256, 0, st>>>(item_tile.p, C.n, n_tiles, I.tile_item_ptr.p);
-  k_iota<<<grid_for(C.n, 256), 256, 0, st>>>(iota.p, C.n, 0);
-  BA_TRY(sort_to_csr(I.item_target.p, iota.p, C.n, n_targets, I.tgt_ptr, I.red_items, st));
+  k_seg_ptr<int32_t><<<grid_for(ni > n_tiles + 1 ? ni : n_tiles + 1, 256), 256, 0, st>>>(item_tile.p, ni, n_tiles, I.tile_item_ptr.p);
+  BA_TRY(sort_to_csr(I.item_target.p, iota.p, ni, n_targets, I.tgt_ptr, I.red_items, st));
   BA_TRY(build_chunks(I.red_ch, I.tgt_ptr.p, (int)n_targets, FA_CH_RED, st));
   BA_CUDA_TRY(cudaStreamSynchronize(st));
   BA_CUDA_TRY(cudaGetLastError());
@@ -157,16 +218,19 @@ inline int build_fused_a(FusedA& F, const Structure& S, cudaStream_t st) {
   F.ready = false;
   const int64_t ne = S.ne, nb = S.nb, nf = S.nf;
   if (ne == 0 || nb == 0 || S.nslots != 1) return BA_ERR_UNSUPPORTED;
+  F.tobs = FA_TOBS_DEFAULT;
+  if (const char* env = std::getenv("BA_FA_TOBS")) { const int v = std::atoi(env); if (v >= 64 && v <= 1024) F.tobs = v; }
   DVec<int32_t> flag, tile_of_pt;
-  DVec<int> wide;
-  BA_TRY(flag.alloc(ne)); BA_TRY(tile_of_pt.alloc(ne)); BA_TRY(wide.alloc_zero(1, st));
-  k_fa_tile_flags<<<grid_for(ne, 256), 256, 0, st>>>(S.e_ptr.p, ne, flag.p, wide.p);
+  DVec<int> kmax;
+  BA_TRY(flag.alloc(ne)); BA_TRY(tile_of_pt.alloc(ne)); BA_TRY(kmax.alloc_zero(1, st));
+  k_fa_tile_flags<<<grid_for(ne, 256), 256, 0, st>>>(S.e_ptr.p, ne, F.tobs, flag.p, kmax.p);
   BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::InclusiveSum(t, b, flag.p, tile_of_pt.p, (int)ne, st); }));
-  int h_wide = 0, last_tile = 0;
-  BA_CUDA_TRY(cudaMemcpyAsync(&h_wide, wide.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  int last_tile = 0;
+  BA_CUDA_TRY(cudaMemcpyAsync(&F.kmax, kmax.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   BA_CUDA_TRY(cudaMemcpyAsync(&last_tile, tile_of_pt.p + (ne - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   BA_CUDA_TRY(cudaStreamSynchronize(st));
-  if (h_wide) return BA_ERR_UNSUPPORTED;
+  if (F.kmax > FA_KMAX) return BA_ERR_UNSUPPORTED;
+  F.cap = F.tobs + F.kmax;
   F.n_tiles = last_tile + 1;
   BA_TRY(F.tile_pt_ptr.alloc((size_t)F.n_tiles + 1));
   k_seg_ptr<int32_t><<<grid_for(ne > F.n_tiles + 1 ? ne : F.n_tiles + 1, 256), 256, 0, st>>>(tile_of_pt.p, ne, F.n_tiles, F.tile_pt_ptr.p);
@@ -187,13 +251,19 @@ inline int build_fused_a(FusedA& F, const Structure& S, cudaStream_t st) {
                                                       S.ndest, keys.p, vals.p);
     BA_TRY(build_items(F.pairs, keys, vals, np, F.n_tiles, S.ndest, FA_CH_PAIR, st));
   }
-  // camera items
+  // camera items, the tile camera lists and the per-observation camera slot
   {
     DVec<uint64_t> keys;
-    DVec<int32_t> vals;
+    DVec<int32_t> vals, group_tile;
     BA_TRY(keys.alloc(nb)); BA_TRY(vals.alloc(nb));
     k_fa_cam_fill<<<grid_for(nb, 256), 256, 0, st>>>(S.ob_e.p, S.ob_f0.p, nb, nf, S.e_ptr.p, tile_of_pt.p, F.tile_pt_ptr.p, keys.p, vals.p);
     BA_TRY(build_items(F.cams, keys, vals, nb, F.n_tiles, nf, FA_CH_CAM, st));
+    const int ng = F.cams.n_groups;
+    BA_TRY(group_tile.alloc(ng)); BA_TRY(F.ob_slot.alloc(nb));
+    // group -> tile from the tile_group_ptr CSR (groups are tile-major)
+    k_fa_group_tile<<<grid_for(F.n_tiles, 256), 256, 0, st>>>(F.n_tiles, F.cams.tile_group_ptr.p, group_tile.p);
+    k_fa_ob_slot<<<grid_for(ng, 256), 256, 0, st>>>(ng, F.cams.group_ptr.p, group_tile.p, F.cams.tile_group_ptr.p, F.cams.ent.p, S.e_ptr.p,
+                                                    F.tile_pt_ptr.p, F.ob_slot.p);
   }
   BA_TRY(F.partP.alloc((size_t)F.pairs.n_items * 36)); BA_TRY(F.partC.alloc((size_t)F.cams.n_items * FA_NVC));
   BA_TRY(F.red1P.alloc((size_t)F.pairs.red_ch.n * 36)); BA_TRY(F.red1C.alloc((size_t)F.cams.red_ch.n * FA_NVC));
@@ -229,11 +299,39 @@ __device__ __forceinline__ void fa_linearize(const double* __restrict__ T, const
   je[3] = (cc * T[3] + dd * T[6]) * s[0]; je[4] = (cc * T[4] + dd * T[7]) * s[1]; je[5] = (cc * T[5] + dd * T[8]) * s[2];
 }
 
+// 3x3 Cholesky with reciprocal diagonal: Lp = {L10, L20, L21, 1/L00, 1/L11, 1/L22}; M symmetric, upper part read
+__device__ __forceinline__ bool fa_chol3(const double* M /* m00 m01 m02 m11 m12 m22 */, double* Lp) {
+  const double d0 = M[0];
+  if (!(d0 > 0.0) || !isfinite(d0)) return false;
+  const double i0 = 1.0 / sqrt(d0);
+  const double l10 = M[1] * i0, l20 = M[2] * i0;
+  const double d1 = M[3] - l10 * l10;
+  if (!(d1 > 0.0) || !isfinite(d1)) return false;
+  const double i1 = 1.0 / sqrt(d1);
+  const double l21 = (M[4] - l20 * l10) * i1;
+  const double d2 = M[5] - l20 * l20 - l21 * l21;
+  if (!(d2 > 0.0) || !isfinite(d2)) return false;
+  Lp[0] = l10; Lp[1] = l20; Lp[2] = l21; Lp[3] = i0; Lp[4] = i1; Lp[5] = 1.0 / sqrt(d2);
+  return true;
+}
+__device__ __forceinline__ void fa_fwd3(const double* Lp, double* x) {  // x <- L^-1 x
+  x[0] *= Lp[3];
+  x[1] = (x[1] - Lp[0] * x[0]) * Lp[4];
+  x[2] = (x[2] - Lp[1] * x[0] - Lp[2] * x[1]) * Lp[5];
+}
+__device__ __forceinline__ void fa_bwd3(const double* Lp, double* x) {  // x <- L^-T x
+  x[2] *= Lp[5];
+  x[1] = (x[1] - Lp[2] * x[2]) * Lp[4];
+  x[0] = (x[0] - Lp[0] * x[1] - Lp[1] * x[2]) * Lp[3];
+}
+
 struct FaParams {
   // structure
-  const int64_t* tile_pt_ptr; const int64_t* e_ptr; const int32_t* ob_e; const int32_t* ob_f; const double2* uv;
+  const int64_t* tile_pt_ptr; const int64_t* e_ptr; const int32_t* ob_e; const int32_t* ob_f; const uint16_t* ob_slot; const double2* uv;
+  const int64_t* tile_cam_ptr; const int32_t* tile_cams;
   const int64_t* tile_pitem_ptr; const int64_t* pitem_begin; const int64_t* pitem_end; const int32_t* pent;
   const int64_t* tile_citem_ptr; const int64_t* citem_begin; const int64_t* citem_end; const int32_t* cent;
+  int cap;
   // state
   const double* xe; const double* se; const double* tab_f; const double* radius;
   double min_diag, max_diag;
@@ -246,23 +344,54 @@ struct FaParams {
   int* status;
 };
 
+// the tile's camera tables -> shared memory, SoA [field][slot] so that lanes with different cameras hit different banks
+__device__ __forceinline__ int fa_stage_tables(const FaParams& P, int tile, const double* __restrict__ tab, double* tabs, int nfields,
+                                               const int* field_map) {
+  const int64_t c0 = P.tile_cam_ptr[tile];
+  const int ncam = min((int)(P.tile_cam_ptr[tile + 1] - c0), FA_TCAM);
+  for (int i = threadIdx.x; i < ncam * nfields; i += FA_THREADS) {
+    const int slot = i / nfields, f = i % nfields;
+    tabs[f * FA_TCAM + slot] = __ldg(tab + (int64_t)TAB * P.tile_cams[c0 + slot] + (field_map ? field_map[f] : f));
+  }
+  return ncam;
+}
+__device__ __forceinline__ void fa_get_table(const double* tabs, const double* __restrict__ tab, int slot, int32_t cam, double* T) {
+  if (slot < FA_TCAM) {
+#pragma unroll
+    for (int f = 0; f < TAB; ++f) T[f] = tabs[f * FA_TCAM + slot];
+  } else {
+    load_tab(tab, cam, T);
+  }
+}
+
+// item index of a tile dealt boustrophedon over the threads: round r, thread t -> r * T + (r odd ? T - 1 - t : t)
+#define FA_FOR_ITEMS(it, first, count)                                                                   \
+  for (int64_t r__ = 0, it = 0; r__ * FA_THREADS < (count); ++r__)                                       \
+    if ((it = r__ * FA_THREADS + ((r__ & 1) ? FA_THREADS - 1 - (int)threadIdx.x : (int)threadIdx.x)) < (count) && ((it += (first)), true))
+
 // NORMS = true: iteration 0 only, unscaled Jacobian; writes the Jacobi scaling of the points and the camera items
 // (their F^T F diagonals are the camera column norms); no Schur products.
 template <bool NORMS>
-__global__ void __launch_bounds__(FA_THREADS, 2) k_fa_pass1(FaParams P) {
-  extern __shared__ double rec[];  // [FA_CAP][FA_REC]: U (6) | Jf (12) | r (2) | w (2)
+__global__ void __launch_bounds__(FA_THREADS, 3) k_fa_pass1(FaParams P) {
+  extern __shared__ double smem[];
+  double* rec = smem;                                   // [cap][FA_REC]: U (6) | Jf (12) | r (2) | w (2)
+  double* Ls = rec + (size_t)P.cap * FA_REC;            // [FA_TPTS][FA_LS]
+  double* tabs = Ls + FA_TPTS * FA_LS;                  // [TAB][FA_TCAM]
+  uint16_t* oblp = reinterpret_cast<uint16_t*>(tabs + FA_TCAM * TAB);  // [cap] local point of an observation
   __shared__ double red[32];
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int64_t pt0 = P.tile_pt_ptr[tile], pt1 = P.tile_pt_ptr[tile + 1];
   const int64_t ob0 = P.e_ptr[pt0], ob1 = P.e_ptr[pt1];
   const int nobs = (int)(ob1 - ob0), npts = (int)(pt1 - pt0);
+  fa_stage_tables(P, tile, P.tab_f, tabs, TAB, nullptr);
+  __syncthreads();
   // ---- A1: one thread per observation ----
   double sq = 0.0;
   for (int l = tid; l < nobs; l += FA_THREADS) {
     const int64_t o = ob0 + l;
     const int64_t e = P.ob_e[o];
     double T[TAB];
-    load_tab(P.tab_f, P.ob_f[o], T);
+    fa_get_table(tabs, P.tab_f, P.ob_slot[o], P.ob_f[o], T);
     const double X[3] = {P.xe[3 * e], P.xe[3 * e + 1], P.xe[3 * e + 2]};
     double s[3] = {1.0, 1.0, 1.0};
     if (!NORMS) { s[0] = P.se[3 * e]; s[1] = P.se[3 * e + 1]; s[2] = P.se[3 * e + 2]; }
@@ -276,26 +405,27 @@ __global__ void __launch_bounds__(FA_THREADS, 2) k_fa_pass1(FaParams P) {
     for (int k = 0; k < 6; ++k) R2[3 + k] = make_double2(jf[2 * k], jf[2 * k + 1]);
     R2[9] = make_double2(r[0], r[1]);
     R2[10] = make_double2(0.0, 0.0);
+    oblp[l] = (uint16_t)(e - pt0);
   }
   __syncthreads();
-  // ---- A2: one thread per point ----
+  // ---- A2a: one thread per point ----
   double gmx = 0.0, g2 = 0.0;
   const double radius = *P.radius;
   for (int lp = tid; lp < npts; lp += FA_THREADS) {
     const int64_t e = pt0 + lp;
     const int l0 = (int)(P.e_ptr[e] - ob0), l1 = (int)(P.e_ptr[e + 1] - ob0);
-    double M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    double M[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};  // m00 m01 m02 m11 m12 m22
     for (int l = l0; l < l1; ++l) {
       const double* R = rec + (size_t)l * FA_REC;
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const double j0 = R[3 * rr], j1 = R[3 * rr + 1], j2 = R[3 * rr + 2], rv = R[18 + rr];
-        M[0] += j0 * j0; M[1] += j0 * j1; M[2] += j0 * j2; M[4] += j1 * j1; M[5] += j1 * j2; M[8] += j2 * j2;
+        M[0] += j0 * j0; M[1] += j0 * j1; M[2] += j0 * j2; M[3] += j1 * j1; M[4] += j1 * j2; M[5] += j2 * j2;
         g[0] += j0 * rv; g[1] += j1 * rv; g[2] += j2 * rv;
       }
     }
     if (NORMS) {
-      P.se_out[3 * e] = 1.0 / (1.0 + sqrt(M[0])); P.se_out[3 * e + 1] = 1.0 / (1.0 + sqrt(M[4])); P.se_out[3 * e + 2] = 1.0 / (1.0 + sqrt(M[8]));
+      P.se_out[3 * e] = 1.0 / (1.0 + sqrt(M[0])); P.se_out[3 * e + 1] = 1.0 / (1.0 + sqrt(M[3])); P.se_out[3 * e + 2] = 1.0 / (1.0 + sqrt(M[5]));
       continue;
     }
     if (l1 > l0) {  // |x - Plus(x, -g)| of the unscaled gradient (TrustRegionMinimizer::EvaluateGradientAndJacobian)
@@ -306,64 +436,62 @@ __global__ void __launch_bounds__(FA_THREADS, 2) k_fa_pass1(FaParams P) {
         gmx = fmax(gmx, fabs(d)); g2 += d * d;
       }
     }
-    M[3] = M[1]; M[6] = M[2]; M[7] = M[5];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double d = sqrt(fmin(fmax(M[4 * k], P.min_diag), P.max_diag) / radius);
-      M[4 * k] += d * d;
+    {
+      const double da = sqrt(fmin(fmax(M[0], P.min_diag), P.max_diag) / radius);
+      const double db = sqrt(fmin(fmax(M[3], P.min_diag), P.max_diag) / radius);
+      const double dc = sqrt(fmin(fmax(M[5], P.min_diag), P.max_diag) / radius);
+      M[0] += da * da; M[3] += db * db; M[5] += dc * dc;
     }
-    if (!chol_small<3>(M)) {
+    double Lp[6];
+    if (!fa_chol3(M, Lp)) {
       atomicOr(P.status, 1);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) M[k] = (k % 4 == 0) ? 1.0 : 0.0;
+      Lp[0] = Lp[1] = Lp[2] = 0.0; Lp[3] = Lp[4] = Lp[5] = 1.0;
     }
-    fwd_small<3>(M, g);  // z
+    fa_fwd3(Lp, g);  // z
     double* out = P.Lz + 9 * e;
-    out[0] = M[0]; out[1] = M[3]; out[2] = M[4]; out[3] = M[6]; out[4] = M[7]; out[5] = M[8]; out[6] = g[0]; out[7] = g[1]; out[8] = g[2];
-    for (int l = l0; l < l1; ++l) {
+    double* ls = Ls + lp * FA_LS;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { out[k] = Lp[k]; ls[k] = Lp[k]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { out[6 + k] = g[k]; ls[6 + k] = g[k]; }
+  }
+  __syncthreads();
+  // ---- A2b: one thread per observation: U = L^-1 J_e^T (rows), w = U^T z ----
+  if (!NORMS) {
+    for (int l = tid; l < nobs; l += FA_THREADS) {
       double* R = rec + (size_t)l * FA_REC;
+      const double* ls = Ls + (int)oblp[l] * FA_LS;
+      double Lp[6], z[3];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Lp[k] = ls[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) z[k] = ls[6 + k];
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         double u[3] = {R[3 * rr], R[3 * rr + 1], R[3 * rr + 2]};
-        fwd_small<3>(M, u);  // u_rr = L^-1 (J_e row rr)^T
+        fa_fwd3(Lp, u);
         R[3 * rr] = u[0]; R[3 * rr + 1] = u[1]; R[3 * rr + 2] = u[2];
-        R[20 + rr] = u[0] * g[0] + u[1] * g[1] + u[2] * g[2];  // w_rr = u_rr . z
+        R[20 + rr] = u[0] * z[0] + u[1] * z[1] + u[2] * z[2];
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
   // ---- B: one thread per work item ----
-  for (int64_t it = P.tile_citem_ptr[tile] + tid; it < P.tile_citem_ptr[tile + 1]; it += FA_THREADS) {
-    double acc[FA_NVC];
-#pragma unroll
-    for (int k = 0; k < FA_NVC; ++k) acc[k] = 0.0;
-    for (int64_t q = P.citem_begin[it]; q < P.citem_end[it]; ++q) {
-      const double2* R2 = reinterpret_cast<const double2*>(rec + (size_t)P.cent[q] * FA_REC);
-      double jf[12];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) { const double2 v = R2[3 + k]; jf[2 * k] = v.x; jf[2 * k + 1] = v.y; }
-      const double2 rv = R2[9], wv = R2[10];
-      int c = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int b = a; b < 6; ++b) acc[c++] += jf[a] * jf[b] + jf[6 + a] * jf[6 + b];
-#pragma unroll
-      for (int a = 0; a < 6; ++a) { acc[21 + a] += jf[a] * rv.x + jf[6 + a] * rv.y; acc[27 + a] += jf[a] * wv.x + jf[6 + a] * wv.y; }
-    }
-    double* out = P.partC + (size_t)it * FA_NVC;
-#pragma unroll
-    for (int k = 0; k < FA_NVC; ++k) out[k] = acc[k];
-  }
   if (!NORMS) {
-    for (int64_t it = P.tile_pitem_ptr[tile] + tid; it < P.tile_pitem_ptr[tile + 1]; it += FA_THREADS) {
+    const int64_t first = P.tile_pitem_ptr[tile];
+    const int64_t count = P.tile_pitem_ptr[tile + 1] - first;
+    FA_FOR_ITEMS(it, first, count) {
       double acc[36];
 #pragma unroll
       for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-      for (int64_t q = P.pitem_begin[it]; q < P.pitem_end[it]; ++q) {
-        const int32_t ent = P.pent[q];
-        const double2* Ri = reinterpret_cast<const double2*>(rec + (size_t)(ent & 0xffff) * FA_REC);
-        const double2* Rj = reinterpret_cast<const double2*>(rec + (size_t)((ent >> 16) & 0xffff) * FA_REC);
+      const int64_t q1 = P.pitem_end[it];
+      int64_t q = P.pitem_begin[it];
+      int32_t ent = P.pent[q];
+      for (; q < q1; ++q) {
+        const int32_t cur = ent;
+        if (q + 1 < q1) ent = P.pent[q + 1];  // one ahead: hides the L2 latency of the entry list
+        const double2* Ri = reinterpret_cast<const double2*>(rec + (size_t)(cur & 0xffff) * FA_REC);
+        const double2* Rj = reinterpret_cast<const double2*>(rec + (size_t)((cur >> 16) & 0xffff) * FA_REC);
         double ui[6], uj[6], fj[12];
 #pragma unroll
         for (int k = 0; k < 3; ++k) { const double2 a = Ri[k], b = Rj[k]; ui[2 * k] = a.x; ui[2 * k + 1] = a.y; uj[2 * k] = b.x; uj[2 * k + 1] = b.y; }
@@ -388,7 +516,34 @@ __global__ void __launch_bounds__(FA_THREADS, 2) k_fa_pass1(FaParams P) {
 #pragma unroll
       for (int k = 0; k < 18; ++k) out[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
     }
-    // cost and gradient-norm partials of the tile (fixed tree)
+  }
+  {
+    const int64_t first = P.tile_citem_ptr[tile];
+    const int64_t count = P.tile_citem_ptr[tile + 1] - first;
+    FA_FOR_ITEMS(it, first, count) {
+      double acc[FA_NVC];
+#pragma unroll
+      for (int k = 0; k < FA_NVC; ++k) acc[k] = 0.0;
+      for (int64_t q = P.citem_begin[it]; q < P.citem_end[it]; ++q) {
+        const double2* R2 = reinterpret_cast<const double2*>(rec + (size_t)P.cent[q] * FA_REC);
+        double jf[12];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { const double2 v = R2[3 + k]; jf[2 * k] = v.x; jf[2 * k + 1] = v.y; }
+        const double2 rv = R2[9], wv = R2[10];
+        int c = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int b = a; b < 6; ++b) acc[c++] += jf[a] * jf[b] + jf[6 + a] * jf[6 + b];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { acc[21 + a] += jf[a] * rv.x + jf[6 + a] * rv.y; acc[27 + a] += jf[a] * wv.x + jf[6 + a] * wv.y; }
+      }
+      double* out = P.partC + (size_t)it * FA_NVC;
+#pragma unroll
+      for (int k = 0; k < FA_NVC; ++k) out[k] = acc[k];
+    }
+  }
+  if (!NORMS) {  // cost and gradient-norm partials of the tile (fixed tree)
     sq = block_sum(sq, red);
     g2 = block_sum(g2, red);
     gmx = block_max(gmx, red);
@@ -396,21 +551,29 @@ __global__ void __launch_bounds__(FA_THREADS, 2) k_fa_pass1(FaParams P) {
   }
 }
 
+__device__ __constant__ int kFaCandFields[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 18, 19, 20, 21, 22, 23, 24};  // R | t | fx fy ppx ppy
+
 // back-substitution, model cost change, candidate point and candidate cost of one tile
-__global__ void __launch_bounds__(FA_THREADS, 2) k_fa_pass2(FaParams P) {
-  extern __shared__ double rec[];  // [FA_CAP][FA_REC2]: J_e (6) | r (2) | J_f yf (2) ; then [FA_TPTS][3] candidate points
+__global__ void __launch_bounds__(FA_THREADS, 3) k_fa_pass2(FaParams P) {
+  extern __shared__ double smem[];
+  double* rec = smem;                                   // [cap][FA_REC2]: J_e (6) | r (2) | J_f yf (2)
+  double* Xc = rec + (size_t)P.cap * FA_REC2;           // [FA_TPTS][3] candidate points
+  double* tabs = Xc + FA_TPTS * 3;                      // [TAB][FA_TCAM] tables at x
+  double* tabc = tabs + FA_TCAM * TAB;                  // [16][FA_TCAM] tables at the candidate (R, t, intrinsics)
   __shared__ double red[32];
-  double* Xc = rec + (size_t)FA_CAP * FA_REC2;
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int64_t pt0 = P.tile_pt_ptr[tile], pt1 = P.tile_pt_ptr[tile + 1];
   const int64_t ob0 = P.e_ptr[pt0], ob1 = P.e_ptr[pt1];
   const int nobs = (int)(ob1 - ob0), npts = (int)(pt1 - pt0);
+  fa_stage_tables(P, tile, P.tab_f, tabs, TAB, nullptr);
+  fa_stage_tables(P, tile, P.tabc_f, tabc, 16, kFaCandFields);
+  __syncthreads();
   for (int l = tid; l < nobs; l += FA_THREADS) {
     const int64_t o = ob0 + l;
     const int64_t e = P.ob_e[o];
     const int32_t c = P.ob_f[o];
     double T[TAB];
-    load_tab(P.tab_f, c, T);
+    fa_get_table(tabs, P.tab_f, P.ob_slot[o], c, T);
     const double X[3] = {P.xe[3 * e], P.xe[3 * e + 1], P.xe[3 * e + 2]};
     const double s[3] = {P.se[3 * e], P.se[3 * e + 1], P.se[3 * e + 2]};
     double r[2], je[6], jf[12];
@@ -433,19 +596,22 @@ __global__ void __launch_bounds__(FA_THREADS, 2) k_fa_pass2(FaParams P) {
     const int64_t e = pt0 + lp;
     const int l0 = (int)(P.e_ptr[e] - ob0), l1 = (int)(P.e_ptr[e + 1] - ob0);
     const double* in = P.Lz + 9 * e;
-    const double L[9] = {in[0], 0.0, 0.0, in[1], in[2], 0.0, in[3], in[4], in[5]};
-    double t[3] = {in[6], in[7], in[8]};
+    double Lp[6], t[3];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Lp[k] = in[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t[k] = in[6 + k];
     for (int l = l0; l < l1; ++l) {
       const double* R = rec + (size_t)l * FA_REC2;
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         double u[3] = {R[3 * rr], R[3 * rr + 1], R[3 * rr + 2]};
-        fwd_small<3>(L, u);
+        fa_fwd3(Lp, u);
         const double q = R[8 + rr];
         t[0] -= u[0] * q; t[1] -= u[1] * q; t[2] -= u[2] * q;
       }
     }
-    bwd_small<3>(L, t);  // y_e
+    fa_bwd3(Lp, t);  // y_e
     // Ceres: model_cost_change = -(J step)^T (r + J step / 2) with step = -y; the caller negates the sum
     for (int l = l0; l < l1; ++l) {
       const double* R = rec + (size_t)l * FA_REC2;
@@ -469,17 +635,23 @@ __global__ void __launch_bounds__(FA_THREADS, 2) k_fa_pass2(FaParams P) {
   for (int l = tid; l < nobs; l += FA_THREADS) {
     const int64_t o = ob0 + l;
     const int lp = (int)(P.ob_e[o] - pt0);
-    const double* T = P.tabc_f + TAB * (int64_t)P.ob_f[o];
-    double Rm[9];
+    const int slot = P.ob_slot[o];
+    double C[16];
+    if (slot < FA_TCAM) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Rm[k] = __ldg(T + k);
+      for (int f = 0; f < 16; ++f) C[f] = tabc[f * FA_TCAM + slot];
+    } else {
+      const double* T = P.tabc_f + TAB * (int64_t)P.ob_f[o];
+#pragma unroll
+      for (int f = 0; f < 16; ++f) C[f] = __ldg(T + kFaCandFields[f]);
+    }
     const double X[3] = {Xc[3 * lp], Xc[3 * lp + 1], Xc[3 * lp + 2]};
     double q[3];
-    mat3_vec(Rm, X, q);
-    const double p0 = q[0] + __ldg(T + 18), p1 = q[1] + __ldg(T + 19), p2 = q[2] + __ldg(T + 20);
+    mat3_vec(C, X, q);
+    const double p0 = q[0] + C[9], p1 = q[1] + C[10], p2 = q[2] + C[11];
     const double2 ob = P.uv[o];
-    const double r0 = __ldg(T + 21) * p0 / p2 + __ldg(T + 23) - ob.x;
-    const double r1 = __ldg(T + 22) * p1 / p2 + __ldg(T + 24) - ob.y;
+    const double r0 = C[12] * p0 / p2 + C[14] - ob.x;
+    const double r1 = C[13] * p1 / p2 + C[15] - ob.y;
     sq += r0 * r0 + r1 * r1;
   }
   mcc = block_sum(mcc, red);
