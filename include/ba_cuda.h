@@ -155,6 +155,11 @@ void ba_cuda_destroy(ba_cuda_problem* p);
 const char* ba_cuda_last_error(void); /* thread-local message of the last failure */
 int ba_cuda_device_count(void);
 
+/* Device buffers are recycled through a caching allocator (cudaMalloc / cudaFree cost milliseconds and synchronise
+ * the device; rebuilding a problem reuses the previous buffers).  The cache is emptied when the last problem is
+ * destroyed; this call empties it at once, e.g. before handing the GPU to another library. */
+void ba_cuda_release_cached_memory(void);
+
 /* All work of a problem is enqueued on one CUDA stream: by default a private non-blocking stream; a caller
  * that wants to order / time the work with its own events passes its cudaStream_t here (NULL restores the
  * private stream).  Must not be called while a solve is in flight. */

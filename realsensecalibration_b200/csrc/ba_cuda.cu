@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <string>
@@ -144,8 +145,20 @@ namespace {
 
 int use_device(ba_cuda_problem* p) {
   BA_CUDA_TRY(cudaSetDevice(p->device));
+  DevCache::current_stream() = p->st;  // device buffers freed from here on are reused in this stream's order
   return BA_OK;
 }
+std::atomic<int> g_live_problems{0};
+struct PhaseTimer {  // BA_CUDA_TIMING=1: host wall clock of the phases of ba_cuda_set_model_* on stderr
+  const bool on = std::getenv("BA_CUDA_TIMING") != nullptr;
+  double t = now_s();
+  void lap(const char* what) {
+    if (!on) return;
+    const double n = now_s();
+    std::fprintf(stderr, "[ba_cuda timing] %-28s %9.3f ms\n", what, 1e3 * (n - t));
+    t = n;
+  }
+};
 
 // ---- per-kernel accounting -------------------------------------------------------------
 cudaEvent_t pool_event(ba_cuda_problem* p, size_t* idx) {
@@ -1066,8 +1079,11 @@ int ba_cuda_create(ba_cuda_problem** out, int device_id) {
   BA_CUDA_TRY(cudaMallocHost((void**)&p->h_scal, sizeof(double) * S_COUNT));
   BA_CUDA_TRY(cudaMallocHost((void**)&p->h_status, sizeof(int)));
   *out = p;
+  ++g_live_problems;
   return BA_OK;
 }
+
+void ba_cuda_release_cached_memory(void) { DevCache::get().trim(); }
 
 void ba_cuda_destroy(ba_cuda_problem* p) {
   if (!p) return;
@@ -1080,9 +1096,12 @@ void ba_cuda_destroy(ba_cuda_problem* p) {
   if (p->h_scal) cudaFreeHost(p->h_scal);
   if (p->h_status) cudaFreeHost(p->h_status);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
-  cudaStream_t st = p->own_st;
+  cudaStream_t st = p->own_st, used = p->st;
+  DevCache::current_stream() = used;
   delete p;
+  DevCache::get().mark_clean(used);  // synchronised above
   if (st) cudaStreamDestroy(st);
+  if (--g_live_problems == 0) DevCache::get().trim();  // the cache only lives as long as some problem does
 }
 
 int ba_cuda_comm_unique_id(uint8_t id[BA_CUDA_UNIQUE_ID_BYTES]) {
@@ -1132,11 +1151,15 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
   for (int64_t i = 0; i < n_obs; ++i)
     if (cam_idx[i] < 0 || cam_idx[i] >= n_cam || pt_idx[i] < 0 || pt_idx[i] >= n_pt)
       return fail(BA_ERR_INVALID_ARGUMENT, "observation %lld references camera %d / point %d out of range", (long long)i, cam_idx[i], pt_idx[i]);
+  PhaseTimer T;
+  T.lap("validate indices");
   BA_TRY(use_device(p));
   reset_problem(p);
+  T.lap("reset");
   p->n_cam = n_cam; p->n_pt = n_pt; p->n_time = 0; p->n_marker = 0;
   p->n_params = 6 * (int64_t)n_cam + 3 * n_pt;
   BA_TRY(build_structure(p->S, n_obs, n_pt, n_cam, pt_idx, cam_idx, nullptr, p->st));
+  T.lap("build_structure");
   p->model = 0;
   // observations in sorted order, intrinsics per f-block
   {
@@ -1150,9 +1173,10 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
     BA_TRY(p->intr_f.upload(K.data(), K.size(), p->st));
     BA_CUDA_TRY(cudaStreamSynchronize(p->st));
   }
-  p->h_perm.resize(n_obs);
-  BA_CUDA_TRY(cudaMemcpy(p->h_perm.data(), p->S.perm.p, sizeof(int32_t) * n_obs, cudaMemcpyDeviceToHost));
+  T.lap("observations upload");
+  p->h_perm.clear();  // fetched on demand by ba_cuda_eval
   BA_TRY(alloc_workspace(p, 2, 3));
+  T.lap("alloc_workspace");
   {  // fused two-pass pipeline when every point has <= FA_KMAX observations, else the generic one
     const int rc = build_fused_a(p->FA, p->S, p->st);
     if (rc != BA_OK && rc != BA_ERR_UNSUPPORTED) return rc;
@@ -1160,7 +1184,10 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
     if (p->use_fused) BA_TRY(p->fa_part.alloc((size_t)7 * p->FA.n_tiles));
     else BA_TRY(ensure_generic_workspace(p));
   }
-  return build_activity(p);
+  T.lap("build_fused_a");
+  const int rc = build_activity(p);
+  T.lap("build_activity");
+  return rc;
 }
 
 int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32_t n_marker, int64_t n_mobs,
@@ -1200,8 +1227,7 @@ int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32
     BA_TRY(p->intr_f.upload(K.data(), K.size(), p->st));
     BA_CUDA_TRY(cudaStreamSynchronize(p->st));
   }
-  p->h_perm.resize(n_mobs);
-  BA_CUDA_TRY(cudaMemcpy(p->h_perm.data(), p->S.perm.p, sizeof(int32_t) * n_mobs, cudaMemcpyDeviceToHost));
+  p->h_perm.clear();
   BA_TRY(alloc_workspace(p, 8, 6));
   p->use_fused = false;
   BA_TRY(ensure_generic_workspace(p));
@@ -1314,7 +1340,9 @@ int ba_cuda_set_stream(ba_cuda_problem* p, void* cuda_stream) {
   if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
   BA_TRY(use_device(p));
   BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  DevCache::get().mark_clean(p->st);
   p->st = cuda_stream ? (cudaStream_t)cuda_stream : p->own_st;
+  DevCache::current_stream() = p->st;
   return BA_OK;
 }
 
@@ -1396,6 +1424,10 @@ int ba_cuda_eval(ba_cuda_problem* p, double* cost, double* residuals, double* ja
   BA_TRY(fetch_scalars(p));
   BA_CUDA_TRY(cudaEventElapsedTime(&p->last_kernel_ms, p->k0, p->k1));
   if (cost) *cost = 0.5 * p->h_scal[S_COST];
+  if ((residuals || jac) && (int64_t)p->h_perm.size() != S.nb) {
+    p->h_perm.resize(S.nb);
+    BA_CUDA_TRY(cudaMemcpy(p->h_perm.data(), S.perm.p, sizeof(int32_t) * S.nb, cudaMemcpyDeviceToHost));
+  }
   if (residuals) {
     std::vector<double> h(S.nb * RD);
     BA_CUDA_TRY(cudaMemcpy(h.data(), p->RES.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));

@@ -7,6 +7,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "ba_cuda.h"
@@ -40,6 +43,77 @@ inline int fail(int code, const char* fmt, ...) {
     if (rc__ != BA_OK) return rc__; \
   } while (0)
 
+// ---- caching device allocator ----------------------------------------------------------
+// cudaMalloc / cudaFree cost milliseconds for the buffers of a BAL-sized problem and cudaFree synchronises the
+// device; ba_cuda_set_model_* allocates ~150 buffers.  Freed blocks are therefore kept in a per-device free list and
+// handed out again by size (best fit).  Reuse is stream-ordered: every block remembers the stream that was current
+// when it was freed; taking it from another stream first synchronises the device (rare: one stream per problem).
+struct DevCache {
+  struct Block { void* p; int dev; cudaStream_t st; };
+  std::mutex mu;
+  std::multimap<size_t, Block> free_blocks;
+  std::unordered_map<void*, size_t> live;   // every block handed out -> rounded size
+  size_t cached_bytes = 0;
+  static DevCache& get() { static DevCache* c = new DevCache(); return *c; }  // leaked on purpose: outlives static destructors
+  static cudaStream_t& current_stream() { static thread_local cudaStream_t s = nullptr; return s; }
+  static size_t round_up(size_t b) {
+    if (b == 0) b = 1;
+    const size_t g = b < (1u << 20) ? 512 : (size_t)2 << 20;
+    return (b + g - 1) / g * g;
+  }
+  cudaError_t malloc(void** out, size_t bytes) {
+    const size_t want = round_up(bytes);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (auto it = free_blocks.lower_bound(want); it != free_blocks.end() && it->first <= want + want / 4 + 512; ++it) {
+        if (it->second.dev != dev) continue;
+        Block b = it->second;
+        const size_t sz = it->first;
+        free_blocks.erase(it);
+        cached_bytes -= sz;
+        live[b.p] = sz;
+        if (b.st != nullptr && b.st != current_stream()) cudaDeviceSynchronize();
+        *out = b.p;
+        return cudaSuccess;
+      }
+    }
+    cudaError_t e = cudaMalloc(out, want);
+    if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and try again
+      cudaGetLastError();
+      trim();
+      e = cudaMalloc(out, want);
+    }
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(mu); live[*out] = want; }
+    return e;
+  }
+  void free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = live.find(p);
+    if (it == live.end()) { cudaFree(p); return; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    free_blocks.emplace(it->second, Block{p, dev, current_stream()});
+    cached_bytes += it->second;
+    live.erase(it);
+  }
+  void mark_clean(cudaStream_t st) {  // the stream was synchronised: its freed blocks are safe for any stream
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& kv : free_blocks) if (kv.second.st == st) kv.second.st = nullptr;
+  }
+  void trim() {  // cudaFree everything cached (all devices)
+    std::lock_guard<std::mutex> lk(mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (auto& kv : free_blocks) { cudaSetDevice(kv.second.dev); cudaFree(kv.second.p); }
+    cudaSetDevice(dev);
+    free_blocks.clear();
+    cached_bytes = 0;
+  }
+};
+
 // ---- owning device buffer -----------------------------------------------------------
 template <typename T>
 struct DVec {
@@ -50,7 +124,7 @@ struct DVec {
   DVec& operator=(const DVec&) = delete;
   ~DVec() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) DevCache::get().free(p);
     p = nullptr;
     n = 0;
   }
@@ -58,7 +132,7 @@ struct DVec {
     release();
     n = count;
     if (count == 0) count = 1;  // keep pointers non-null so kernels can take them
-    BA_CUDA_TRY(cudaMalloc((void**)&p, count * sizeof(T)));
+    BA_CUDA_TRY(DevCache::get().malloc((void**)&p, count * sizeof(T)));
     return BA_OK;
   }
   int alloc_zero(size_t count, cudaStream_t s) {
@@ -86,9 +160,9 @@ int cub_call(F&& f) {
   void* tmp = nullptr;
   size_t bytes = 0;
   BA_CUDA_TRY(f(tmp, bytes));
-  BA_CUDA_TRY(cudaMalloc(&tmp, bytes ? bytes : 1));
+  BA_CUDA_TRY(DevCache::get().malloc(&tmp, bytes ? bytes : 1));
   cudaError_t e = f(tmp, bytes);
-  cudaFree(tmp);
+  DevCache::get().free(tmp);
   BA_CUDA_TRY(e);
   return BA_OK;
 }

@@ -24,6 +24,7 @@ EXPORTS = [
     "ba_cuda_project_points_error", "ba_cuda_model_b_outputs", "ba_cuda_solve_begin", "ba_cuda_solve_iterate",
     "ba_cuda_solve_end", "ba_cuda_set_stream", "ba_cuda_get_kernel_stats", "ba_cuda_num_launches", "ba_cuda_reset_stats",
     "ba_cuda_save_parameters", "ba_cuda_restore_parameters", "ba_cuda_project_points_error_rt",
+    "ba_cuda_release_cached_memory",
 ]
 
 
@@ -48,6 +49,7 @@ def lib():
         L.ba_cuda_last_kernel_ms.restype = C.c_double
         L.ba_cuda_num_launches.restype = C.c_int64
         L.ba_cuda_reset_stats.restype = None
+        L.ba_cuda_release_cached_memory.restype = None
         L.ba_cuda_options_init.argtypes = [C.POINTER(Options)]
         _LIB = L
     return _LIB
@@ -66,6 +68,10 @@ def default_options():
 
 def device_count():
     return int(lib().ba_cuda_device_count())
+
+
+def release_cached_memory():
+    lib().ba_cuda_release_cached_memory()
 
 
 def shard_blocks(weights, world_size):

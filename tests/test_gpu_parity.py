@@ -217,7 +217,10 @@ def test_pcg_matches_oracle_pcg(gpu, oracle, name):
         assert abs(ia - ib) <= max(2, 0.1 * ib), (a, b)
         same = same and ia == ib
         assert H.rel(a["cost"], b["cost"]) <= (1e-5 if same else 1e-3), (a, b)   # truncated CG amplifies summation-order round-off
-        assert H.rel(a["trust_region_radius"], b["trust_region_radius"]) <= (1e-4 if same else 0.5)
+        # the radius follows rho = cost_change / model_cost_change through the cubic rule: late rows, where the cost
+        # change is 1e-4 of the cost, turn a 1e-6 cost difference into a 1e-3 radius difference (the dense solver on
+        # the same problem agrees with the oracle to 1e-13, see test_solve_synthetic_vs_oracle)
+        assert H.rel(a["trust_region_radius"], b["trust_region_radius"]) <= (5e-3 if same else 0.5)
     assert np.abs(x - xo).max() < (1e-4 if same else 1e-2)
     assert rows[1]["linear_solver_iterations"] == rows_o[1]["linear_solver_iterations"] > 0
 
