@@ -474,6 +474,8 @@ FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt) {
   FaParams P;
   P.tile_pt_ptr = F.tile_pt_ptr.p; P.e_ptr = S.e_ptr.p; P.ob_e = S.ob_e.p; P.ob_f = S.ob_f0.p; P.ob_slot = F.ob_slot.p; P.uv = p->uv.p;
   P.tile_cam_ptr = F.cams.tile_group_ptr.p; P.tile_cams = F.cams.group_target.p; P.cap = F.cap;
+  P.tile_pent_ptr = F.tile_pent_ptr.p; P.tile_cent_ptr = F.tile_cent_ptr.p;
+  P.pts_cap = F.pts_cap; P.tcam = F.tcam; P.tcs = F.tcs; P.pent_cap = F.pent_cap;
   P.tile_pitem_ptr = F.pairs.tile_item_ptr.p; P.pitem_begin = F.pairs.item_begin.p; P.pitem_end = F.pairs.item_end.p; P.pent = F.pairs.ent.p;
   P.tile_citem_ptr = F.cams.tile_item_ptr.p; P.citem_begin = F.cams.item_begin.p; P.citem_end = F.cams.item_end.p; P.cent = F.cams.ent.p;
   P.xe = p->xe.p; P.se = p->se.p; P.tab_f = p->tab_f.p; P.radius = p->scal.p + S_RADIUS;
@@ -536,7 +538,7 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms) {
   const FaParams P = fa_params(p, opt);
   const int nt = F.n_tiles;
   if (norms) {
-    BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<true>), nt, FA_THREADS, F.smem1(), P);
+    BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<true>), nt, F.threads, F.smem1(), P);
     BA_TRY(fa_reduce(p, true, false));
     BA_TRY(allreduce(p, F.camacc.p, F.camacc.n, kNcclSum));
     BA_LAUNCH(p, KT_MISC, (k_jacobi_scale<6, FA_NVC>), grid_for(S.nf * 6, 256), 256, 0, S.nf, F.camacc.p, p->sf.p);
@@ -545,7 +547,7 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms) {
     return BA_OK;
   }
   BA_CUDA_TRY(cudaMemsetAsync(p->status.p, 0, sizeof(int), p->st));
-  BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<false>), nt, FA_THREADS, F.smem1(), P);
+  BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<false>), nt, F.threads, F.smem1(), P);
   {
     FoldJob J = {{P.cost_partial, P.g2_partial, P.gmax_partial, nullptr}, {S_COST, S_G2E, S_GMAXE, 0}, {0, 0, 1, 0}};
     BA_LAUNCH(p, KT_FOLD, k_fold_multi, 3, 1024, 0, J, nt, p->scal.p);
@@ -621,7 +623,7 @@ int fa_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   }
   BA_TRY(build_tables(p, true));
   const FaParams P = fa_params(p, opt);
-  BA_LAUNCH(p, KT_FA_P2, k_fa_pass2, F.n_tiles, FA_THREADS, F.smem2(), P);
+  BA_LAUNCH(p, KT_FA_P2, k_fa_pass2, F.n_tiles, F.threads, F.smem2(), P);
   {
     FoldJob J = {{P.mcc_partial, P.x2_partial, P.d2_partial, P.cand_partial}, {S_MCC, S_XE2, S_DE2, S_CAND}, {0, 0, 0, 0}};
     BA_LAUNCH(p, KT_FOLD, k_fold_multi, 4, 1024, 0, J, F.n_tiles, p->scal.p);

@@ -25,6 +25,8 @@
 // Replaces ReprojectionError + AutoDiff (Test1_BundleAdjustment/bundle_adjustmenter.cpp:106-148) and, inside
 // Ceres, SchurEliminator::Eliminate / BackSubstitute.
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "ba_kernels.cuh"
 #include "ba_structure.cuh"
 
@@ -38,9 +40,11 @@ constexpr int FA_CH_PAIR = 16;               // pairs per pair item
 constexpr int FA_CH_CAM = 4;                 // observations per camera item
 constexpr int FA_CH_RED = 64;                // partial blocks per first-level reduction chunk
 constexpr int FA_NVC = 33;                   // per camera: 21 packed upper F^T F | 6 F^T r | 6 sum of v_i
-constexpr int FA_THREADS = 128;
+constexpr int FA_MAX_THREADS = 256;          // launch bound: 2 x 256 or 4 x 128 threads per SM at <= 128 registers
+constexpr int FA_THREADS_DEFAULT = 128;      // BA_FA_THREADS overrides, for tuning
 constexpr int FA_REC = 22;                   // doubles per observation record in shared memory (pass 1)
 constexpr int FA_REC2 = 10;                  // pass 2
+constexpr int FA_PENT_MAX = 6144;            // pair entries staged in shared memory per tile (24 KB)
 constexpr int FA_LS = 10;                    // per point in shared memory: L10 L20 L21 | 1/L00 1/L11 1/L22 | z (3) | pad
 
 // work items of one kind (pair items or camera items) and the static reduction lists over their partial blocks
@@ -63,13 +67,22 @@ struct ItemSet {
 
 struct FusedA {
   bool ready = false;
-  int n_tiles = 0, tobs = FA_TOBS_DEFAULT, kmax = 0, cap = 0;
+  int n_tiles = 0, tobs = FA_TOBS_DEFAULT, kmax = 0, cap = 0, threads = FA_THREADS_DEFAULT;
   DVec<int64_t> tile_pt_ptr;    // n_tiles + 1
+  DVec<int64_t> tile_pent_ptr;  // n_tiles + 1: the tile's slice of pairs.ent (entries are tile-major)
+  DVec<int64_t> tile_cent_ptr;  // n_tiles + 1: the tile's slice of cams.ent
   ItemSet pairs, cams;
   DVec<uint16_t> ob_slot;       // per observation: slot of its camera in the tile's camera list
   DVec<double> partP, partC, red1P, red1C, camacc, Lz;
-  size_t smem1() const { return ((size_t)cap * FA_REC + FA_TPTS * FA_LS + FA_TCAM * TAB) * 8 + (size_t)cap * 2; }
-  size_t smem2() const { return ((size_t)cap * FA_REC2 + FA_TPTS * 3 + FA_TCAM * (TAB + 16)) * 8; }
+  // shared-memory geometry, from the maxima over the tiles of this problem (so that small tiles co-reside on an SM)
+  int pts_cap = FA_TPTS;        // points of the fullest tile
+  int tcam = FA_TCAM;           // camera tables staged per tile (cameras beyond are read from L2)
+  int tcs = FA_TCAM + 1;        // stride of one table field in shared memory (odd: conflict-free staging)
+  int pent_cap = 0;             // pair entries staged per tile (entries beyond are read from L2)
+  size_t smem1() const {
+    return ((size_t)cap * FA_REC + (size_t)pts_cap * FA_LS + (size_t)tcs * TAB) * 8 + ((size_t)pent_cap + cap) * 4 + (size_t)cap * 2;
+  }
+  size_t smem2() const { return ((size_t)cap * FA_REC2 + (size_t)pts_cap * 3 + (size_t)tcs * (TAB + 16)) * 8; }
 };
 
 __global__ void k_fa_tile_flags(const int64_t* __restrict__ e_ptr, int64_t ne, int tobs, int32_t* __restrict__ flag, int* __restrict__ kmax) {
@@ -154,6 +167,22 @@ __global__ void k_fa_ob_slot(int ng, const int64_t* __restrict__ group_ptr, cons
   for (int64_t q = group_ptr[g]; q < group_ptr[g + 1]; ++q) ob_slot[ob0 + ent[q]] = slot;
 }
 
+// per tile: slice of an entry list (entries are sorted tile-major, groups are tile-major) and the maxima the
+// shared-memory geometry is sized by; stat = {max points, max cameras, max pair entries}
+__global__ void k_fa_tile_ent_ptr(int n_tiles, const int64_t* __restrict__ tile_group_ptr, const int64_t* __restrict__ group_ptr,
+                                  int64_t* __restrict__ tile_ent_ptr) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t <= n_tiles) tile_ent_ptr[t] = group_ptr[tile_group_ptr[t]];
+}
+__global__ void k_fa_tile_stats(int n_tiles, const int64_t* __restrict__ tile_pt_ptr, const int64_t* __restrict__ tile_cam_ptr,
+                                const int64_t* __restrict__ tile_pent_ptr, int* __restrict__ stat) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  atomicMax(stat + 0, (int)(tile_pt_ptr[t + 1] - tile_pt_ptr[t]));
+  atomicMax(stat + 1, (int)(tile_cam_ptr[t + 1] - tile_cam_ptr[t]));
+  atomicMax(stat + 2, (int)min(tile_pent_ptr[t + 1] - tile_pent_ptr[t], (int64_t)INT32_MAX));
+}
+
 // keys (tile * n_targets + target) with their entries -> sorted entries, groups, items of <= ch entries ordered by
 // (tile, descending length), reduction lists
 inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, int64_t n, int n_tiles, int64_t n_targets, int ch,
@@ -220,6 +249,8 @@ inline int build_fused_a(FusedA& F, const Structure& S, cudaStream_t st) {
   if (ne == 0 || nb == 0 || S.nslots != 1) return BA_ERR_UNSUPPORTED;
   F.tobs = FA_TOBS_DEFAULT;
   if (const char* env = std::getenv("BA_FA_TOBS")) { const int v = std::atoi(env); if (v >= 64 && v <= 1024) F.tobs = v; }
+  F.threads = FA_THREADS_DEFAULT;
+  if (const char* env = std::getenv("BA_FA_THREADS")) { const int v = std::atoi(env); if (v >= 32 && v <= FA_MAX_THREADS && v % 32 == 0) F.threads = v; }
   DVec<int32_t> flag, tile_of_pt;
   DVec<int> kmax;
   BA_TRY(flag.alloc(ne)); BA_TRY(tile_of_pt.alloc(ne)); BA_TRY(kmax.alloc_zero(1, st));
@@ -264,6 +295,23 @@ inline int build_fused_a(FusedA& F, const Structure& S, cudaStream_t st) {
     k_fa_group_tile<<<grid_for(F.n_tiles, 256), 256, 0, st>>>(F.n_tiles, F.cams.tile_group_ptr.p, group_tile.p);
     k_fa_ob_slot<<<grid_for(ng, 256), 256, 0, st>>>(ng, F.cams.group_ptr.p, group_tile.p, F.cams.tile_group_ptr.p, F.cams.ent.p, S.e_ptr.p,
                                                     F.tile_pt_ptr.p, F.ob_slot.p);
+  }
+  {  // per-tile slices of the entry lists; shared-memory geometry from the fullest tile
+    const int nt = F.n_tiles;
+    BA_TRY(F.tile_pent_ptr.alloc((size_t)nt + 1)); BA_TRY(F.tile_cent_ptr.alloc((size_t)nt + 1));
+    k_fa_tile_ent_ptr<<<grid_for(nt + 1, 256), 256, 0, st>>>(nt, F.pairs.tile_group_ptr.p, F.pairs.group_ptr.p, F.tile_pent_ptr.p);
+    k_fa_tile_ent_ptr<<<grid_for(nt + 1, 256), 256, 0, st>>>(nt, F.cams.tile_group_ptr.p, F.cams.group_ptr.p, F.tile_cent_ptr.p);
+    DVec<int> stat;
+    BA_TRY(stat.alloc_zero(3, st));
+    k_fa_tile_stats<<<grid_for(nt, 256), 256, 0, st>>>(nt, F.tile_pt_ptr.p, F.cams.tile_group_ptr.p, F.tile_pent_ptr.p, stat.p);
+    int h[3] = {0, 0, 0};
+    BA_CUDA_TRY(cudaMemcpyAsync(h, stat.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+    F.pts_cap = std::max(1, std::min(h[0], FA_TPTS));
+    F.tcam = std::max(1, std::min(h[1], FA_TCAM));
+    F.tcs = F.tcam | 1;
+    F.pent_cap = std::min(h[2], FA_PENT_MAX);
+    F.pent_cap += F.pent_cap & 1;  // keeps the int32 areas 8-byte sized
   }
   BA_TRY(F.partP.alloc((size_t)F.pairs.n_items * 36)); BA_TRY(F.partC.alloc((size_t)F.cams.n_items * FA_NVC));
   BA_TRY(F.red1P.alloc((size_t)F.pairs.red_ch.n * 36)); BA_TRY(F.red1C.alloc((size_t)F.cams.red_ch.n * FA_NVC));
@@ -331,7 +379,8 @@ struct FaParams {
   const int64_t* tile_cam_ptr; const int32_t* tile_cams;
   const int64_t* tile_pitem_ptr; const int64_t* pitem_begin; const int64_t* pitem_end; const int32_t* pent;
   const int64_t* tile_citem_ptr; const int64_t* citem_begin; const int64_t* citem_end; const int32_t* cent;
-  int cap;
+  const int64_t* tile_pent_ptr; const int64_t* tile_cent_ptr;
+  int cap, pts_cap, tcam, tcs, pent_cap;
   // state
   const double* xe; const double* se; const double* tab_f; const double* radius;
   double min_diag, max_diag;
@@ -348,17 +397,18 @@ struct FaParams {
 __device__ __forceinline__ int fa_stage_tables(const FaParams& P, int tile, const double* __restrict__ tab, double* tabs, int nfields,
                                                const int* field_map) {
   const int64_t c0 = P.tile_cam_ptr[tile];
-  const int ncam = min((int)(P.tile_cam_ptr[tile + 1] - c0), FA_TCAM);
-  for (int i = threadIdx.x; i < ncam * nfields; i += FA_THREADS) {
+  const int ncam = min((int)(P.tile_cam_ptr[tile + 1] - c0), P.tcam);
+  for (int i = threadIdx.x; i < ncam * nfields; i += blockDim.x) {
     const int slot = i / nfields, f = i % nfields;
-    tabs[f * FA_TCAM + slot] = __ldg(tab + (int64_t)TAB * P.tile_cams[c0 + slot] + (field_map ? field_map[f] : f));
+    tabs[f * P.tcs + slot] = __ldg(tab + (int64_t)TAB * P.tile_cams[c0 + slot] + (field_map ? field_map[f] : f));
   }
   return ncam;
 }
-__device__ __forceinline__ void fa_get_table(const double* tabs, const double* __restrict__ tab, int slot, int32_t cam, double* T) {
-  if (slot < FA_TCAM) {
+__device__ __forceinline__ void fa_get_table(const FaParams& P, const double* tabs, const double* __restrict__ tab, int slot, int32_t cam,
+                                             double* T) {
+  if (slot < P.tcam) {
 #pragma unroll
-    for (int f = 0; f < TAB; ++f) T[f] = tabs[f * FA_TCAM + slot];
+    for (int f = 0; f < TAB; ++f) T[f] = tabs[f * P.tcs + slot];
   } else {
     load_tab(tab, cam, T);
   }
@@ -366,32 +416,42 @@ __device__ __forceinline__ void fa_get_table(const double* tabs, const double* _
 
 // item index of a tile dealt boustrophedon over the threads: round r, thread t -> r * T + (r odd ? T - 1 - t : t)
 #define FA_FOR_ITEMS(it, first, count)                                                                   \
-  for (int64_t r__ = 0, it = 0; r__ * FA_THREADS < (count); ++r__)                                       \
-    if ((it = r__ * FA_THREADS + ((r__ & 1) ? FA_THREADS - 1 - (int)threadIdx.x : (int)threadIdx.x)) < (count) && ((it += (first)), true))
+  for (int64_t r__ = 0, it = 0; r__ * blockDim.x < (count); ++r__)                                       \
+    if ((it = r__ * blockDim.x + ((r__ & 1) ? blockDim.x - 1 - (int)threadIdx.x : (int)threadIdx.x)) < (count) && ((it += (first)), true))
 
 // NORMS = true: iteration 0 only, unscaled Jacobian; writes the Jacobi scaling of the points and the camera items
 // (their F^T F diagonals are the camera column norms); no Schur products.
 template <bool NORMS>
-__global__ void __launch_bounds__(FA_THREADS, 3) k_fa_pass1(FaParams P) {
+__global__ void __launch_bounds__(FA_MAX_THREADS, 2) k_fa_pass1(FaParams P) {
   extern __shared__ double smem[];
   double* rec = smem;                                   // [cap][FA_REC]: U (6) | Jf (12) | r (2) | w (2)
-  double* Ls = rec + (size_t)P.cap * FA_REC;            // [FA_TPTS][FA_LS]
-  double* tabs = Ls + FA_TPTS * FA_LS;                  // [TAB][FA_TCAM]
-  uint16_t* oblp = reinterpret_cast<uint16_t*>(tabs + FA_TCAM * TAB);  // [cap] local point of an observation
+  double* Ls = rec + (size_t)P.cap * FA_REC;            // [pts_cap][FA_LS]
+  double* tabs = Ls + (size_t)P.pts_cap * FA_LS;        // [TAB][tcs]
+  int32_t* pent_s = reinterpret_cast<int32_t*>(tabs + (size_t)P.tcs * TAB);  // [pent_cap] the tile's pair entries
+  int32_t* cent_s = pent_s + P.pent_cap;                // [cap] the tile's camera-item entries
+  uint16_t* oblp = reinterpret_cast<uint16_t*>(cent_s + P.cap);  // [cap] local point of an observation
   __shared__ double red[32];
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int64_t pt0 = P.tile_pt_ptr[tile], pt1 = P.tile_pt_ptr[tile + 1];
   const int64_t ob0 = P.e_ptr[pt0], ob1 = P.e_ptr[pt1];
   const int nobs = (int)(ob1 - ob0), npts = (int)(pt1 - pt0);
+  // the work-item entry lists of the tile -> shared memory, asynchronously (needed in phase B only): the item loops
+  // then never wait on L2 for their next entry
+  const int64_t pe0 = P.tile_pent_ptr[tile], ce0 = P.tile_cent_ptr[tile];
+  const int npe = NORMS ? 0 : (int)min(P.tile_pent_ptr[tile + 1] - pe0, (int64_t)P.pent_cap);
+  const int nce = (int)min(P.tile_cent_ptr[tile + 1] - ce0, (int64_t)P.cap);
+  for (int i = tid; i < npe; i += blockDim.x) __pipeline_memcpy_async(pent_s + i, P.pent + pe0 + i, 4);
+  for (int i = tid; i < nce; i += blockDim.x) __pipeline_memcpy_async(cent_s + i, P.cent + ce0 + i, 4);
+  __pipeline_commit();
   fa_stage_tables(P, tile, P.tab_f, tabs, TAB, nullptr);
   __syncthreads();
   // ---- A1: one thread per observation ----
   double sq = 0.0;
-  for (int l = tid; l < nobs; l += FA_THREADS) {
+  for (int l = tid; l < nobs; l += blockDim.x) {
     const int64_t o = ob0 + l;
     const int64_t e = P.ob_e[o];
     double T[TAB];
-    fa_get_table(tabs, P.tab_f, P.ob_slot[o], P.ob_f[o], T);
+    fa_get_table(P, tabs, P.tab_f, P.ob_slot[o], P.ob_f[o], T);
     const double X[3] = {P.xe[3 * e], P.xe[3 * e + 1], P.xe[3 * e + 2]};
     double s[3] = {1.0, 1.0, 1.0};
     if (!NORMS) { s[0] = P.se[3 * e]; s[1] = P.se[3 * e + 1]; s[2] = P.se[3 * e + 2]; }
@@ -411,7 +471,7 @@ __global__ void __launch_bounds__(FA_THREADS, 3) k_fa_pass1(FaParams P) {
   // ---- A2a: one thread per point ----
   double gmx = 0.0, g2 = 0.0;
   const double radius = *P.radius;
-  for (int lp = tid; lp < npts; lp += FA_THREADS) {
+  for (int lp = tid; lp < npts; lp += blockDim.x) {
     const int64_t e = pt0 + lp;
     const int l0 = (int)(P.e_ptr[e] - ob0), l1 = (int)(P.e_ptr[e + 1] - ob0);
     double M[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};  // m00 m01 m02 m11 m12 m22
@@ -455,10 +515,11 @@ __global__ void __launch_bounds__(FA_THREADS, 3) k_fa_pass1(FaParams P) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) { out[6 + k] = g[k]; ls[6 + k] = g[k]; }
   }
+  __pipeline_wait_prior(0);
   __syncthreads();
   // ---- A2b: one thread per observation: U = L^-1 J_e^T (rows), w = U^T z ----
   if (!NORMS) {
-    for (int l = tid; l < nobs; l += FA_THREADS) {
+    for (int l = tid; l < nobs; l += blockDim.x) {
       double* R = rec + (size_t)l * FA_REC;
       const double* ls = Ls + (int)oblp[l] * FA_LS;
       double Lp[6], z[3];
@@ -484,12 +545,9 @@ __global__ void __launch_bounds__(FA_THREADS, 3) k_fa_pass1(FaParams P) {
       double acc[36];
 #pragma unroll
       for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-      const int64_t q1 = P.pitem_end[it];
-      int64_t q = P.pitem_begin[it];
-      int32_t ent = P.pent[q];
-      for (; q < q1; ++q) {
-        const int32_t cur = ent;
-        if (q + 1 < q1) ent = P.pent[q + 1];  // one ahead: hides the L2 latency of the entry list
+      const int q1 = (int)(P.pitem_end[it] - pe0);
+      for (int q = (int)(P.pitem_begin[it] - pe0); q < q1; ++q) {
+        const int32_t cur = q < npe ? pent_s[q] : P.pent[pe0 + q];
         const double2* Ri = reinterpret_cast<const double2*>(rec + (size_t)(cur & 0xffff) * FA_REC);
         const double2* Rj = reinterpret_cast<const double2*>(rec + (size_t)((cur >> 16) & 0xffff) * FA_REC);
         double ui[6], uj[6], fj[12];
@@ -524,8 +582,9 @@ __global__ void __launch_bounds__(FA_THREADS, 3) k_fa_pass1(FaParams P) {
       double acc[FA_NVC];
 #pragma unroll
       for (int k = 0; k < FA_NVC; ++k) acc[k] = 0.0;
-      for (int64_t q = P.citem_begin[it]; q < P.citem_end[it]; ++q) {
-        const double2* R2 = reinterpret_cast<const double2*>(rec + (size_t)P.cent[q] * FA_REC);
+      const int q1 = (int)(P.citem_end[it] - ce0);
+      for (int q = (int)(P.citem_begin[it] - ce0); q < q1; ++q) {
+        const double2* R2 = reinterpret_cast<const double2*>(rec + (size_t)cent_s[q] * FA_REC);
         double jf[12];
 #pragma unroll
         for (int k = 0; k < 6; ++k) { const double2 v = R2[3 + k]; jf[2 * k] = v.x; jf[2 * k + 1] = v.y; }
@@ -554,12 +613,12 @@ __global__ void __launch_bounds__(FA_THREADS, 3) k_fa_pass1(FaParams P) {
 __device__ __constant__ int kFaCandFields[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 18, 19, 20, 21, 22, 23, 24};  // R | t | fx fy ppx ppy
 
 // back-substitution, model cost change, candidate point and candidate cost of one tile
-__global__ void __launch_bounds__(FA_THREADS, 3) k_fa_pass2(FaParams P) {
+__global__ void __launch_bounds__(FA_MAX_THREADS, 2) k_fa_pass2(FaParams P) {
   extern __shared__ double smem[];
   double* rec = smem;                                   // [cap][FA_REC2]: J_e (6) | r (2) | J_f yf (2)
-  double* Xc = rec + (size_t)P.cap * FA_REC2;           // [FA_TPTS][3] candidate points
-  double* tabs = Xc + FA_TPTS * 3;                      // [TAB][FA_TCAM] tables at x
-  double* tabc = tabs + FA_TCAM * TAB;                  // [16][FA_TCAM] tables at the candidate (R, t, intrinsics)
+  double* Xc = rec + (size_t)P.cap * FA_REC2;           // [pts_cap][3] candidate points
+  double* tabs = Xc + (size_t)P.pts_cap * 3;            // [TAB][tcs] tables at x
+  double* tabc = tabs + (size_t)P.tcs * TAB;            // [16][tcs] tables at the candidate (R, t, intrinsics)
   __shared__ double red[32];
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int64_t pt0 = P.tile_pt_ptr[tile], pt1 = P.tile_pt_ptr[tile + 1];
@@ -568,12 +627,12 @@ __global__ void __launch_bounds__(FA_THREADS, 3) k_fa_pass2(FaParams P) {
   fa_stage_tables(P, tile, P.tab_f, tabs, TAB, nullptr);
   fa_stage_tables(P, tile, P.tabc_f, tabc, 16, kFaCandFields);
   __syncthreads();
-  for (int l = tid; l < nobs; l += FA_THREADS) {
+  for (int l = tid; l < nobs; l += blockDim.x) {
     const int64_t o = ob0 + l;
     const int64_t e = P.ob_e[o];
     const int32_t c = P.ob_f[o];
     double T[TAB];
-    fa_get_table(tabs, P.tab_f, P.ob_slot[o], c, T);
+    fa_get_table(P, tabs, P.tab_f, P.ob_slot[o], c, T);
     const double X[3] = {P.xe[3 * e], P.xe[3 * e + 1], P.xe[3 * e + 2]};
     const double s[3] = {P.se[3 * e], P.se[3 * e + 1], P.se[3 * e + 2]};
     double r[2], je[6], jf[12];
@@ -592,7 +651,7 @@ __global__ void __launch_bounds__(FA_THREADS, 3) k_fa_pass2(FaParams P) {
   }
   __syncthreads();
   double mcc = 0.0, x2 = 0.0, d2 = 0.0;
-  for (int lp = tid; lp < npts; lp += FA_THREADS) {
+  for (int lp = tid; lp < npts; lp += blockDim.x) {
     const int64_t e = pt0 + lp;
     const int l0 = (int)(P.e_ptr[e] - ob0), l1 = (int)(P.e_ptr[e + 1] - ob0);
     const double* in = P.Lz + 9 * e;
@@ -632,14 +691,14 @@ __global__ void __launch_bounds__(FA_THREADS, 3) k_fa_pass2(FaParams P) {
   }
   __syncthreads();
   double sq = 0.0;
-  for (int l = tid; l < nobs; l += FA_THREADS) {
+  for (int l = tid; l < nobs; l += blockDim.x) {
     const int64_t o = ob0 + l;
     const int lp = (int)(P.ob_e[o] - pt0);
     const int slot = P.ob_slot[o];
     double C[16];
-    if (slot < FA_TCAM) {
+    if (slot < P.tcam) {
 #pragma unroll
-      for (int f = 0; f < 16; ++f) C[f] = tabc[f * FA_TCAM + slot];
+      for (int f = 0; f < 16; ++f) C[f] = tabc[f * P.tcs + slot];
     } else {
       const double* T = P.tabc_f + TAB * (int64_t)P.ob_f[o];
 #pragma unroll
@@ -671,11 +730,28 @@ k_reduce_items(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const
   if (c >= nchunks) return;
   const int64_t begin = chunk_begin[c];
   const int64_t end = min(begin + ch, tgt_ptr[chunk_seg[c] + 1]);
-  for (int v = lane; v < NV; v += 32) {
-    double a = 0.0;
-    for (int64_t idx = begin; idx < end; ++idx) a += part[(int64_t)items[idx] * NV + v];
-    out[(int64_t)c * NV + v] = a;
+  // lanes fetch 32 item ids at a time, then eight independent block loads are in flight per lane; the sum itself
+  // stays strictly sequential in list order
+  double a0 = 0.0, a1 = 0.0;  // values lane, lane + 32
+  for (int64_t base = begin; base < end; base += 32) {
+    const int n = (int)min((int64_t)32, end - base);
+    const int32_t mine = lane < n ? items[base + lane] : 0;
+    for (int k = 0; k < n; k += 8) {
+      double x0[8], x1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int32_t id = __shfl_sync(0xffffffffu, mine, (k + u) & 31);
+        const bool on = k + u < n;
+        x0[u] = on ? part[(int64_t)id * NV + lane] : 0.0;
+        x1[u] = (on && lane + 32 < NV) ? part[(int64_t)id * NV + lane + 32] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k + u < n) { a0 += x0[u]; a1 += x1[u]; }
+    }
   }
+  out[(int64_t)c * NV + lane] = a0;
+  if (lane + 32 < NV) out[(int64_t)c * NV + lane + 32] = a1;
 }
 // second level: one warp per target over its chunk partials
 template <int NV>
