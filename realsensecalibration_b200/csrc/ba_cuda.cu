@@ -492,7 +492,7 @@ FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt) {
 int fa_set_smem_attr() {
   static bool done = false;
   if (!done) {
-    const int kMax = 200 * 1024;  // dynamic part; the kernels also hold a little static shared memory
+    const int kMax = (int)FA_SMEM_MAX;  // dynamic part; the kernels also hold a little static shared memory
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
@@ -623,7 +623,7 @@ int fa_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   }
   BA_TRY(build_tables(p, true));
   const FaParams P = fa_params(p, opt);
-  BA_LAUNCH(p, KT_FA_P2, k_fa_pass2, F.n_tiles, F.threads, F.smem2(), P);
+  BA_LAUNCH(p, KT_FA_P2, k_fa_pass2, F.n_tiles, F.threads2, F.smem2(), P);
   {
     FoldJob J = {{P.mcc_partial, P.x2_partial, P.d2_partial, P.cand_partial}, {S_MCC, S_XE2, S_DE2, S_CAND}, {0, 0, 0, 0}};
     BA_LAUNCH(p, KT_FOLD, k_fold_multi, 4, 1024, 0, J, F.n_tiles, p->scal.p);

@@ -34,17 +34,17 @@ namespace ba {
 
 constexpr int FA_TOBS_DEFAULT = 256;         // observation window of a tile (BA_FA_TOBS overrides, for tuning)
 constexpr int FA_KMAX = 64;                  // max observations of one point (fused path)
-constexpr int FA_TPTS = 128;                 // max points of a tile
+constexpr int FA_TPTS = 512;                 // max points of a tile
 constexpr int FA_TCAM = 48;                  // camera tables staged in shared memory per tile (more: read from L2)
 constexpr int FA_CH_PAIR = 16;               // pairs per pair item
-constexpr int FA_CH_CAM = 4;                 // observations per camera item
 constexpr int FA_CH_RED = 64;                // partial blocks per first-level reduction chunk
 constexpr int FA_NVC = 33;                   // per camera: 21 packed upper F^T F | 6 F^T r | 6 sum of v_i
-constexpr int FA_MAX_THREADS = 256;          // launch bound: 2 x 256 or 4 x 128 threads per SM at <= 128 registers
+constexpr int FA_MAX_THREADS = 512;          // launch bound: 1 x 512, 2 x 256 or 4 x 128 threads per SM at <= 128 registers
 constexpr int FA_THREADS_DEFAULT = 128;      // BA_FA_THREADS overrides, for tuning
 constexpr int FA_REC = 22;                   // doubles per observation record in shared memory (pass 1)
 constexpr int FA_REC2 = 10;                  // pass 2
 constexpr int FA_PENT_MAX = 6144;            // pair entries staged in shared memory per tile (24 KB)
+constexpr size_t FA_SMEM_MAX = 231000;      // dynamic shared memory per CTA (232448 opt-in limit minus the static part)
 constexpr int FA_LS = 10;                    // per point in shared memory: L10 L20 L21 | 1/L00 1/L11 1/L22 | z (3) | pad
 
 // work items of one kind (pair items or camera items) and the static reduction lists over their partial blocks
@@ -67,7 +67,7 @@ struct ItemSet {
 
 struct FusedA {
   bool ready = false;
-  int n_tiles = 0, tobs = FA_TOBS_DEFAULT, kmax = 0, cap = 0, threads = FA_THREADS_DEFAULT;
+  int n_tiles = 0, tobs = FA_TOBS_DEFAULT, kmax = 0, cap = 0, threads = FA_THREADS_DEFAULT, threads2 = FA_THREADS_DEFAULT, ch_cam = 16;
   DVec<int64_t> tile_pt_ptr;    // n_tiles + 1
   DVec<int64_t> tile_pent_ptr;  // n_tiles + 1: the tile's slice of pairs.ent (entries are tile-major)
   DVec<int64_t> tile_cent_ptr;  // n_tiles + 1: the tile's slice of cams.ent
@@ -243,14 +243,46 @@ inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, in
 
 // Returns BA_ERR_UNSUPPORTED when the problem does not fit the fused path (a point with more than FA_KMAX
 // observations, or nothing to do): the caller then keeps the generic pipeline.
+inline int env_int(const char* name, int lo, int hi, int fallback) {
+  if (const char* env = std::getenv(name)) { const int v = std::atoi(env); if (v >= lo && v <= hi) return v; }
+  return fallback;
+}
+
+inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, int tobs);
+
+// Tile geometry: measured on B200 (profiles/README.md), a problem whose points carry many observation pairs
+// (cfg5: 4.8 pairs per observation) wants the largest tile shared memory can hold (the partial blocks written per
+// work item, 288 B each, are what the kernel pays for in HBM) and 512 threads on it; a sparse one (cfg4: 3 pairs
+// per observation) runs best on 512-observation tiles, two CTAs of 128 threads per SM.  BA_FA_TOBS / BA_FA_THREADS /
+// BA_FA_THREADS2 / BA_FA_CH_CAM override, for tuning.  A geometry that does not fit is retried at half the tile.
 inline int build_fused_a(FusedA& F, const Structure& S, cudaStream_t st) {
   F.ready = false;
+  if (S.ne == 0 || S.nb == 0 || S.nslots != 1) return BA_ERR_UNSUPPORTED;
+  int64_t np = 0;
+  {
+    DVec<int64_t> cnt, off;
+    BA_TRY(cnt.alloc(S.ne + 1)); BA_TRY(off.alloc(S.ne + 1));
+    k_pair_count<<<grid_for(S.ne + 1, 128), 128, 0, st>>>(S.e_ptr.p, S.ob_f0.p, S.ne, cnt.p);
+    BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt.p, off.p, (int)(S.ne + 1), st); }));
+    BA_CUDA_TRY(cudaMemcpyAsync(&np, off.p + S.ne, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  if (np >= (int64_t)INT32_MAX) return BA_ERR_UNSUPPORTED;
+  const bool dense_pairs = (double)np >= 4.0 * (double)S.nb;
+  int tobs = env_int("BA_FA_TOBS", 64, 1024, dense_pairs ? 1024 : 512);
+  for (;; tobs /= 2) {
+    F.threads = env_int("BA_FA_THREADS", 32, FA_MAX_THREADS, tobs >= 768 ? 512 : 128) / 32 * 32;
+    F.threads2 = env_int("BA_FA_THREADS2", 32, FA_MAX_THREADS, tobs >= 768 ? 256 : 128) / 32 * 32;
+    F.ch_cam = env_int("BA_FA_CH_CAM", 1, 64, 16);
+    const int rc = build_fused_a_tobs(F, S, st, tobs);
+    if (rc != BA_ERR_UNSUPPORTED || tobs <= 128 || F.kmax > FA_KMAX) return rc;
+  }
+}
+
+inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, int tobs) {
+  F.ready = false;
   const int64_t ne = S.ne, nb = S.nb, nf = S.nf;
-  if (ne == 0 || nb == 0 || S.nslots != 1) return BA_ERR_UNSUPPORTED;
-  F.tobs = FA_TOBS_DEFAULT;
-  if (const char* env = std::getenv("BA_FA_TOBS")) { const int v = std::atoi(env); if (v >= 64 && v <= 1024) F.tobs = v; }
-  F.threads = FA_THREADS_DEFAULT;
-  if (const char* env = std::getenv("BA_FA_THREADS")) { const int v = std::atoi(env); if (v >= 32 && v <= FA_MAX_THREADS && v % 32 == 0) F.threads = v; }
+  F.tobs = tobs;
   DVec<int32_t> flag, tile_of_pt;
   DVec<int> kmax;
   BA_TRY(flag.alloc(ne)); BA_TRY(tile_of_pt.alloc(ne)); BA_TRY(kmax.alloc_zero(1, st));
@@ -288,7 +320,7 @@ inline int build_fused_a(FusedA& F, const Structure& S, cudaStream_t st) {
     DVec<int32_t> vals, group_tile;
     BA_TRY(keys.alloc(nb)); BA_TRY(vals.alloc(nb));
     k_fa_cam_fill<<<grid_for(nb, 256), 256, 0, st>>>(S.ob_e.p, S.ob_f0.p, nb, nf, S.e_ptr.p, tile_of_pt.p, F.tile_pt_ptr.p, keys.p, vals.p);
-    BA_TRY(build_items(F.cams, keys, vals, nb, F.n_tiles, nf, FA_CH_CAM, st));
+    BA_TRY(build_items(F.cams, keys, vals, nb, F.n_tiles, nf, F.ch_cam, st));
     const int ng = F.cams.n_groups;
     BA_TRY(group_tile.alloc(ng)); BA_TRY(F.ob_slot.alloc(nb));
     // group -> tile from the tile_group_ptr CSR (groups are tile-major)
@@ -312,6 +344,11 @@ inline int build_fused_a(FusedA& F, const Structure& S, cudaStream_t st) {
     F.tcs = F.tcam | 1;
     F.pent_cap = std::min(h[2], FA_PENT_MAX);
     F.pent_cap += F.pent_cap & 1;  // keeps the int32 areas 8-byte sized
+    if (F.smem1() > FA_SMEM_MAX) {   // stage fewer pair entries (the rest is read from L2) before giving up
+      const size_t excess = (F.smem1() - FA_SMEM_MAX + 7) / 8 * 2;
+      F.pent_cap = (size_t)F.pent_cap > excess ? F.pent_cap - (int)excess : 0;
+    }
+    if (F.smem1() > FA_SMEM_MAX || F.smem2() > FA_SMEM_MAX) return BA_ERR_UNSUPPORTED;
   }
   BA_TRY(F.partP.alloc((size_t)F.pairs.n_items * 36)); BA_TRY(F.partC.alloc((size_t)F.cams.n_items * FA_NVC));
   BA_TRY(F.red1P.alloc((size_t)F.pairs.red_ch.n * 36)); BA_TRY(F.red1C.alloc((size_t)F.cams.red_ch.n * FA_NVC));
@@ -419,10 +456,15 @@ __device__ __forceinline__ void fa_get_table(const FaParams& P, const double* ta
   for (int64_t r__ = 0, it = 0; r__ * blockDim.x < (count); ++r__)                                       \
     if ((it = r__ * blockDim.x + ((r__ & 1) ? blockDim.x - 1 - (int)threadIdx.x : (int)threadIdx.x)) < (count) && ((it += (first)), true))
 
+// the same dealt from the other end: the camera items go first to the threads whose pair items were the shortest
+#define FA_FOR_ITEMS_REV(it, first, count)                                                               \
+  for (int64_t r__ = 0, it = 0; r__ * blockDim.x < (count); ++r__)                                       \
+    if ((it = r__ * blockDim.x + ((r__ & 1) ? (int)threadIdx.x : blockDim.x - 1 - (int)threadIdx.x)) < (count) && ((it += (first)), true))
+
 // NORMS = true: iteration 0 only, unscaled Jacobian; writes the Jacobi scaling of the points and the camera items
 // (their F^T F diagonals are the camera column norms); no Schur products.
 template <bool NORMS>
-__global__ void __launch_bounds__(FA_MAX_THREADS, 2) k_fa_pass1(FaParams P) {
+__global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
   extern __shared__ double smem[];
   double* rec = smem;                                   // [cap][FA_REC]: U (6) | Jf (12) | r (2) | w (2)
   double* Ls = rec + (size_t)P.cap * FA_REC;            // [pts_cap][FA_LS]
@@ -578,7 +620,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 2) k_fa_pass1(FaParams P) {
   {
     const int64_t first = P.tile_citem_ptr[tile];
     const int64_t count = P.tile_citem_ptr[tile + 1] - first;
-    FA_FOR_ITEMS(it, first, count) {
+    FA_FOR_ITEMS_REV(it, first, count) {
       double acc[FA_NVC];
 #pragma unroll
       for (int k = 0; k < FA_NVC; ++k) acc[k] = 0.0;
@@ -613,7 +655,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 2) k_fa_pass1(FaParams P) {
 __device__ __constant__ int kFaCandFields[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 18, 19, 20, 21, 22, 23, 24};  // R | t | fx fy ppx ppy
 
 // back-substitution, model cost change, candidate point and candidate cost of one tile
-__global__ void __launch_bounds__(FA_MAX_THREADS, 2) k_fa_pass2(FaParams P) {
+__global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass2(FaParams P) {
   extern __shared__ double smem[];
   double* rec = smem;                                   // [cap][FA_REC2]: J_e (6) | r (2) | J_f yf (2)
   double* Xc = rec + (size_t)P.cap * FA_REC2;           // [pts_cap][3] candidate points
