@@ -61,7 +61,9 @@ Nccl& nccl() {
 }
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-enum Scal { S_COST = 0, S_G2E, S_GMAXE, S_CAND, S_MCC, S_XE2, S_DE2, S_XF2, S_DF2, S_GMAXF, S_G2F, S_RADIUS, S_COUNT = 16 };
+// S_CAND .. S_STATUSD are contiguous: the shard-local values one ncclAllReduce sums after a step
+enum Scal { S_COST = 0, S_G2E, S_GMAXE, S_CAND, S_MCC, S_XE2, S_DE2, S_STATUSD, S_XF2, S_DF2, S_GMAXF, S_G2F, S_RADIUS, S_COUNT = 16 };
+constexpr int kMaxWorld = 64;  // ranks whose gradient maxima ride in the tail of one sum-allreduce
 enum Family { F_JAC = 0, F_SCHUR, F_SOLVE, F_UPDATE, F_COST, F_COLL, F_COUNT };
 // one entry per kernel (family member) of the solve path; names are what ba_cuda_get_kernel_stats() reports
 enum KT {
@@ -222,6 +224,41 @@ int allreduce(ba_cuda_problem* p, void* buf, size_t count, int op, int dtype = k
   return BA_OK;
 }
 
+// Shard-local scalars ride on collectives that are needed anyway (every separate ncclAllReduce costs ~25 us of latency):
+// tail = [cost, |g_e|^2, gmax_e of rank 0 .. world-1]; a SUM all-reduce then carries the maximum too.
+__global__ void k_pack_grad_tail(const double* __restrict__ scal, int rank, int world, double* __restrict__ tail) {
+  const int i = threadIdx.x;
+  if (i == 0) tail[0] = scal[S_COST];
+  if (i == 1) tail[1] = scal[S_G2E];
+  if (i < world) tail[2 + i] = i == rank ? scal[S_GMAXE] : 0.0;
+}
+__global__ void k_unpack_grad_tail(const double* __restrict__ tail, int world, double* __restrict__ scal) {
+  if (threadIdx.x != 0) return;
+  scal[S_COST] = tail[0];
+  scal[S_G2E] = tail[1];
+  double m = 0.0;
+  for (int r = 0; r < world; ++r) m = fmax(m, tail[2 + r]);
+  scal[S_GMAXE] = m;
+}
+__global__ void k_status_to_scal(const int* __restrict__ status, double* __restrict__ scal) { scal[S_STATUSD] = *status != 0 ? 1.0 : 0.0; }
+
+// after a step: candidate cost, model cost change, |x_e|^2, |delta_e|^2 and the "a block factorisation failed" flag of
+// all shards in one collective
+int allreduce_step_scalars(ba_cuda_problem* p) {
+  if (p->world <= 1) return BA_OK;
+  k_status_to_scal<<<1, 1, 0, p->st>>>(p->status.p, p->scal.p);
+  return allreduce(p, p->scal.p + S_CAND, S_STATUSD - S_CAND + 1, kNcclSum);
+}
+// after a linearisation: cost, |g_e|^2 (sums) and max |g_e| through `tail` (2 + world doubles at the end of `buf`)
+int allreduce_with_grad_tail(ba_cuda_problem* p, double* buf, size_t n) {
+  if (p->world <= 1) return BA_OK;
+  k_pack_grad_tail<<<1, kMaxWorld, 0, p->st>>>(p->scal.p, p->rank, p->world, buf + n);
+  BA_TRY(allreduce(p, buf, n + 2 + p->world, kNcclSum));
+  k_unpack_grad_tail<<<1, 32, 0, p->st>>>(buf + n, p->world, p->scal.p);
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
 // Multi-GPU: every rank only knows the destination blocks its own shard couples; the stored pattern has to be
 // the union, identical on all ranks, so that one ncclAllReduce sums the block values in place.
 int build_global_pattern(ba_cuda_problem* p) {
@@ -335,13 +372,19 @@ int run_normal_parts(ba_cuda_problem* p) {
 }
 
 template <int DE>
-int run_gradient_norms(ba_cuda_problem* p) {
+int run_gradient_norms_e(ba_cuda_problem* p) {  // eliminated blocks: shard local
   const Structure& S = p->S;
   constexpr int NU = DE * (DE + 1) / 2;
-  const int ge = (int)grid_for(S.ne * DE, 256), gf = (int)grid_for(S.nf * 6, 256);
+  const int ge = (int)grid_for(S.ne * DE, 256);
   BA_LAUNCH(p, KT_GRADNORM, (k_gradient_norm<DE, NU + DE, NU>), ge, 256, 0, S.ne, S.e_ptr.p, p->xe.p, p->se.p, p->ME.p, p->bp0.p, p->bp1.p);
   BA_TRY(fold(p, p->bp0.p, ge, S_GMAXE, true));
   BA_TRY(fold(p, p->bp1.p, ge, S_G2E));
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+int run_gradient_norms_f(ba_cuda_problem* p) {  // kept blocks: from the (globally summed) F^T r
+  const Structure& S = p->S;
+  const int gf = (int)grid_for(S.nf * 6, 256);
   BA_LAUNCH(p, KT_GRADNORM, (k_gradient_norm<6, NV_F, 21>), gf, 256, 0, S.nf, p->f_act_ptr.p, p->xf.p, p->sf.p, p->HG.p, p->bp0.p, p->bp1.p);
   BA_TRY(fold(p, p->bp0.p, gf, S_GMAXF, true));
   BA_TRY(fold(p, p->bp1.p, gf, S_G2F));
@@ -372,17 +415,13 @@ int eval_gradient_and_jacobian(ba_cuda_problem* p, bool first, bool jacobi_scali
     BA_TRY((run_normal_parts<RD, DE, GE>(p)));
   }
   fam_end(p, F_SCHUR);
-  if (p->world > 1) {
+  BA_TRY(run_gradient_norms_e<DE>(p));
+  if (p->world > 1) {  // F^T F | F^T r of the kept blocks and the shard-local gradient scalars in one collective
     fam_begin(p, F_COLL);
-    BA_TRY(allreduce(p, p->HG.p, S.nf * NV_F, kNcclSum));
+    BA_TRY(allreduce_with_grad_tail(p, p->HG.p, S.nf * NV_F));
     fam_end(p, F_COLL);
   }
-  BA_TRY(run_gradient_norms<DE>(p));
-  if (p->world > 1) {
-    BA_TRY(allreduce(p, p->scal.p + S_COST, 2, kNcclSum));  // S_COST, S_G2E
-    BA_TRY(allreduce(p, p->scal.p + S_GMAXE, 1, kNcclMax));
-  }
-  return BA_OK;
+  return run_gradient_norms_f(p);
 }
 
 // LevenbergMarquardtStrategy::ComputeStep + SchurEliminator + dense Cholesky + BackSubstitute + the model cost
@@ -462,8 +501,7 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   fam_begin(p, F_COST);
   BA_TRY(run_cost_candidate(p));
   fam_end(p, F_COST);
-  if (p->world > 1) BA_TRY(allreduce(p, p->scal.p + S_CAND, 4, kNcclSum));  // S_CAND, S_MCC, S_XE2, S_DE2
-  return BA_OK;
+  return allreduce_step_scalars(p);
 }
 
 // ---- fused Model A path (ba_fused_a.cuh) -------------------------------------------------------------
@@ -540,7 +578,7 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms) {
   if (norms) {
     BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<true>), nt, F.threads, F.smem1(), P);
     BA_TRY(fa_reduce(p, true, false));
-    BA_TRY(allreduce(p, F.camacc.p, F.camacc.n, kNcclSum));
+    BA_TRY(allreduce(p, F.camacc.p, (size_t)S.nf * FA_NVC, kNcclSum));
     BA_LAUNCH(p, KT_MISC, (k_jacobi_scale<6, FA_NVC>), grid_for(S.nf * 6, 256), 256, 0, S.nf, F.camacc.p, p->sf.p);
     BA_CUDA_TRY(cudaGetLastError());
     fam_end(p, F_JAC);
@@ -556,9 +594,9 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms) {
   fam_begin(p, F_SCHUR);
   BA_TRY(fa_reduce(p, true, true));
   fam_end(p, F_SCHUR);
-  if (p->world > 1) {
+  if (p->world > 1) {  // camera sums and the shard-local gradient scalars in one collective
     fam_begin(p, F_COLL);
-    BA_TRY(allreduce(p, F.camacc.p, F.camacc.n, kNcclSum));
+    BA_TRY(allreduce_with_grad_tail(p, F.camacc.p, (size_t)S.nf * FA_NVC));
     fam_end(p, F_COLL);
   }
   const int gf = (int)grid_for(S.nf * 6, 256);
@@ -566,10 +604,6 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms) {
   {
     FoldJob J = {{p->bp0.p, p->bp1.p, nullptr, nullptr}, {S_GMAXF, S_G2F, 0, 0}, {1, 0, 0, 0}};
     BA_LAUNCH(p, KT_FOLD, k_fold_multi, 2, 1024, 0, J, gf, p->scal.p);
-  }
-  if (p->world > 1) {
-    BA_TRY(allreduce(p, p->scal.p + S_COST, 2, kNcclSum));  // S_COST, S_G2E
-    BA_TRY(allreduce(p, p->scal.p + S_GMAXE, 1, kNcclMax));
   }
   BA_CUDA_TRY(cudaGetLastError());
   return BA_OK;
@@ -630,8 +664,7 @@ int fa_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   }
   BA_CUDA_TRY(cudaGetLastError());
   fam_end(p, F_UPDATE);
-  if (p->world > 1) BA_TRY(allreduce(p, p->scal.p + S_CAND, 4, kNcclSum));  // S_CAND, S_MCC, S_XE2, S_DE2
-  return BA_OK;
+  return allreduce_step_scalars(p);
 }
 
 bool lm_fused(const ba_cuda_problem* p) { return p->model == 0 && p->use_fused && !p->lm.opt.force_generic_path; }
@@ -767,14 +800,8 @@ int lm_iterate(ba_cuda_problem* p, int32_t max_new) {
     BA_TRY(fetch_scalars(p));
     row.linear_solver_iterations = p->solver == BA_RCS_PCG ? p->h_pcg_iters : 0;
     int status = *p->h_status;
-    if (p->world > 1) {  // a failed block factorisation on any rank invalidates the step everywhere
-      double flag = status ? 1.0 : 0.0, *d = p->scal.p + S_COUNT - 1;
-      BA_CUDA_TRY(cudaMemcpyAsync(d, &flag, sizeof(double), cudaMemcpyHostToDevice, p->st));
-      BA_TRY(allreduce(p, d, 1, kNcclMax));
-      BA_CUDA_TRY(cudaMemcpyAsync(&flag, d, sizeof(double), cudaMemcpyDeviceToHost, p->st));
-      BA_CUDA_TRY(cudaStreamSynchronize(p->st));
-      status = flag != 0.0 ? 1 : 0;
-    }
+    // a failed block factorisation on any rank invalidates the step everywhere (summed with the step scalars)
+    if (p->world > 1) status = p->h_scal[S_STATUSD] != 0.0 ? 1 : 0;
     const double model_cost_change = -p->h_scal[S_MCC];
     const bool solve_ok = status == 0 && std::isfinite(model_cost_change);
     row.step_is_valid = solve_ok && model_cost_change > 0.0;
@@ -925,7 +952,7 @@ int ensure_generic_workspace(ba_cuda_problem* p) {
   const int RD = p->model == 0 ? 2 : 8, DE = p->model == 0 ? 3 : 6;
   BA_TRY(p->RES.alloc(S.nb * RD)); BA_TRY(p->JE.alloc(S.nb * RD * DE)); BA_TRY(p->JF0.alloc(S.nb * RD * 6));
   BA_TRY(p->JF1.alloc(p->model == 1 ? S.nb * RD * 6 : 0));
-  BA_TRY(p->ME.alloc(S.ne * (DE * (DE + 1) / 2 + DE))); BA_TRY(p->HG.alloc(S.nf * NV_F));
+  BA_TRY(p->ME.alloc(S.ne * (DE * (DE + 1) / 2 + DE))); BA_TRY(p->HG.alloc(S.nf * NV_F + 2 + kMaxWorld));
   BA_TRY(p->Wt.alloc(p->model == 1 ? S.ninc * 36 : 0));
   BA_TRY(p->Lb.alloc(S.ne * DE * DE)); BA_TRY(p->zb.alloc(S.ne * DE));
   BA_TRY(p->Yt.alloc(S.ninc * DE * 6)); BA_TRY(p->vb.alloc(S.ninc * 6));
@@ -1117,6 +1144,7 @@ int ba_cuda_comm_unique_id(uint8_t id[BA_CUDA_UNIQUE_ID_BYTES]) {
 
 int ba_cuda_comm_init(ba_cuda_problem* p, int rank, int world_size, const uint8_t id[BA_CUDA_UNIQUE_ID_BYTES]) {
   if (!p || world_size < 1 || rank < 0 || rank >= world_size) return fail(BA_ERR_INVALID_ARGUMENT, "bad rank/world");
+  if (world_size > kMaxWorld) return fail(BA_ERR_UNSUPPORTED, "at most %d ranks", kMaxWorld);
   BA_TRY(use_device(p));
   p->rank = rank; p->world = world_size;
   if (world_size == 1) return BA_OK;

@@ -352,7 +352,8 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
   }
   BA_TRY(F.partP.alloc((size_t)F.pairs.n_items * 36)); BA_TRY(F.partC.alloc((size_t)F.cams.n_items * FA_NVC));
   BA_TRY(F.red1P.alloc((size_t)F.pairs.red_ch.n * 36)); BA_TRY(F.red1C.alloc((size_t)F.cams.red_ch.n * FA_NVC));
-  BA_TRY(F.camacc.alloc((size_t)nf * FA_NVC)); BA_TRY(F.Lz.alloc((size_t)ne * 9));
+  BA_TRY(F.camacc.alloc((size_t)nf * FA_NVC + 2 + 64));  // tail: shard-local gradient scalars (ba_cuda.cu, kMaxWorld)
+  BA_TRY(F.Lz.alloc((size_t)ne * 9));
   BA_CUDA_TRY(cudaStreamSynchronize(st));
   BA_CUDA_TRY(cudaGetLastError());
   F.ready = true;
