@@ -253,7 +253,7 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
 // Tile geometry: measured on B200 (profiles/README.md), a problem whose points carry many observation pairs
 // (cfg5: 4.8 pairs per observation) wants the largest tile shared memory can hold (the partial blocks written per
 // work item, 288 B each, are what the kernel pays for in HBM) and 512 threads on it; a sparse one (cfg4: 3 pairs
-// per observation) runs best on 512-observation tiles, two CTAs of 128 threads per SM.  BA_FA_TOBS / BA_FA_THREADS /
+// per observation) runs best on 480-observation tiles, two CTAs of 256 threads per SM.  BA_FA_TOBS / BA_FA_THREADS /
 // BA_FA_THREADS2 / BA_FA_CH_CAM override, for tuning.  A geometry that does not fit is retried at half the tile.
 inline int build_fused_a(FusedA& F, const Structure& S, cudaStream_t st) {
   F.ready = false;
@@ -269,9 +269,9 @@ inline int build_fused_a(FusedA& F, const Structure& S, cudaStream_t st) {
   }
   if (np >= (int64_t)INT32_MAX) return BA_ERR_UNSUPPORTED;
   const bool dense_pairs = (double)np >= 4.0 * (double)S.nb;
-  int tobs = env_int("BA_FA_TOBS", 64, 1024, dense_pairs ? 1024 : 512);
+  int tobs = env_int("BA_FA_TOBS", 64, 1024, dense_pairs ? 1024 : 480);
   for (;; tobs /= 2) {
-    F.threads = env_int("BA_FA_THREADS", 32, FA_MAX_THREADS, tobs >= 768 ? 512 : 128) / 32 * 32;
+    F.threads = env_int("BA_FA_THREADS", 32, FA_MAX_THREADS, tobs >= 768 ? 512 : 256) / 32 * 32;
     F.threads2 = env_int("BA_FA_THREADS2", 32, FA_MAX_THREADS, tobs >= 768 ? 256 : 128) / 32 * 32;
     F.ch_cam = env_int("BA_FA_CH_CAM", 1, 64, 16);
     const int rc = build_fused_a_tobs(F, S, st, tobs);

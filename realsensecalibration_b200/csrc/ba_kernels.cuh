@@ -103,6 +103,25 @@ __device__ __forceinline__ void rot_deriv(const double* A, const double* b, doub
   }
 }
 
+// Coalesced AoS store: every thread of the CTA owns W consecutive doubles of dst (record tid of the CTA's
+// contiguous slice starting at dst); a direct store would scatter 16-byte pieces W * 8 bytes apart.  The records go
+// through shared memory (row stride WS doubles, chosen so that the double2 stores are conflict free) and leave as
+// full 128-byte lines.  All threads of the CTA must call; n_valid = records of this CTA that exist.
+template <int W, int WS>
+__device__ __forceinline__ void staged_store(double* stage, const double* vals, bool valid, double* __restrict__ dst, int n_valid) {
+  static_assert(W % 2 == 0 && WS % 2 == 0 && WS >= W, "double2 granularity");
+  if (valid) {
+    double2* row = reinterpret_cast<double2*>(stage + (size_t)threadIdx.x * WS);
+#pragma unroll
+    for (int k = 0; k < W / 2; ++k) row[k] = make_double2(vals[2 * k], vals[2 * k + 1]);
+  }
+  __syncthreads();
+  const double2* src = reinterpret_cast<const double2*>(stage);
+  double2* out = reinterpret_cast<double2*>(dst);
+  for (int g = threadIdx.x; g < n_valid * (W / 2); g += blockDim.x) out[g] = src[(g / (W / 2)) * (WS / 2) + g % (W / 2)];
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------
 // Model A.  One thread per observation (sorted by point).
 // ---------------------------------------------------------------------------------------
@@ -111,8 +130,12 @@ k_jac_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
         const double* __restrict__ tab_f, const double* __restrict__ xe, const double* __restrict__ se,
         double* __restrict__ RES, double* __restrict__ JE, double* __restrict__ JF0, double* __restrict__ cost_partial) {
   __shared__ double sm[32];
-  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  __shared__ __align__(16) double stage[256 * 14];
+  const int64_t o0 = blockIdx.x * (int64_t)blockDim.x;
+  const int64_t o = o0 + threadIdx.x;
+  const int n_valid = (int)min((int64_t)blockDim.x, nb - o0);
   double sq = 0.0;
+  double jf[12], je[6];
   if (o < nb) {
     const int32_t e = ob_e[o], c = ob_f0[o];
     double T[TAB];
@@ -130,7 +153,6 @@ k_jac_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
     const double a = T[21] * iz, bb = -T[21] * p0 * iz * iz, cc = T[22] * iz, dd = -T[22] * p1 * iz * iz;
     double D[9];
     rot_deriv(T + 9, T[25] != 0.0 ? X : q, D);
-    double jf[12];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       jf[k] = (a * D[k] + bb * D[6 + k]) * T[26 + k];
@@ -138,17 +160,12 @@ k_jac_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
     }
     jf[3] = a * T[29]; jf[4] = 0.0;        jf[5] = bb * T[31];
     jf[9] = 0.0;       jf[10] = cc * T[30]; jf[11] = dd * T[31];
-    double je[6];
     je[0] = (a * T[0] + bb * T[6]) * s0; je[1] = (a * T[1] + bb * T[7]) * s1; je[2] = (a * T[2] + bb * T[8]) * s2;
     je[3] = (cc * T[3] + dd * T[6]) * s0; je[4] = (cc * T[4] + dd * T[7]) * s1; je[5] = (cc * T[5] + dd * T[8]) * s2;
     reinterpret_cast<double2*>(RES)[o] = make_double2(r0, r1);
-    double2* pf = reinterpret_cast<double2*>(JF0 + 12 * o);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) pf[k] = make_double2(jf[2 * k], jf[2 * k + 1]);
-    double2* pe = reinterpret_cast<double2*>(JE + 6 * o);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) pe[k] = make_double2(je[2 * k], je[2 * k + 1]);
   }
+  staged_store<12, 14>(stage, jf, o < nb, JF0 + 12 * o0, n_valid);
+  staged_store<6, 6>(stage, je, o < nb, JE + 6 * o0, n_valid);
   sq = block_sum(sq, sm);
   if (threadIdx.x == 0) cost_partial[blockIdx.x] = sq;
 }
@@ -254,10 +271,14 @@ k_jac_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
         const double* __restrict__ tab_e, double half, double* __restrict__ RES, double* __restrict__ JE,
         double* __restrict__ JF0, double* __restrict__ JF1, double* __restrict__ cost_partial) {
   __shared__ double sm[32];
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  __shared__ __align__(16) double stage[128 * 14];
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x;   // (marker observation, corner) records are contiguous: 12 doubles each
+  const int64_t t = t0 + threadIdx.x;
   const int64_t o = t >> 2;
   const int corner = (int)(t & 3);
+  const int n_valid = (int)min((int64_t)blockDim.x, 4 * nb - t0);
   double sq = 0.0;
+  double je12[12], jc12[12], jm12[12];
   if (o < nb) {
     const int32_t f0 = ob_f0[o], f1 = ob_f1[o];
     double Tc[TAB], Tt[TAB], Tm[TAB];
@@ -277,19 +298,19 @@ k_jac_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
     RES[8 * o + 2 * corner] = r0;
     RES[8 * o + 2 * corner + 1] = r1;
     double row0[6], row1[6];
-    double* je = JE + 48 * o + 12 * corner;
     b_rows(P.G, Tt + 9, P.bt, Tt + 26, a, bb, cc, dd, row0, row1);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { je[k] = row0[k]; je[6 + k] = row1[k]; }
-    double* jc = JF0 + 48 * o + 12 * corner;
+    for (int k = 0; k < 6; ++k) { je12[k] = row0[k]; je12[6 + k] = row1[k]; }
     if (f0 >= 0) b_rows(nullptr, Tc + 9, P.bc, Tc + 26, a, bb, cc, dd, row0, row1);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { jc[k] = f0 >= 0 ? row0[k] : 0.0; jc[6 + k] = f0 >= 0 ? row1[k] : 0.0; }
-    double* jm = JF1 + 48 * o + 12 * corner;
+    for (int k = 0; k < 6; ++k) { jc12[k] = f0 >= 0 ? row0[k] : 0.0; jc12[6 + k] = f0 >= 0 ? row1[k] : 0.0; }
     if (f1 >= 0) b_rows(P.H, Tm + 9, P.bm, Tm + 26, a, bb, cc, dd, row0, row1);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { jm[k] = f1 >= 0 ? row0[k] : 0.0; jm[6 + k] = f1 >= 0 ? row1[k] : 0.0; }
+    for (int k = 0; k < 6; ++k) { jm12[k] = f1 >= 0 ? row0[k] : 0.0; jm12[6 + k] = f1 >= 0 ? row1[k] : 0.0; }
   }
+  staged_store<12, 14>(stage, je12, o < nb, JE + 12 * t0, n_valid);
+  staged_store<12, 14>(stage, jc12, o < nb, JF0 + 12 * t0, n_valid);
+  staged_store<12, 14>(stage, jm12, o < nb, JF1 + 12 * t0, n_valid);
   sq = block_sum(sq, sm);
   if (threadIdx.x == 0) cost_partial[blockIdx.x] = sq;
 }
@@ -299,10 +320,14 @@ k_cost_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict
          const int32_t* __restrict__ ob_cam, const double* __restrict__ obs8, const double* __restrict__ tab_f,
          const double* __restrict__ tab_e, double half, double* __restrict__ cost_partial) {
   __shared__ double sm[32];
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  __shared__ __align__(16) double stage[128 * 14];
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x;   // (marker observation, corner) records are contiguous: 12 doubles each
+  const int64_t t = t0 + threadIdx.x;
   const int64_t o = t >> 2;
   const int corner = (int)(t & 3);
+  const int n_valid = (int)min((int64_t)blockDim.x, 4 * nb - t0);
   double sq = 0.0;
+  double je12[12], jc12[12], jm12[12];
   if (o < nb) {
     const int32_t f0 = ob_f0[o], f1 = ob_f1[o];
     double Tc[TAB], Tt[TAB], Tm[TAB];
