@@ -49,6 +49,11 @@ WORKLOADS = {
                  kind="bal", args=(10000, 4000000, 7.5, 30, 0xBA05), kwargs=dict(variable_degree=True)),
     "small": dict(desc="smoke-sized BAL-shaped synthetic: 50 cameras x 20k points x 100k observations",
                   kind="bal", args=(50, 20000, 5, 12, 0xBA00)),
+    "cfg2": dict(desc="Main_Calibration shape (Model B): 4 cameras x 20 markers x 200 frames = 16k marker observations (64k corner "
+                      "observations), camera 0 and marker 0 fixed",
+                 kind="rig_b", args=(4, 20, 200, 0xBA02)),
+    "cfg3": dict(desc="large rig (Model B): 8 cameras x 100 markers x 1000 frames = 800k marker observations (3.2M corner observations)",
+                 kind="rig_b", args=(8, 100, 1000, 0xBA03)),
 }
 DEFAULT_WORKLOAD = "cfg4"
 
@@ -58,15 +63,55 @@ def make_workload(name):
     w = WORKLOADS[name]
     if w["kind"] == "rig_a":
         return S.marker_rig_a(*w["args"])
+    if w["kind"] == "rig_b":
+        return S.marker_rig_b(*w["args"])
     return S.bal_like(*w["args"], **w.get("kwargs", {}))
 
 
-def shard_model_a(pr, rank, world):
-    """Points (with all their observations) are block-distributed over ranks, balanced by observation count;
-    cameras are replicated.  Returns the rank-local arrays."""
-    from realsensecalibration_b200 import sharding
-    sh = sharding.shard_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.params, rank, world)
-    return sh.n_pt, sh.cam_idx, sh.pt_idx, sh.obs_xy, sh.params
+class Job:
+    """One workload as the bench sees it: the rank-local shard, how to hand it to the C ABI, the CPU oracle call."""
+
+    def __init__(self, name, rank, world):
+        from realsensecalibration_b200 import sharding
+        self.pr = pr = make_workload(name)
+        self.model = "B" if WORKLOADS[name]["kind"] == "rig_b" else "A"
+        if self.model == "A":
+            sh = sharding.shard_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.params, rank, world)
+            self.local = (sh.n_pt, sh.cam_idx, sh.pt_idx, np.asarray(sh.obs_xy), sh.params)
+            self.n_obs = pr.n_obs                    # corner observations (2 residuals each)
+            self.jac_bytes_per_obs = 184
+            self.blocks = {"n_cameras": pr.n_cam, "n_points": pr.n_pt, "n_obs": pr.n_obs}
+            self.sharded = "points"
+        else:
+            sh = sharding.shard_model_b(pr.n_cam, pr.n_time, pr.n_marker, pr.time_idx, pr.cam_idx, pr.marker_idx, pr.obs8, pr.params, rank, world)
+            self.local = (sh.n_time, sh.time_idx, sh.cam_idx, sh.marker_idx, np.asarray(sh.obs8), sh.params)
+            self.n_obs = pr.n_mobs                   # marker observations (8 residuals each)
+            self.jac_bytes_per_obs = 1292
+            self.blocks = {"n_cameras": pr.n_cam, "n_frames": pr.n_time, "n_markers": pr.n_marker, "n_marker_obs": pr.n_mobs,
+                           "n_corner_obs": 4 * pr.n_mobs}
+            self.sharded = "frames"
+        self.params = self.local[-1]
+        self.h2d = sum(np.asarray(a).nbytes for a in self.local[1:]) + pr.intr.nbytes
+
+    def set_model(self, P):
+        pr = self.pr
+        if self.model == "A":
+            n_pt, cam, pt, obs, _ = self.local
+            P.set_model_a(pr.n_cam, n_pt, cam, pt, obs, pr.intr)
+        else:
+            n_time, ti, ci, mi, obs8, _ = self.local
+            P.set_model_b(pr.n_cam, n_time, pr.n_marker, ti, ci, mi, obs8, pr.intr, pr.marker_side, True)
+
+    def oracle_solver(self, O):
+        n_kept = self.pr.n_cam if self.model == "A" else self.pr.n_cam + self.pr.n_marker
+        return O.SCHUR_DENSE if 6 * n_kept <= 768 else O.SCHUR_PCG
+
+    def oracle_solve(self, O, opts, threads):
+        pr = self.pr
+        if self.model == "A":
+            return O.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opts,
+                                   linear_solver=self.oracle_solver(O), n_threads=threads)
+        return O.solve_model_b(pr, pr.intr, pr.marker_side, True, options=opts, linear_solver=self.oracle_solver(O), n_threads=threads)
 
 
 class ClockSampler:
@@ -140,7 +185,7 @@ def run_steps(P, opts, k):
     return P.solve_end()
 
 
-def oracle_steps(pr, k, threads, linear_solver):
+def oracle_steps(job, k, threads):
     """The reference arm: the CPU oracle on the same workload, same restart rule; returns (seconds, rows)."""
     from oracle import oracle_py as O
     o = O.default_options()
@@ -150,8 +195,7 @@ def oracle_steps(pr, k, threads, linear_solver):
         n = min(ITERS_PER_SOLVE, k - done)
         o.max_num_iterations = n
         t0 = time.perf_counter()
-        _, s, rows = O.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=o,
-                                     linear_solver=linear_solver, n_threads=threads)
+        _, s, rows = job.oracle_solve(O, o, threads)
         t += time.perf_counter() - t0
         done += n
     return t, rows
@@ -179,11 +223,11 @@ def main():
         if rank != 0:
             return 0
         from oracle import oracle_py as O
-        pr = make_workload(a.workload)
+        job = Job(a.workload, 0, 1)
         threads = O.max_threads()
         if W > 0:
-            oracle_steps(pr, min(W, 1), threads, O.SCHUR_DENSE if pr.n_cam <= 64 else O.SCHUR_PCG)
-        secs, rows = oracle_steps(pr, K, threads, O.SCHUR_DENSE if pr.n_cam <= 64 else O.SCHUR_PCG)
+            oracle_steps(job, min(W, 1), threads)
+        secs, rows = oracle_steps(job, K, threads)
         v = K / secs
         print(json.dumps({
             "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": K, "warmup": W,
@@ -207,8 +251,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    pr = make_workload(a.workload)
-    n_pt_l, cam_l, pt_l, obs_l, par_l = shard_model_a(pr, rank, world)
+    job = Job(a.workload, rank, world)
+    pr, par_l = job.pr, job.params
     stream = torch.cuda.Stream()
     P = cuda.Problem(local_rank)
     P.set_stream(stream.cuda_stream)
@@ -223,7 +267,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident measurement ("value") ----------------------------------------------------
-    P.set_model_a(pr.n_cam, n_pt_l, cam_l, pt_l, obs_l, pr.intr)
+    job.set_model(P)
     P.set_parameters(par_l)
     P.save_parameters()
     opts = bench_options(cuda, profile=False)
@@ -280,10 +324,11 @@ def main():
             t = torch.tensor([jms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             jms = float(t.item())
-        jac_mobs = pr.n_obs / 1e6 / (jms * 1e-3)   # whole job: shards run concurrently
-        gbs = 184.0 * pr.n_obs / world / (jms * 1e-3) / 1e9
-        jacobian = {"kernel": "k_jac_a", "ms": jms, "mobs_per_sec": jac_mobs, "algorithmic_bytes_per_obs": 184,
-                    "achieved_gbs_per_gpu": gbs, "frac_of_hbm_peak": gbs / peak}
+        jac_mobs = job.n_obs / 1e6 / (jms * 1e-3)   # whole job: shards run concurrently
+        gbs = job.jac_bytes_per_obs * job.n_obs / world / (jms * 1e-3) / 1e9
+        jacobian = {"kernel": "k_jac_a" if job.model == "A" else "k_jac_b", "ms": jms, "mobs_per_sec": jac_mobs,
+                    "unit_of_obs": "corner observation (2 residuals)" if job.model == "A" else "marker observation (8 residuals)",
+                    "algorithmic_bytes_per_obs": job.jac_bytes_per_obs, "achieved_gbs_per_gpu": gbs, "frac_of_hbm_peak": gbs / peak}
 
     # roofline of the dominant kernel
     timed = [s for s in stats if s["total_ms"] > 0 and s["algorithmic_bytes_per_launch"] > 0]
@@ -304,7 +349,7 @@ def main():
     e2e = None
     if not a.no_e2e:
         opts_e = bench_options(cuda, profile=False)
-        h2d = cam_l.nbytes + pt_l.nbytes + np.asarray(obs_l).nbytes + pr.intr.nbytes + par_l.nbytes
+        h2d = job.h2d
         d2h = par_l.nbytes
         def e2e_solves(k):
             done = 0
@@ -312,7 +357,7 @@ def main():
             while done < k:
                 n = min(ITERS_PER_SOLVE, k - done)
                 opts_e.max_num_iterations = n
-                P.set_model_a(pr.n_cam, n_pt_l, cam_l, pt_l, obs_l, pr.intr)
+                job.set_model(P)
                 P.set_parameters(par_l)
                 P.solve(opts_e)
                 x = P.get_parameters()
@@ -338,18 +383,24 @@ def main():
         from oracle import oracle_py as O
         threads = O.max_threads()
         kc = min(K, ITERS_PER_SOLVE)
-        secs, _ = oracle_steps(pr, kc, threads, O.SCHUR_DENSE if pr.n_cam <= 64 else O.SCHUR_PCG)
+        secs, _ = oracle_steps(job, kc, threads)
         cpu = {"value": kc / secs, "unit": unit, "cores": threads, "kind": "port",
                "sample": "full workload, one solve of %d LM iterations (problem construction + initial evaluation included), "
                          "oracle/ba_oracle.cpp with OpenMP" % kc}
 
+    ws_mb = job.n_obs * (job.jac_bytes_per_obs if job.model == "B" else 72) / 1e6 / world
+    l2_note = ("per-step working set of %.0f MB per rank exceeds the 126 MB L2; no explicit flush" % ws_mb if ws_mb > 126 else
+               "per-step working set of %.0f MB per rank fits the 126 MB L2 (this is the reference's own problem size); no flush: the "
+               "real workload is L2 resident too" % ws_mb)
     if rank == 0:
         out = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": a.workload, "description": wl["desc"], "n_cameras": pr.n_cam, "n_points": pr.n_pt, "n_obs": pr.n_obs,
-                       "iters_per_solve": ITERS_PER_SOLVE, "parallelism": "points sharded over %d rank(s), cameras replicated" % world,
-                       "l2": "working set (Jacobian %.0f MB per rank) exceeds the 126 MB L2; no explicit flush" % (pr.n_obs * 160 / 1e6 / world),
+            "config": {"workload": a.workload, "description": wl["desc"], **job.blocks,
+                       "iters_per_solve": ITERS_PER_SOLVE,
+                       "parallelism": "%s sharded over %d rank(s), kept blocks (cameras%s) replicated" %
+                                      (job.sharded, world, "" if job.model == "A" else ", markers"),
+                       "l2": l2_note,
                        "rcs_solver": {1: "dense_cholesky", 2: "pcg"}.get(int(summary.rcs_solver_used), "?"), "rcs_dim": int(summary.rcs_dim)},
             "jacobian_mobs_per_sec": jac_mobs, "jacobian": jacobian, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "final_cost_last_solve": float(summary.final_cost), "ms_per_step_profiled_pass": ms_prof / K,

@@ -15,6 +15,7 @@
 #include <string>
 
 #include "ba_dense.cuh"
+#include "ba_dense_blocked.cuh"
 #include "ba_kernels.cuh"
 #include "ba_structure.cuh"
 #include "ba_rcs.cuh"
@@ -110,6 +111,7 @@ struct ba_cuda_problem {
   // reduced camera system: block-sparse pattern (shared by all ranks), values, PCG workspace
   RcsPattern R;
   PcgWork pcg;
+  CholBlockedWork cholb;
   DVec<double> Sb;           // R.nd * 36 block values | nf * 6 rhs correction (one collective covers both)
   int solver = 0;            // ba_rcs_solver resolved for the current solve
   FusedA FA;                 // Model A: tile structure of the fused two-pass pipeline
@@ -257,6 +259,14 @@ int allreduce_with_grad_tail(ba_cuda_problem* p, double* buf, size_t n) {
   k_unpack_grad_tail<<<1, 32, 0, p->st>>>(buf + n, p->world, p->scal.p);
   BA_CUDA_TRY(cudaGetLastError());
   return BA_OK;
+}
+
+// dense RCS solve: whole matrix in one CTA's shared memory while it fits, blocked DMMA Cholesky over the GPU above
+int dense_solve(ba_cuda_problem* p, int64_t n) {
+  // measured on B200: n = 132 (cfg2) 0.18 ms blocked vs 0.24 ms single CTA; below ~96 the single CTA wins (one launch, no grid barrier)
+  static const int smem_max_n = env_int("BA_DENSE_SMEM_MAX_N", 0, CHOL_SMEM_MAX_N, 96);
+  if (n <= smem_max_n) return launch_chol_solve((int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p, p->st);
+  return launch_chol_blocked(p->cholb, (int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p, p->device, p->st);
 }
 
 // Multi-GPU: every rank only knows the destination blocks its own shard couples; the stored pattern has to be
@@ -479,7 +489,7 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
     BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_dense, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->HG.p, NV_F, p->vsum(), 6, radius, opt.min_lm_diagonal,
               opt.max_lm_diagonal, n, p->Sd.p, p->rhs.p);
     LaunchScope scope(p, KT_RCS);
-    BA_TRY(launch_chol_solve((int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p, p->st));
+    BA_TRY(dense_solve(p, n));
   }
   fam_end(p, F_SOLVE);
   fam_begin(p, F_UPDATE);
@@ -645,7 +655,7 @@ int fa_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
     BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_dense, grid_for(S.nf * 6, 128), 128, 0, S.nf, F.camacc.p, FA_NVC, F.camacc.p + 27, FA_NVC, radius,
               opt.min_lm_diagonal, opt.max_lm_diagonal, n, p->Sd.p, p->rhs.p);
     LaunchScope scope(p, KT_RCS);
-    BA_TRY(launch_chol_solve((int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p, p->st));
+    BA_TRY(dense_solve(p, n));
   }
   fam_end(p, F_SOLVE);
   fam_begin(p, F_UPDATE);
@@ -672,7 +682,8 @@ bool lm_fused(const ba_cuda_problem* p) { return p->model == 0 && p->use_fused &
 // Resolves options.rcs_solver for this problem and makes sure the matching RCS storage exists.
 // BA_RCS_AUTO: dense Cholesky while the system is rig sized (Ceres DENSE_SCHUR, what the reference asks for),
 // block-sparse PCG above.
-constexpr int64_t kDenseAutoMaxN = 768;
+constexpr int64_t kDenseAutoMaxN = 1536;   // rigs (cameras + markers); BAL-scale camera counts go to PCG
+constexpr int64_t kDenseMaxN = 16384;      // 2 GiB of fp64
 int prepare_solver(ba_cuda_problem* p, const ba_cuda_options& opt) {
   const Structure& S = p->S;
   const int64_t n = p->n_rcs();
@@ -680,8 +691,8 @@ int prepare_solver(ba_cuda_problem* p, const ba_cuda_options& opt) {
   if (want == BA_RCS_AUTO) want = n <= kDenseAutoMaxN ? BA_RCS_DENSE_CHOLESKY : BA_RCS_PCG;
   if (want != BA_RCS_DENSE_CHOLESKY && want != BA_RCS_PCG) return fail(BA_ERR_INVALID_ARGUMENT, "unknown rcs_solver %d", opt.rcs_solver);
   if (want == BA_RCS_DENSE_CHOLESKY) {
-    if (2 * (size_t)n * sizeof(double) > 200 * 1024)
-      return fail(BA_ERR_UNSUPPORTED, "dense RCS of dimension %lld is too large for the single-CTA Cholesky; use BA_RCS_PCG", (long long)n);
+    if (n > kDenseMaxN)
+      return fail(BA_ERR_UNSUPPORTED, "dense RCS of dimension %lld is too large; use BA_RCS_PCG", (long long)n);
     if (p->Sd.n != (size_t)(n * n + n)) BA_TRY(p->Sd.alloc(n * n + n));
   } else {
     if (p->R.nd == 0 || p->R.nf != S.nf) {

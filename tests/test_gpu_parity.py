@@ -169,6 +169,32 @@ def test_solve_synthetic_vs_oracle(gpu, oracle, name):
         assert np.abs(x - xo).max() < POSE_ATOL
 
 
+@pytest.mark.parametrize("name", ["balA_n720", "rigB_n384", "balA_n1806_forced"])
+def test_blocked_dense_cholesky_vs_oracle(gpu, oracle, name):
+    # reduced camera systems too large for one CTA's shared memory (n > 160): blocked DMMA Cholesky over the whole GPU
+    # (ba_dense_blocked.cuh); n not a multiple of the 32-wide panel / 64-wide tile in every case
+    opt_g, opt_o = cuda.default_options(), oracle.default_options()
+    for o in (opt_g, opt_o):
+        o.rcs_solver = abi.RCS_DENSE_CHOLESKY
+        o.max_num_iterations = 8
+    if name == "rigB_n384":
+        pr = S.marker_rig_b(6, 60, 40, 9, visibility=0.5)
+        pb = F.ModelBFile(pr.n_time, pr.n_cam, pr.n_marker, pr.counts, pr.time_idx, pr.cam_idx, pr.marker_idx, pr.obs8, pr.params)
+        _set_b(gpu, pb, pr.intr, pr.marker_side, 1)
+        xo, so, rows_o = oracle.solve_model_b(pb, pr.intr, pr.marker_side, 1, options=opt_o)
+    else:
+        pr = S.bal_like(120, 8000, 5, 16, 21) if name == "balA_n720" else S.bal_like(301, 12000, 5, 20, 23)
+        gpu.set_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr)
+        gpu.set_parameters(pr.params)
+        xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o,
+                                              n_threads=4)
+    s, rows = gpu.solve(opt_g)
+    x = gpu.get_parameters()
+    assert s.rcs_solver_used == abi.RCS_DENSE_CHOLESKY and s.rcs_dim == so.rcs_dim > 160
+    _check_rows(rows, rows_o)
+    assert np.abs(x - xo).max() < POSE_ATOL
+
+
 @pytest.mark.parametrize("seed,perturb", [(24, (0.25, 0.07)), (27, (0.3, 0.08))])
 def test_rejected_steps_follow_the_same_schedule(gpu, oracle, seed, perturb):
     # a poor start makes LM overshoot: rejected steps (2 resp. 3 of them), radius halving / quartering, then recovery.
