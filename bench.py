@@ -337,8 +337,17 @@ def main():
         top = max(timed, key=lambda s: s["total_ms"])
         avg_s = top["total_ms"] / top["launches"] * 1e-3
         ach = top["algorithmic_bytes_per_launch"] / avg_s / 1e9
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                ent = json.load(f).get(a.workload, {}).get(top["name"])
+            if ent and world == 1:
+                traffic, traffic_src = ent["bytes"], ent["source"]
+        except (OSError, ValueError):
+            pass
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_s * 1e3, "launches": top["launches"],
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"], "peak_source": peak_src, "avg_launch_ms": avg_s * 1e3, "launches": top["launches"],
                     "share_of_step": top["total_ms"] / ms_prof,
                     "all_kernels": [{"name": s["name"], "launches": s["launches"], "ms_per_launch": s["total_ms"] / s["launches"],
                                      "share": s["total_ms"] / ms_prof,
