@@ -93,6 +93,20 @@ class Job:
         self.params = self.local[-1]
         self.h2d = sum(np.asarray(a).nbytes for a in self.local[1:]) + pr.intr.nbytes
 
+    def pin(self):
+        """The rank-local input arrays (and nothing else) move to pinned host memory, as the e2e contract says: the
+        library's cudaMemcpyAsync calls then run as direct DMA instead of being staged by the driver."""
+        import torch
+
+        def pinned(a):
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            self._keep.append(t)
+            return t.numpy()
+        self._keep = []
+        self.local = (self.local[0],) + tuple(pinned(a) for a in self.local[1:])
+        self.params = self.local[-1]
+        self.result = pinned(np.zeros_like(self.params))   # where ba_cuda_get_parameters writes the solution
+
     def set_model(self, P):
         pr = self.pr
         if self.model == "A":
@@ -252,6 +266,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     job = Job(a.workload, rank, world)
+    job.pin()
     pr, par_l = job.pr, job.params
     stream = torch.cuda.Stream()
     P = cuda.Problem(local_rank)
@@ -369,7 +384,7 @@ def main():
                 job.set_model(P)
                 P.set_parameters(par_l)
                 P.solve(opts_e)
-                x = P.get_parameters()
+                x = P.get_parameters(out=job.result)
                 done += n
             return x
         e2e_solves(min(W, ITERS_PER_SOLVE) or 1)

@@ -885,14 +885,29 @@ void lm_end(ba_cuda_problem* p, ba_cuda_summary* sum) {
   if (sum) *sum = Z;
 }
 
-// number of active blocks (host side, from the CSR pointers)
+// index validation on the device (a host loop over 30M observations costs more than the upload): first offender wins
+__global__ void k_validate_a(int64_t n, const int32_t* __restrict__ cam, const int32_t* __restrict__ pt, int32_t n_cam, int64_t n_pt,
+                             unsigned long long* __restrict__ first_bad) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (cam[i] < 0 || cam[i] >= n_cam || pt[i] < 0 || pt[i] >= n_pt) atomicMin(first_bad, (unsigned long long)i);
+}
+__global__ void k_count_active(const int64_t* __restrict__ ptr, int64_t n, unsigned long long* __restrict__ count) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int active = (i < n && ptr[i + 1] > ptr[i]) ? 1 : 0;
+  const unsigned ballot = __ballot_sync(0xffffffffu, active);
+  if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(count, (unsigned long long)__popc(ballot));
+}
+
+// number of active blocks (from the CSR pointers)
 int count_active(ba_cuda_problem* p, const DVec<int64_t>& ptr, int64_t nblk, int64_t* out) {
-  std::vector<int64_t> h(nblk + 1);
-  BA_CUDA_TRY(cudaMemcpyAsync(h.data(), ptr.p, sizeof(int64_t) * (nblk + 1), cudaMemcpyDeviceToHost, p->st));
+  DVec<unsigned long long> cnt;
+  BA_TRY(cnt.alloc_zero(1, p->st));
+  k_count_active<<<grid_for(nblk, 256), 256, 0, p->st>>>(ptr.p, nblk, cnt.p);
+  unsigned long long h = 0;
+  BA_CUDA_TRY(cudaMemcpyAsync(&h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, p->st));
   BA_CUDA_TRY(cudaStreamSynchronize(p->st));
-  int64_t c = 0;
-  for (int64_t i = 0; i < nblk; ++i) c += h[i + 1] > h[i] ? 1 : 0;
-  *out = c;
+  *out = (int64_t)h;
   return BA_OK;
 }
 
@@ -1189,18 +1204,29 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
       (intr_stride != 0 && intr_stride != 4))
     return fail(BA_ERR_INVALID_ARGUMENT, "ba_cuda_set_model_a: bad arguments");
   if (n_pt >= (int64_t)INT32_MAX) return fail(BA_ERR_UNSUPPORTED, "too many points for one GPU shard");
-  for (int64_t i = 0; i < n_obs; ++i)
-    if (cam_idx[i] < 0 || cam_idx[i] >= n_cam || pt_idx[i] < 0 || pt_idx[i] >= n_pt)
-      return fail(BA_ERR_INVALID_ARGUMENT, "observation %lld references camera %d / point %d out of range", (long long)i, cam_idx[i], pt_idx[i]);
   PhaseTimer T;
-  T.lap("validate indices");
   BA_TRY(use_device(p));
   reset_problem(p);
   T.lap("reset");
   p->n_cam = n_cam; p->n_pt = n_pt; p->n_time = 0; p->n_marker = 0;
   p->n_params = 6 * (int64_t)n_cam + 3 * n_pt;
-  BA_TRY(build_structure(p->S, n_obs, n_pt, n_cam, pt_idx, cam_idx, nullptr, p->st));
-  T.lap("build_structure");
+  {
+    const int rc = build_structure(p->S, n_obs, n_pt, n_cam, pt_idx, cam_idx, nullptr, p->st, [&](const int32_t* d_pt, const int32_t* d_cam) {
+      // the uploaded index arrays are checked on the device before anything is built from them
+      DVec<unsigned long long> bad;
+      BA_TRY(bad.alloc(1));
+      BA_CUDA_TRY(cudaMemsetAsync(bad.p, 0xff, sizeof(unsigned long long), p->st));
+      k_validate_a<<<grid_for(n_obs, 256), 256, 0, p->st>>>(n_obs, d_cam, d_pt, n_cam, n_pt, bad.p);
+      unsigned long long h = 0;
+      BA_CUDA_TRY(cudaMemcpyAsync(&h, bad.p, sizeof(h), cudaMemcpyDeviceToHost, p->st));
+      BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+      if (h != ~0ull)
+        return fail(BA_ERR_INVALID_ARGUMENT, "observation %lld references camera %d / point %d out of range", (long long)h, cam_idx[h], pt_idx[h]);
+      return (int)BA_OK;
+    });
+    if (rc != BA_OK) { reset_problem(p); return rc; }
+  }
+  T.lap("upload + validate + build_structure");
   p->model = 0;
   // observations in sorted order, intrinsics per f-block
   {
@@ -1251,7 +1277,8 @@ int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32
   p->n_params = 6 * ((int64_t)n_cam + n_time + n_marker);
   p->half_side = marker_side / 2;
   const int64_t nf = (int64_t)n_cam + n_marker;
-  BA_TRY(build_structure(p->S, n_mobs, n_time, nf, time_idx, f0.data(), f1.data(), p->st));
+  BA_TRY(build_structure(p->S, n_mobs, n_time, nf, time_idx, f0.data(), f1.data(), p->st,
+                         [](const int32_t*, const int32_t*) { return (int)BA_OK; }));  // validated above, on the host
   p->model = 1;
   {
     DVec<double> tmp;

@@ -215,8 +215,9 @@ inline int sort_to_csr(const int32_t* keys_in, const int32_t* vals_in, int64_t n
 }
 
 // h_e / h_f0 / h_f1 are in the caller's observation order; h_f1 may be NULL (one f slot).
+template <typename Validate>
 inline int build_structure(Structure& S, int64_t nb, int64_t ne, int64_t nf, const int32_t* h_e, const int32_t* h_f0,
-                           const int32_t* h_f1, cudaStream_t st) {
+                           const int32_t* h_f1, cudaStream_t st, Validate&& validate) {
   if (nb >= (int64_t)1 << 30) return fail(BA_ERR_UNSUPPORTED, "more than 2^30 residual blocks per GPU are not supported");
   S.nb = nb; S.ne = ne; S.nf = nf; S.nslots = h_f1 ? 2 : 1;
   const int B = 256;
@@ -224,6 +225,7 @@ inline int build_structure(Structure& S, int64_t nb, int64_t ne, int64_t nf, con
   BA_TRY(e_in.upload(h_e, nb, st));
   BA_TRY(f0_in.upload(h_f0, nb, st));
   if (h_f1) BA_TRY(f1_in.upload(h_f1, nb, st));
+  BA_TRY(validate(e_in.p, f0_in.p));
   BA_TRY(iota.alloc(nb));
   k_iota<<<grid_for(nb, B), B, 0, st>>>(iota.p, nb, 0);
   // 1. observations sorted by e (stable)

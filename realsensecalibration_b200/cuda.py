@@ -141,9 +141,11 @@ class Problem:
         x = np.ascontiguousarray(params, np.float64)
         _check(lib().ba_cuda_set_parameters(self._h, x.ctypes, C.c_int64(x.shape[0])))
 
-    def get_parameters(self):
-        x = np.zeros(self.num_parameters(), np.float64)
-        _check(lib().ba_cuda_get_parameters(self._h, x.ctypes, C.c_int64(x.shape[0])))
+    def get_parameters(self, out=None):
+        """`out`: an optional float64 array of num_parameters() to receive the result (e.g. pinned memory)."""
+        x = np.empty(self.num_parameters(), np.float64) if out is None else out
+        assert x.dtype == np.float64 and x.flags.c_contiguous and x.size == self.num_parameters()
+        _check(lib().ba_cuda_get_parameters(self._h, x.ctypes, C.c_int64(x.size)))
         return x
 
     def save_parameters(self):
