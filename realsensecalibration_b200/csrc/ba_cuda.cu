@@ -324,11 +324,24 @@ int build_tables(ba_cuda_problem* p, bool candidate) {
   return BA_OK;
 }
 
+FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt);
+int fa_set_smem_attr();
+
 // K1 at the current parameters: residuals, scaled Jacobian, sum of squares -> scal[S_COST]
 int run_jacobian(ba_cuda_problem* p) {
   const Structure& S = p->S;
   BA_TRY(build_tables(p, false));
   int grid;
+  if (p->model == 0 && p->use_fused) {  // the tile structure exists: tables staged in shared memory, J leaves as full lines
+    BA_TRY(fa_set_smem_attr());
+    ba_cuda_options o;
+    ba_cuda_options_init(&o);
+    const FaParams P = fa_params(p, o);
+    grid = p->FA.n_tiles;
+    BA_LAUNCH(p, KT_JAC, k_fa_jac, grid, p->FA.threads, p->FA.smemj(), P);
+    BA_CUDA_TRY(cudaGetLastError());
+    return fold(p, p->fa_part.p, grid, S_COST);
+  }
   if (p->model == 0) {
     grid = (int)grid_for(S.nb, 256);
     BA_LAUNCH(p, KT_JAC, k_jac_a, grid, 256, 0, S.nb, S.ob_e.p, S.ob_f0.p, p->uv.p, p->tab_f.p, p->xe.p, p->se.p, p->RES.p,
@@ -520,12 +533,11 @@ FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt) {
   FusedA& F = p->FA;
   const size_t nt = (size_t)F.n_tiles;
   FaParams P;
-  P.tile_pt_ptr = F.tile_pt_ptr.p; P.e_ptr = S.e_ptr.p; P.ob_e = S.ob_e.p; P.ob_f = S.ob_f0.p; P.ob_slot = F.ob_slot.p; P.uv = p->uv.p;
-  P.tile_cam_ptr = F.cams.tile_group_ptr.p; P.tile_cams = F.cams.group_target.p; P.cap = F.cap;
-  P.tile_pent_ptr = F.tile_pent_ptr.p; P.tile_cent_ptr = F.tile_cent_ptr.p;
+  P.tiles = F.tiles.p; P.e_ptr = S.e_ptr.p; P.ob_e = S.ob_e.p; P.ob_f = S.ob_f0.p; P.ob_slot = F.ob_slot.p; P.uv = p->uv.p;
+  P.tile_cams = F.cams.group_target.p; P.cap = F.cap;
   P.pts_cap = F.pts_cap; P.tcam = F.tcam; P.tcs = F.tcs; P.pent_cap = F.pent_cap;
-  P.tile_pitem_ptr = F.pairs.tile_item_ptr.p; P.pitem_begin = F.pairs.item_begin.p; P.pitem_end = F.pairs.item_end.p; P.pent = F.pairs.ent.p;
-  P.tile_citem_ptr = F.cams.tile_item_ptr.p; P.citem_begin = F.cams.item_begin.p; P.citem_end = F.cams.item_end.p; P.cent = F.cams.ent.p;
+  P.pitem_begin = F.pairs.item_begin.p; P.pitem_end = F.pairs.item_end.p; P.pent = F.pairs.ent.p;
+  P.citem_begin = F.cams.item_begin.p; P.citem_end = F.cams.item_end.p; P.cent = F.cams.ent.p;
   P.xe = p->xe.p; P.se = p->se.p; P.tab_f = p->tab_f.p; P.radius = p->scal.p + S_RADIUS;
   P.min_diag = opt.min_lm_diagonal; P.max_diag = opt.max_lm_diagonal;
   P.partP = F.partP.p; P.partC = F.partC.p; P.Lz = F.Lz.p; P.se_out = p->se.p;
@@ -533,6 +545,7 @@ FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt) {
   P.yf = p->yf.p; P.tabc_f = p->tabc_f.p; P.xe_c = p->xe_c.p;
   P.mcc_partial = p->fa_part.p + 3 * nt; P.x2_partial = p->fa_part.p + 4 * nt; P.d2_partial = p->fa_part.p + 5 * nt;
   P.cand_partial = p->fa_part.p + 6 * nt;
+  P.RES = p->RES.p; P.JE = p->JE.p; P.JF = p->JF0.p;
   P.status = p->status.p;
   return P;
 }
@@ -544,6 +557,7 @@ int fa_set_smem_attr() {
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_jac, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     done = true;
   }
   return BA_OK;

@@ -46,6 +46,40 @@ constexpr int FA_REC2 = 10;                  // pass 2
 constexpr int FA_PENT_MAX = 6144;            // pair entries staged in shared memory per tile (24 KB)
 constexpr size_t FA_SMEM_MAX = 231000;      // dynamic shared memory per CTA (232448 opt-in limit minus the static part)
 constexpr int FA_LS = 10;                    // per point in shared memory: L10 L20 L21 | 1/L00 1/L11 1/L22 | z (3) | pad
+constexpr int FA_PS2 = 7;                    // pass 2 / k_fa_jac, per point in shared memory: x_e (3, then the candidate) | scale (3) | pad (odd stride)
+constexpr int FA_RECJ = 18;                  // k_fa_jac record: J_e (6) | J_f (12); 9 x 16 B: odd, conflict free for double2
+
+// Everything a CTA needs to know about its tile in one 96-byte record (one L2 round trip instead of a chain of
+// dependent pointer loads): built once per problem by k_fa_tile_desc.
+struct __align__(16) FaTile {
+  int64_t pt0, ob0, cam0, pe0, ce0, pitem0, citem0;    // first point / observation / camera-list entry / pair entry / camera entry / items
+  int32_t npts, nobs, ncam, npe, nce, npitem, ncitem;  // counts (unclamped)
+  int32_t pad_[3];
+};
+static_assert(sizeof(FaTile) == 96, "FaTile is loaded as six 16-byte words");
+
+
+__global__ void k_fa_tile_desc(int n_tiles, const int64_t* __restrict__ tile_pt_ptr, const int64_t* __restrict__ e_ptr,
+                               const int64_t* __restrict__ tile_cam_ptr, const int64_t* __restrict__ tile_pent_ptr,
+                               const int64_t* __restrict__ tile_cent_ptr, const int64_t* __restrict__ tile_pitem_ptr,
+                               const int64_t* __restrict__ tile_citem_ptr, FaTile* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const int64_t cap32 = INT32_MAX;
+  FaTile T;
+  T.pt0 = tile_pt_ptr[t];
+  const int64_t pt1 = tile_pt_ptr[t + 1];
+  T.ob0 = e_ptr[T.pt0];
+  T.npts = (int32_t)(pt1 - T.pt0);
+  T.nobs = (int32_t)(e_ptr[pt1] - T.ob0);
+  T.cam0 = tile_cam_ptr[t];   T.ncam = (int32_t)min(tile_cam_ptr[t + 1] - T.cam0, cap32);
+  T.pe0 = tile_pent_ptr[t];   T.npe = (int32_t)min(tile_pent_ptr[t + 1] - T.pe0, cap32);
+  T.ce0 = tile_cent_ptr[t];   T.nce = (int32_t)min(tile_cent_ptr[t + 1] - T.ce0, cap32);
+  T.pitem0 = tile_pitem_ptr[t]; T.npitem = (int32_t)min(tile_pitem_ptr[t + 1] - T.pitem0, cap32);
+  T.citem0 = tile_citem_ptr[t]; T.ncitem = (int32_t)min(tile_citem_ptr[t + 1] - T.citem0, cap32);
+  T.pad_[0] = T.pad_[1] = T.pad_[2] = 0;
+  out[t] = T;
+}
 
 // work items of one kind (pair items or camera items) and the static reduction lists over their partial blocks
 struct ItemSet {
@@ -73,6 +107,7 @@ struct FusedA {
   DVec<int64_t> tile_cent_ptr;  // n_tiles + 1: the tile's slice of cams.ent
   ItemSet pairs, cams;
   DVec<uint16_t> ob_slot;       // per observation: slot of its camera in the tile's camera list
+  DVec<FaTile> tiles;           // n_tiles descriptors
   DVec<double> partP, partC, red1P, red1C, camacc, Lz;
   // shared-memory geometry, from the maxima over the tiles of this problem (so that small tiles co-reside on an SM)
   int pts_cap = FA_TPTS;        // points of the fullest tile
@@ -82,7 +117,8 @@ struct FusedA {
   size_t smem1() const {
     return ((size_t)cap * FA_REC + (size_t)pts_cap * FA_LS + (size_t)tcs * TAB) * 8 + ((size_t)pent_cap + cap) * 4 + (size_t)cap * 2;
   }
-  size_t smem2() const { return ((size_t)cap * FA_REC2 + (size_t)pts_cap * 3 + (size_t)tcs * (TAB + 16)) * 8; }
+  size_t smem2() const { return ((size_t)cap * FA_REC2 + (size_t)pts_cap * FA_PS2 + (size_t)tcs * (TAB + 16)) * 8; }
+  size_t smemj() const { return ((size_t)cap * FA_RECJ + (size_t)pts_cap * FA_PS2 + (size_t)tcs * TAB) * 8; }
 };
 
 __global__ void k_fa_tile_flags(const int64_t* __restrict__ e_ptr, int64_t ne, int tobs, int32_t* __restrict__ flag, int* __restrict__ kmax) {
@@ -348,8 +384,11 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
       const size_t excess = (F.smem1() - FA_SMEM_MAX + 7) / 8 * 2;
       F.pent_cap = (size_t)F.pent_cap > excess ? F.pent_cap - (int)excess : 0;
     }
-    if (F.smem1() > FA_SMEM_MAX || F.smem2() > FA_SMEM_MAX) return BA_ERR_UNSUPPORTED;
+    if (F.smem1() > FA_SMEM_MAX || F.smem2() > FA_SMEM_MAX || F.smemj() > FA_SMEM_MAX) return BA_ERR_UNSUPPORTED;
   }
+  BA_TRY(F.tiles.alloc((size_t)F.n_tiles));
+  k_fa_tile_desc<<<grid_for(F.n_tiles, 256), 256, 0, st>>>(F.n_tiles, F.tile_pt_ptr.p, S.e_ptr.p, F.cams.tile_group_ptr.p, F.tile_pent_ptr.p,
+                                                          F.tile_cent_ptr.p, F.pairs.tile_item_ptr.p, F.cams.tile_item_ptr.p, F.tiles.p);
   BA_TRY(F.partP.alloc((size_t)F.pairs.n_items * 36)); BA_TRY(F.partC.alloc((size_t)F.cams.n_items * FA_NVC));
   BA_TRY(F.red1P.alloc((size_t)F.pairs.red_ch.n * 36)); BA_TRY(F.red1C.alloc((size_t)F.cams.red_ch.n * FA_NVC));
   BA_TRY(F.camacc.alloc((size_t)nf * FA_NVC + 2 + 64));  // tail: shard-local gradient scalars (ba_cuda.cu, kMaxWorld)
@@ -389,15 +428,15 @@ __device__ __forceinline__ void fa_linearize(const double* __restrict__ T, const
 __device__ __forceinline__ bool fa_chol3(const double* M /* m00 m01 m02 m11 m12 m22 */, double* Lp) {
   const double d0 = M[0];
   if (!(d0 > 0.0) || !isfinite(d0)) return false;
-  const double i0 = 1.0 / sqrt(d0);
+  const double i0 = rsqrt(d0);
   const double l10 = M[1] * i0, l20 = M[2] * i0;
   const double d1 = M[3] - l10 * l10;
   if (!(d1 > 0.0) || !isfinite(d1)) return false;
-  const double i1 = 1.0 / sqrt(d1);
+  const double i1 = rsqrt(d1);
   const double l21 = (M[4] - l20 * l10) * i1;
   const double d2 = M[5] - l20 * l20 - l21 * l21;
   if (!(d2 > 0.0) || !isfinite(d2)) return false;
-  Lp[0] = l10; Lp[1] = l20; Lp[2] = l21; Lp[3] = i0; Lp[4] = i1; Lp[5] = 1.0 / sqrt(d2);
+  Lp[0] = l10; Lp[1] = l20; Lp[2] = l21; Lp[3] = i0; Lp[4] = i1; Lp[5] = rsqrt(d2);
   return true;
 }
 __device__ __forceinline__ void fa_fwd3(const double* Lp, double* x) {  // x <- L^-1 x
@@ -413,11 +452,11 @@ __device__ __forceinline__ void fa_bwd3(const double* Lp, double* x) {  // x <- 
 
 struct FaParams {
   // structure
-  const int64_t* tile_pt_ptr; const int64_t* e_ptr; const int32_t* ob_e; const int32_t* ob_f; const uint16_t* ob_slot; const double2* uv;
-  const int64_t* tile_cam_ptr; const int32_t* tile_cams;
-  const int64_t* tile_pitem_ptr; const int64_t* pitem_begin; const int64_t* pitem_end; const int32_t* pent;
-  const int64_t* tile_citem_ptr; const int64_t* citem_begin; const int64_t* citem_end; const int32_t* cent;
-  const int64_t* tile_pent_ptr; const int64_t* tile_cent_ptr;
+  const FaTile* tiles;
+  const int64_t* e_ptr; const int32_t* ob_e; const int32_t* ob_f; const uint16_t* ob_slot; const double2* uv;
+  const int32_t* tile_cams;
+  const int64_t* pitem_begin; const int64_t* pitem_end; const int32_t* pent;
+  const int64_t* citem_begin; const int64_t* citem_end; const int32_t* cent;
   int cap, pts_cap, tcam, tcs, pent_cap;
   // state
   const double* xe; const double* se; const double* tab_f; const double* radius;
@@ -428,19 +467,37 @@ struct FaParams {
   // pass 2 inputs / outputs
   const double* yf; const double* tabc_f; double* xe_c;
   double* mcc_partial; double* x2_partial; double* d2_partial; double* cand_partial;
+  // standalone residual + Jacobian (k_fa_jac)
+  double* RES; double* JE; double* JF;
   int* status;
 };
 
-// the tile's camera tables -> shared memory, SoA [field][slot] so that lanes with different cameras hit different banks
-__device__ __forceinline__ int fa_stage_tables(const FaParams& P, int tile, const double* __restrict__ tab, double* tabs, int nfields,
-                                               const int* field_map) {
-  const int64_t c0 = P.tile_cam_ptr[tile];
-  const int ncam = min((int)(P.tile_cam_ptr[tile + 1] - c0), P.tcam);
-  for (int i = threadIdx.x; i < ncam * nfields; i += blockDim.x) {
-    const int slot = i / nfields, f = i % nfields;
-    tabs[f * P.tcs + slot] = __ldg(tab + (int64_t)TAB * P.tile_cams[c0 + slot] + (field_map ? field_map[f] : f));
+__device__ __forceinline__ FaTile fa_load_tile(const FaTile* __restrict__ p) {
+  FaTile T;
+  const int4* s = reinterpret_cast<const int4*>(p);
+  int4* d = reinterpret_cast<int4*>(&T);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) d[k] = __ldg(s + k);
+  return T;
+}
+
+// The tile's camera tables -> shared memory, SoA [field][slot] so that lanes with different cameras hit different
+// banks.  One warp per camera row: the (uniform) camera ids of four rows are fetched first, then lane f copies field f
+// of each row with an 8-byte cp.async, so nothing of this waits in a register; the caller commits and waits on the
+// pipeline.  nfields <= 32; field_map = nullptr copies fields 0 .. nfields-1.
+__device__ __forceinline__ void fa_stage_tables_async(const FaParams& P, const FaTile& T, const double* __restrict__ tab, double* tabs,
+                                                      int nfields, const int* field_map) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int ncam = min(T.ncam, P.tcam);
+  const int src_f = lane < nfields ? (field_map ? field_map[lane] : lane) : 0;
+  for (int s0 = warp; s0 < ncam; s0 += 4 * nw) {
+    int32_t cam[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int s = s0 + u * nw; cam[u] = s < ncam ? __ldg(P.tile_cams + T.cam0 + s) : -1; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (cam[u] >= 0 && lane < nfields) __pipeline_memcpy_async(tabs + lane * P.tcs + (s0 + u * nw), tab + (int64_t)TAB * cam[u] + src_f, 8);
   }
-  return ncam;
 }
 __device__ __forceinline__ void fa_get_table(const FaParams& P, const double* tabs, const double* __restrict__ tab, int slot, int32_t cam,
                                              double* T) {
@@ -452,54 +509,103 @@ __device__ __forceinline__ void fa_get_table(const FaParams& P, const double* ta
   }
 }
 
-// item index of a tile dealt boustrophedon over the threads: round r, thread t -> r * T + (r odd ? T - 1 - t : t)
-#define FA_FOR_ITEMS(it, first, count)                                                                   \
-  for (int64_t r__ = 0, it = 0; r__ * blockDim.x < (count); ++r__)                                       \
-    if ((it = r__ * blockDim.x + ((r__ & 1) ? blockDim.x - 1 - (int)threadIdx.x : (int)threadIdx.x)) < (count) && ((it += (first)), true))
+// three / four tile scalars through one barrier: warp trees, then warp 0 folds the per-warp values (the same fixed
+// tree as block_sum / block_max); result valid in thread 0
+__device__ __forceinline__ void fa_block_reduce(double* v, const bool* is_max, int n, double* red /* [n][32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  for (int k = 0; k < n; ++k) {
+    v[k] = is_max[k] ? warp_max(v[k]) : warp_sum(v[k]);
+    if (lane == 0) red[32 * k + warp] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0)
+    for (int k = 0; k < n; ++k) {
+      const double x = lane < nw ? red[32 * k + lane] : 0.0;
+      v[k] = is_max[k] ? warp_max(x) : warp_sum(x);
+    }
+}
 
-// the same dealt from the other end: the camera items go first to the threads whose pair items were the shortest
-#define FA_FOR_ITEMS_REV(it, first, count)                                                               \
-  for (int64_t r__ = 0, it = 0; r__ * blockDim.x < (count); ++r__)                                       \
-    if ((it = r__ * blockDim.x + ((r__ & 1) ? (int)threadIdx.x : blockDim.x - 1 - (int)threadIdx.x)) < (count) && ((it += (first)), true))
+// item index of a tile dealt boustrophedon over the threads: round r, thread t -> r * T + (r odd ? T - 1 - t : t);
+// the camera items are dealt from the other end, so they go first to the threads whose pair items were the shortest
+__device__ __forceinline__ int fa_item_index(int r, bool reverse) {
+  const int t = (int)threadIdx.x, n = (int)blockDim.x;
+  return r * n + ((((r & 1) != 0) != reverse) ? n - 1 - t : t);
+}
 
 // NORMS = true: iteration 0 only, unscaled Jacobian; writes the Jacobi scaling of the points and the camera items
 // (their F^T F diagonals are the camera column norms); no Schur products.
+//
+// Latency plan (the kernel is bound by dependent round trips, not by bytes or flops): the tile descriptor is one
+// load; the camera tables, the tile's points (x_e, scale) and the work-item entry lists arrive by cp.async while the
+// threads fetch, into registers, the first observation, the first point range and the first work items they will
+// handle -- so every phase after the first barrier starts from shared memory or registers.
 template <bool NORMS>
 __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
   extern __shared__ double smem[];
   double* rec = smem;                                   // [cap][FA_REC]: U (6) | Jf (12) | r (2) | w (2)
-  double* Ls = rec + (size_t)P.cap * FA_REC;            // [pts_cap][FA_LS]
+  double* Ls = rec + (size_t)P.cap * FA_REC;            // [pts_cap][FA_LS]: x_e (3) | scale (3), then L (6) | z (3)
   double* tabs = Ls + (size_t)P.pts_cap * FA_LS;        // [TAB][tcs]
   int32_t* pent_s = reinterpret_cast<int32_t*>(tabs + (size_t)P.tcs * TAB);  // [pent_cap] the tile's pair entries
   int32_t* cent_s = pent_s + P.pent_cap;                // [cap] the tile's camera-item entries
   uint16_t* oblp = reinterpret_cast<uint16_t*>(cent_s + P.cap);  // [cap] local point of an observation
-  __shared__ double red[32];
-  const int tile = blockIdx.x, tid = threadIdx.x;
-  const int64_t pt0 = P.tile_pt_ptr[tile], pt1 = P.tile_pt_ptr[tile + 1];
-  const int64_t ob0 = P.e_ptr[pt0], ob1 = P.e_ptr[pt1];
-  const int nobs = (int)(ob1 - ob0), npts = (int)(pt1 - pt0);
-  // the work-item entry lists of the tile -> shared memory, asynchronously (needed in phase B only): the item loops
-  // then never wait on L2 for their next entry
-  const int64_t pe0 = P.tile_pent_ptr[tile], ce0 = P.tile_cent_ptr[tile];
-  const int npe = NORMS ? 0 : (int)min(P.tile_pent_ptr[tile + 1] - pe0, (int64_t)P.pent_cap);
-  const int nce = (int)min(P.tile_cent_ptr[tile + 1] - ce0, (int64_t)P.cap);
-  for (int i = tid; i < npe; i += blockDim.x) __pipeline_memcpy_async(pent_s + i, P.pent + pe0 + i, 4);
-  for (int i = tid; i < nce; i += blockDim.x) __pipeline_memcpy_async(cent_s + i, P.cent + ce0 + i, 4);
+  __shared__ double red[96];
+  const int tile = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const FaTile T = fa_load_tile(P.tiles + tile);
+  const int64_t pt0 = T.pt0, ob0 = T.ob0, pe0 = T.pe0, ce0 = T.ce0;
+  const int nobs = T.nobs, npts = T.npts;
+  const int npe = NORMS ? 0 : min(T.npe, P.pent_cap);
+  const int nce = min(T.nce, P.cap);
+  // group 1 (needed by A1): camera tables, points
+  fa_stage_tables_async(P, T, P.tab_f, tabs, TAB, nullptr);
+  for (int i = tid; i < 3 * npts; i += nthr) {
+    const int lp = i / 3, k = i - 3 * lp;
+    __pipeline_memcpy_async(Ls + lp * FA_LS + k, P.xe + 3 * pt0 + i, 8);
+    if (!NORMS) __pipeline_memcpy_async(Ls + lp * FA_LS + 3 + k, P.se + 3 * pt0 + i, 8);
+  }
   __pipeline_commit();
-  fa_stage_tables(P, tile, P.tab_f, tabs, TAB, nullptr);
+  // group 2 (needed by B): the work-item entry lists
+  for (int i = tid; i < npe; i += nthr) __pipeline_memcpy_async(pent_s + i, P.pent + pe0 + i, 4);
+  for (int i = tid; i < nce; i += nthr) __pipeline_memcpy_async(cent_s + i, P.cent + ce0 + i, 4);
+  __pipeline_commit();
+  // registers: first work items, first point range, first observation of this thread
+  int pq0 = 0, pq1 = 0, cq0 = 0, cq1 = 0, pl0 = 0, pl1 = 0;
+  if (!NORMS && tid < T.npitem) {
+    pq0 = (int)(P.pitem_begin[T.pitem0 + tid] - pe0);
+    pq1 = (int)(P.pitem_end[T.pitem0 + tid] - pe0);
+  }
+  if (nthr - 1 - tid < T.ncitem) {
+    cq0 = (int)(P.citem_begin[T.citem0 + (nthr - 1 - tid)] - ce0);
+    cq1 = (int)(P.citem_end[T.citem0 + (nthr - 1 - tid)] - ce0);
+  }
+  if (tid < npts) {
+    pl0 = (int)(P.e_ptr[pt0 + tid] - ob0);
+    pl1 = (int)(P.e_ptr[pt0 + tid + 1] - ob0);
+  }
+  int32_t e_n = 0;
+  int slot_n = 0;
+  double2 uv_n = make_double2(0.0, 0.0);
+  if (tid < nobs) { e_n = P.ob_e[ob0 + tid]; slot_n = P.ob_slot[ob0 + tid]; uv_n = P.uv[ob0 + tid]; }
+  __pipeline_wait_prior(1);
   __syncthreads();
-  // ---- A1: one thread per observation ----
+  // ---- A1: one thread per observation (the next round's inputs are in flight while this one computes) ----
   double sq = 0.0;
-  for (int l = tid; l < nobs; l += blockDim.x) {
-    const int64_t o = ob0 + l;
-    const int64_t e = P.ob_e[o];
-    double T[TAB];
-    fa_get_table(P, tabs, P.tab_f, P.ob_slot[o], P.ob_f[o], T);
-    const double X[3] = {P.xe[3 * e], P.xe[3 * e + 1], P.xe[3 * e + 2]};
+  for (int l = tid; l < nobs; l += nthr) {
+    const int lp = (int)(e_n - pt0), slot = slot_n;
+    const double2 ob = uv_n;
+    if (l + nthr < nobs) { const int64_t o = ob0 + l + nthr; e_n = P.ob_e[o]; slot_n = P.ob_slot[o]; uv_n = P.uv[o]; }
+    double Tt[TAB];
+    if (slot < P.tcam) {
+#pragma unroll
+      for (int f = 0; f < TAB; ++f) Tt[f] = tabs[f * P.tcs + slot];
+    } else {
+      load_tab(P.tab_f, P.ob_f[ob0 + l], Tt);
+    }
+    const double* xs = Ls + lp * FA_LS;
+    const double X[3] = {xs[0], xs[1], xs[2]};
     double s[3] = {1.0, 1.0, 1.0};
-    if (!NORMS) { s[0] = P.se[3 * e]; s[1] = P.se[3 * e + 1]; s[2] = P.se[3 * e + 2]; }
+    if (!NORMS) { s[0] = xs[3]; s[1] = xs[4]; s[2] = xs[5]; }
     double r[2], je[6], jf[12];
-    fa_linearize(T, X, s, P.uv[o], r, je, jf);
+    fa_linearize(Tt, X, s, ob, r, je, jf);
     sq += r[0] * r[0] + r[1] * r[1];
     double2* R2 = reinterpret_cast<double2*>(rec + (size_t)l * FA_REC);
 #pragma unroll
@@ -508,15 +614,16 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
     for (int k = 0; k < 6; ++k) R2[3 + k] = make_double2(jf[2 * k], jf[2 * k + 1]);
     R2[9] = make_double2(r[0], r[1]);
     R2[10] = make_double2(0.0, 0.0);
-    oblp[l] = (uint16_t)(e - pt0);
+    oblp[l] = (uint16_t)lp;
   }
   __syncthreads();
   // ---- A2a: one thread per point ----
   double gmx = 0.0, g2 = 0.0;
   const double radius = *P.radius;
-  for (int lp = tid; lp < npts; lp += blockDim.x) {
+  for (int lp = tid; lp < npts; lp += nthr) {
     const int64_t e = pt0 + lp;
-    const int l0 = (int)(P.e_ptr[e] - ob0), l1 = (int)(P.e_ptr[e + 1] - ob0);
+    int l0 = pl0, l1 = pl1;
+    if (lp != tid) { l0 = (int)(P.e_ptr[e] - ob0); l1 = (int)(P.e_ptr[e + 1] - ob0); }
     double M[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};  // m00 m01 m02 m11 m12 m22
     for (int l = l0; l < l1; ++l) {
       const double* R = rec + (size_t)l * FA_REC;
@@ -531,11 +638,12 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
       P.se_out[3 * e] = 1.0 / (1.0 + sqrt(M[0])); P.se_out[3 * e + 1] = 1.0 / (1.0 + sqrt(M[3])); P.se_out[3 * e + 2] = 1.0 / (1.0 + sqrt(M[5]));
       continue;
     }
+    double* ls = Ls + lp * FA_LS;
     if (l1 > l0) {  // |x - Plus(x, -g)| of the unscaled gradient (TrustRegionMinimizer::EvaluateGradientAndJacobian)
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const double xv = P.xe[3 * e + k];
-        const double d = xv - (xv + (-(g[k] / P.se[3 * e + k])));
+        const double xv = ls[k];
+        const double d = xv - (xv + (-(g[k] / ls[3 + k])));
         gmx = fmax(gmx, fabs(d)); g2 += d * d;
       }
     }
@@ -551,18 +659,17 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
       Lp[0] = Lp[1] = Lp[2] = 0.0; Lp[3] = Lp[4] = Lp[5] = 1.0;
     }
     fa_fwd3(Lp, g);  // z
-    double* out = P.Lz + 9 * e;
-    double* ls = Ls + lp * FA_LS;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { out[k] = Lp[k]; ls[k] = Lp[k]; }
+    for (int k = 0; k < 6; ++k) ls[k] = Lp[k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { out[6 + k] = g[k]; ls[6 + k] = g[k]; }
+    for (int k = 0; k < 3; ++k) ls[6 + k] = g[k];
   }
   __pipeline_wait_prior(0);
   __syncthreads();
-  // ---- A2b: one thread per observation: U = L^-1 J_e^T (rows), w = U^T z ----
+  // ---- A2b: one thread per observation: U = L^-1 J_e^T (rows), w = U^T z; L | z of the tile leave as full lines ----
   if (!NORMS) {
-    for (int l = tid; l < nobs; l += blockDim.x) {
+    for (int i = tid; i < 9 * npts; i += nthr) { const int lp = i / 9; P.Lz[9 * pt0 + i] = Ls[lp * FA_LS + (i - 9 * lp)]; }
+    for (int l = tid; l < nobs; l += nthr) {
       double* R = rec + (size_t)l * FA_REC;
       const double* ls = Ls + (int)oblp[l] * FA_LS;
       double Lp[6], z[3];
@@ -582,14 +689,16 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
   }
   // ---- B: one thread per work item ----
   if (!NORMS) {
-    const int64_t first = P.tile_pitem_ptr[tile];
-    const int64_t count = P.tile_pitem_ptr[tile + 1] - first;
-    FA_FOR_ITEMS(it, first, count) {
+    for (int r = 0; r * nthr < T.npitem; ++r) {
+      const int idx = fa_item_index(r, false);
+      if (idx >= T.npitem) continue;
+      const int64_t it = T.pitem0 + idx;
+      int q = pq0, q1 = pq1;
+      if (r > 0) { q = (int)(P.pitem_begin[it] - pe0); q1 = (int)(P.pitem_end[it] - pe0); }
       double acc[36];
 #pragma unroll
       for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-      const int q1 = (int)(P.pitem_end[it] - pe0);
-      for (int q = (int)(P.pitem_begin[it] - pe0); q < q1; ++q) {
+      for (; q < q1; ++q) {
         const int32_t cur = q < npe ? pent_s[q] : P.pent[pe0 + q];
         const double2* Ri = reinterpret_cast<const double2*>(rec + (size_t)(cur & 0xffff) * FA_REC);
         const double2* Rj = reinterpret_cast<const double2*>(rec + (size_t)((cur >> 16) & 0xffff) * FA_REC);
@@ -618,38 +727,38 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
       for (int k = 0; k < 18; ++k) out[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
     }
   }
-  {
-    const int64_t first = P.tile_citem_ptr[tile];
-    const int64_t count = P.tile_citem_ptr[tile + 1] - first;
-    FA_FOR_ITEMS_REV(it, first, count) {
-      double acc[FA_NVC];
+  for (int r = 0; r * nthr < T.ncitem; ++r) {
+    const int idx = fa_item_index(r, true);
+    if (idx >= T.ncitem) continue;
+    const int64_t it = T.citem0 + idx;
+    int q = cq0, q1 = cq1;
+    if (r > 0) { q = (int)(P.citem_begin[it] - ce0); q1 = (int)(P.citem_end[it] - ce0); }
+    double acc[FA_NVC];
 #pragma unroll
-      for (int k = 0; k < FA_NVC; ++k) acc[k] = 0.0;
-      const int q1 = (int)(P.citem_end[it] - ce0);
-      for (int q = (int)(P.citem_begin[it] - ce0); q < q1; ++q) {
-        const double2* R2 = reinterpret_cast<const double2*>(rec + (size_t)cent_s[q] * FA_REC);
-        double jf[12];
+    for (int k = 0; k < FA_NVC; ++k) acc[k] = 0.0;
+    for (; q < q1; ++q) {
+      const double2* R2 = reinterpret_cast<const double2*>(rec + (size_t)cent_s[q] * FA_REC);
+      double jf[12];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { const double2 v = R2[3 + k]; jf[2 * k] = v.x; jf[2 * k + 1] = v.y; }
-        const double2 rv = R2[9], wv = R2[10];
-        int c = 0;
+      for (int k = 0; k < 6; ++k) { const double2 v = R2[3 + k]; jf[2 * k] = v.x; jf[2 * k + 1] = v.y; }
+      const double2 rv = R2[9], wv = R2[10];
+      int c = 0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a)
+      for (int a = 0; a < 6; ++a)
 #pragma unroll
-          for (int b = a; b < 6; ++b) acc[c++] += jf[a] * jf[b] + jf[6 + a] * jf[6 + b];
+        for (int b = a; b < 6; ++b) acc[c++] += jf[a] * jf[b] + jf[6 + a] * jf[6 + b];
 #pragma unroll
-        for (int a = 0; a < 6; ++a) { acc[21 + a] += jf[a] * rv.x + jf[6 + a] * rv.y; acc[27 + a] += jf[a] * wv.x + jf[6 + a] * wv.y; }
-      }
-      double* out = P.partC + (size_t)it * FA_NVC;
-#pragma unroll
-      for (int k = 0; k < FA_NVC; ++k) out[k] = acc[k];
+      for (int a = 0; a < 6; ++a) { acc[21 + a] += jf[a] * rv.x + jf[6 + a] * rv.y; acc[27 + a] += jf[a] * wv.x + jf[6 + a] * wv.y; }
     }
+    double* out = P.partC + (size_t)it * FA_NVC;
+#pragma unroll
+    for (int k = 0; k < FA_NVC; ++k) out[k] = acc[k];
   }
-  if (!NORMS) {  // cost and gradient-norm partials of the tile (fixed tree)
-    sq = block_sum(sq, red);
-    g2 = block_sum(g2, red);
-    gmx = block_max(gmx, red);
-    if (tid == 0) { P.cost_partial[tile] = sq; P.g2_partial[tile] = g2; P.gmax_partial[tile] = gmx; }
+  if (!NORMS) {  // cost and gradient-norm partials of the tile (fixed tree, one barrier)
+    double v[3] = {sq, g2, gmx};
+    const bool mx[3] = {false, false, true};
+    fa_block_reduce(v, mx, 3, red);
+    if (tid == 0) { P.cost_partial[tile] = v[0]; P.g2_partial[tile] = v[1]; P.gmax_partial[tile] = v[2]; }
   }
 }
 
@@ -659,30 +768,49 @@ __device__ __constant__ int kFaCandFields[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 18, 
 __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass2(FaParams P) {
   extern __shared__ double smem[];
   double* rec = smem;                                   // [cap][FA_REC2]: J_e (6) | r (2) | J_f yf (2)
-  double* Xc = rec + (size_t)P.cap * FA_REC2;           // [pts_cap][3] candidate points
-  double* tabs = Xc + (size_t)P.pts_cap * 3;            // [TAB][tcs] tables at x
+  double* Xs = rec + (size_t)P.cap * FA_REC2;           // [pts_cap][FA_PS2]
+  double* tabs = Xs + (size_t)P.pts_cap * FA_PS2;       // [TAB][tcs] tables at x
   double* tabc = tabs + (size_t)P.tcs * TAB;            // [16][tcs] tables at the candidate (R, t, intrinsics)
-  __shared__ double red[32];
-  const int tile = blockIdx.x, tid = threadIdx.x;
-  const int64_t pt0 = P.tile_pt_ptr[tile], pt1 = P.tile_pt_ptr[tile + 1];
-  const int64_t ob0 = P.e_ptr[pt0], ob1 = P.e_ptr[pt1];
-  const int nobs = (int)(ob1 - ob0), npts = (int)(pt1 - pt0);
-  fa_stage_tables(P, tile, P.tab_f, tabs, TAB, nullptr);
-  fa_stage_tables(P, tile, P.tabc_f, tabc, 16, kFaCandFields);
+  __shared__ double red[128];
+  const int tile = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const FaTile T = fa_load_tile(P.tiles + tile);
+  const int64_t pt0 = T.pt0, ob0 = T.ob0;
+  const int nobs = T.nobs, npts = T.npts;
+  fa_stage_tables_async(P, T, P.tab_f, tabs, TAB, nullptr);
+  for (int i = tid; i < 3 * npts; i += nthr) {
+    const int lp = i / 3, k = i - 3 * lp;
+    __pipeline_memcpy_async(Xs + lp * FA_PS2 + k, P.xe + 3 * pt0 + i, 8);
+    __pipeline_memcpy_async(Xs + lp * FA_PS2 + 3 + k, P.se + 3 * pt0 + i, 8);
+  }
+  __pipeline_commit();
+  fa_stage_tables_async(P, T, P.tabc_f, tabc, 16, kFaCandFields);   // needed by the last loop only
+  __pipeline_commit();
+  int pl0 = 0, pl1 = 0;
+  if (tid < npts) {
+    pl0 = (int)(P.e_ptr[pt0 + tid] - ob0);
+    pl1 = (int)(P.e_ptr[pt0 + tid + 1] - ob0);
+  }
+  int32_t e_n = 0, c_n = 0;
+  int slot_n = 0;
+  double2 uv_n = make_double2(0.0, 0.0);
+  if (tid < nobs) { e_n = P.ob_e[ob0 + tid]; c_n = P.ob_f[ob0 + tid]; slot_n = P.ob_slot[ob0 + tid]; uv_n = P.uv[ob0 + tid]; }
+  __pipeline_wait_prior(1);
   __syncthreads();
-  for (int l = tid; l < nobs; l += blockDim.x) {
-    const int64_t o = ob0 + l;
-    const int64_t e = P.ob_e[o];
-    const int32_t c = P.ob_f[o];
-    double T[TAB];
-    fa_get_table(P, tabs, P.tab_f, P.ob_slot[o], c, T);
-    const double X[3] = {P.xe[3 * e], P.xe[3 * e + 1], P.xe[3 * e + 2]};
-    const double s[3] = {P.se[3 * e], P.se[3 * e + 1], P.se[3 * e + 2]};
-    double r[2], je[6], jf[12];
-    fa_linearize(T, X, s, P.uv[o], r, je, jf);
+  for (int l = tid; l < nobs; l += nthr) {
+    const int lp = (int)(e_n - pt0), slot = slot_n;
+    const int32_t c = c_n;
+    const double2 ob = uv_n;
+    if (l + nthr < nobs) { const int64_t o = ob0 + l + nthr; e_n = P.ob_e[o]; c_n = P.ob_f[o]; slot_n = P.ob_slot[o]; uv_n = P.uv[o]; }
     double y[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) y[k] = __ldg(P.yf + 6 * (int64_t)c + k);
+    double Tt[TAB];
+    fa_get_table(P, tabs, P.tab_f, slot, c, Tt);
+    const double* xs = Xs + lp * FA_PS2;
+    const double X[3] = {xs[0], xs[1], xs[2]};
+    const double s[3] = {xs[3], xs[4], xs[5]};
+    double r[2], je[6], jf[12];
+    fa_linearize(Tt, X, s, ob, r, je, jf);
     double q0 = 0.0, q1 = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) { q0 += jf[k] * y[k]; q1 += jf[6 + k] * y[k]; }
@@ -692,11 +820,17 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass2(FaParams P) {
     R2[3] = make_double2(r[0], r[1]);
     R2[4] = make_double2(q0, q1);
   }
+  // the last loop's first observation: in flight across the point phase
+  int32_t e2 = 0, c2 = 0;
+  int slot2 = 0;
+  double2 uv2 = make_double2(0.0, 0.0);
+  if (tid < nobs) { e2 = P.ob_e[ob0 + tid]; c2 = P.ob_f[ob0 + tid]; slot2 = P.ob_slot[ob0 + tid]; uv2 = P.uv[ob0 + tid]; }
   __syncthreads();
   double mcc = 0.0, x2 = 0.0, d2 = 0.0;
-  for (int lp = tid; lp < npts; lp += blockDim.x) {
+  for (int lp = tid; lp < npts; lp += nthr) {
     const int64_t e = pt0 + lp;
-    const int l0 = (int)(P.e_ptr[e] - ob0), l1 = (int)(P.e_ptr[e + 1] - ob0);
+    int l0 = pl0, l1 = pl1;
+    if (lp != tid) { l0 = (int)(P.e_ptr[e] - ob0); l1 = (int)(P.e_ptr[e + 1] - ob0); }
     const double* in = P.Lz + 9 * e;
     double Lp[6], t[3];
 #pragma unroll
@@ -723,44 +857,109 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass2(FaParams P) {
         mcc += m * (R[6 + rr] + m / 2.0);
       }
     }
+    double* xs = Xs + lp * FA_PS2;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const double xv = P.xe[3 * e + k];
-      const double c = xv + (-(t[k]) * P.se[3 * e + k]);
+      const double xv = xs[k];
+      const double c = xv + (-(t[k]) * xs[3 + k]);
       P.xe_c[3 * e + k] = c;
-      Xc[3 * lp + k] = c;
+      xs[k] = c;
       if (l1 > l0) { x2 += xv * xv; const double d = xv - c; d2 += d * d; }
     }
   }
+  __pipeline_wait_prior(0);
   __syncthreads();
   double sq = 0.0;
-  for (int l = tid; l < nobs; l += blockDim.x) {
-    const int64_t o = ob0 + l;
-    const int lp = (int)(P.ob_e[o] - pt0);
-    const int slot = P.ob_slot[o];
+  for (int l = tid; l < nobs; l += nthr) {
+    const int lp = (int)(e2 - pt0), slot = slot2;
+    const int32_t c = c2;
+    const double2 ob = uv2;
+    if (l + nthr < nobs) { const int64_t o = ob0 + l + nthr; e2 = P.ob_e[o]; c2 = P.ob_f[o]; slot2 = P.ob_slot[o]; uv2 = P.uv[o]; }
     double C[16];
     if (slot < P.tcam) {
 #pragma unroll
       for (int f = 0; f < 16; ++f) C[f] = tabc[f * P.tcs + slot];
     } else {
-      const double* T = P.tabc_f + TAB * (int64_t)P.ob_f[o];
+      const double* Tc = P.tabc_f + TAB * (int64_t)c;
 #pragma unroll
-      for (int f = 0; f < 16; ++f) C[f] = __ldg(T + kFaCandFields[f]);
+      for (int f = 0; f < 16; ++f) C[f] = __ldg(Tc + kFaCandFields[f]);
     }
-    const double X[3] = {Xc[3 * lp], Xc[3 * lp + 1], Xc[3 * lp + 2]};
+    const double* xs = Xs + lp * FA_PS2;
+    const double X[3] = {xs[0], xs[1], xs[2]};
     double q[3];
     mat3_vec(C, X, q);
     const double p0 = q[0] + C[9], p1 = q[1] + C[10], p2 = q[2] + C[11];
-    const double2 ob = P.uv[o];
     const double r0 = C[12] * p0 / p2 + C[14] - ob.x;
     const double r1 = C[13] * p1 / p2 + C[15] - ob.y;
     sq += r0 * r0 + r1 * r1;
   }
-  mcc = block_sum(mcc, red);
-  x2 = block_sum(x2, red);
-  d2 = block_sum(d2, red);
+  double v[4] = {mcc, x2, d2, sq};
+  const bool mx[4] = {false, false, false, false};
+  fa_block_reduce(v, mx, 4, red);
+  if (tid == 0) { P.mcc_partial[tile] = v[0]; P.x2_partial[tile] = v[1]; P.d2_partial[tile] = v[2]; P.cand_partial[tile] = v[3]; }
+}
+
+// Standalone residual + Jacobian of Model A (what ba_cuda_eval and the generic pipeline materialise): the tile
+// prologue of pass 1, then r leaves directly (16 B per thread, contiguous) and the J_e / J_f records leave through
+// shared memory as full lines.  Replaces k_jac_a whenever the tile structure exists: k_jac_a reads a 256-byte table
+// per observation through L1 (32 different lines per warp load) and is bound by that, not by HBM.
+__global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_jac(FaParams P) {
+  extern __shared__ double smem[];
+  double* rec = smem;                                   // [cap][FA_RECJ]
+  double* Xs = rec + (size_t)P.cap * FA_RECJ;           // [pts_cap][FA_PS2]
+  double* tabs = Xs + (size_t)P.pts_cap * FA_PS2;       // [TAB][tcs]
+  __shared__ double red[32];
+  const int tile = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const FaTile T = fa_load_tile(P.tiles + tile);
+  const int64_t pt0 = T.pt0, ob0 = T.ob0;
+  const int nobs = T.nobs, npts = T.npts;
+  fa_stage_tables_async(P, T, P.tab_f, tabs, TAB, nullptr);
+  for (int i = tid; i < 3 * npts; i += nthr) {
+    const int lp = i / 3, k = i - 3 * lp;
+    __pipeline_memcpy_async(Xs + lp * FA_PS2 + k, P.xe + 3 * pt0 + i, 8);
+    __pipeline_memcpy_async(Xs + lp * FA_PS2 + 3 + k, P.se + 3 * pt0 + i, 8);
+  }
+  __pipeline_commit();
+  int32_t e_n = 0;
+  int slot_n = 0;
+  double2 uv_n = make_double2(0.0, 0.0);
+  if (tid < nobs) { e_n = P.ob_e[ob0 + tid]; slot_n = P.ob_slot[ob0 + tid]; uv_n = P.uv[ob0 + tid]; }
+  __pipeline_wait_prior(0);
+  __syncthreads();
+  double sq = 0.0;
+  double2* RES2 = reinterpret_cast<double2*>(P.RES);
+  for (int l = tid; l < nobs; l += nthr) {
+    const int lp = (int)(e_n - pt0), slot = slot_n;
+    const double2 ob = uv_n;
+    if (l + nthr < nobs) { const int64_t o = ob0 + l + nthr; e_n = P.ob_e[o]; slot_n = P.ob_slot[o]; uv_n = P.uv[o]; }
+    double Tt[TAB];
+    if (slot < P.tcam) {
+#pragma unroll
+      for (int f = 0; f < TAB; ++f) Tt[f] = tabs[f * P.tcs + slot];
+    } else {
+      load_tab(P.tab_f, P.ob_f[ob0 + l], Tt);
+    }
+    const double* xs = Xs + lp * FA_PS2;
+    const double X[3] = {xs[0], xs[1], xs[2]};
+    const double s[3] = {xs[3], xs[4], xs[5]};
+    double r[2], je[6], jf[12];
+    fa_linearize(Tt, X, s, ob, r, je, jf);
+    sq += r[0] * r[0] + r[1] * r[1];
+    RES2[ob0 + l] = make_double2(r[0], r[1]);
+    double2* R2 = reinterpret_cast<double2*>(rec + (size_t)l * FA_RECJ);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) R2[k] = make_double2(je[2 * k], je[2 * k + 1]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) R2[3 + k] = make_double2(jf[2 * k], jf[2 * k + 1]);
+  }
+  __syncthreads();
+  const double2* src = reinterpret_cast<const double2*>(rec);
+  double2* je_out = reinterpret_cast<double2*>(P.JE + 6 * ob0);
+  double2* jf_out = reinterpret_cast<double2*>(P.JF + 12 * ob0);
+  for (int g = tid; g < 3 * nobs; g += nthr) { const int l = g / 3; je_out[g] = src[l * (FA_RECJ / 2) + (g - 3 * l)]; }
+  for (int g = tid; g < 6 * nobs; g += nthr) { const int l = g / 6; jf_out[g] = src[l * (FA_RECJ / 2) + 3 + (g - 6 * l)]; }
   sq = block_sum(sq, red);
-  if (tid == 0) { P.mcc_partial[tile] = mcc; P.x2_partial[tile] = x2; P.d2_partial[tile] = d2; P.cand_partial[tile] = sq; }
+  if (tid == 0) P.cost_partial[tile] = sq;
 }
 
 // first level: one warp per chunk of <= ch partial blocks of one target, lane = value, sequential over the blocks
