@@ -34,9 +34,9 @@ namespace ba {
 
 constexpr int FA_TOBS_DEFAULT = 256;         // observation window of a tile (BA_FA_TOBS overrides, for tuning)
 constexpr int FA_KMAX = 64;                  // max observations of one point (fused path)
-constexpr int FA_TPTS = 512;                 // max points of a tile
+constexpr int FA_TPTS = 4096;                // max points of a tile (a forced cut every FA_TPTS points: keep it rare)
 constexpr int FA_TCAM = 48;                  // camera tables staged in shared memory per tile (more: read from L2)
-constexpr int FA_CH_PAIR = 16;               // pairs per pair item
+constexpr int FA_CH_PAIR = 16;               // pairs per pair item (BA_FA_CH_PAIR overrides, for tuning)
 constexpr int FA_CH_RED = 64;                // partial blocks per first-level reduction chunk
 constexpr int FA_NVC = 33;                   // per camera: 21 packed upper F^T F | 6 F^T r | 6 sum of v_i
 constexpr int FA_MAX_THREADS = 512;          // launch bound: 1 x 512, 2 x 256 or 4 x 128 threads per SM at <= 128 registers
@@ -57,6 +57,7 @@ struct __align__(16) FaTile {
   int32_t pad_[3];
 };
 static_assert(sizeof(FaTile) == 96, "FaTile is loaded as six 16-byte words");
+static_assert(TAB == 32, "one lane per table field when the tables are staged");
 
 
 __global__ void k_fa_tile_desc(int n_tiles, const int64_t* __restrict__ tile_pt_ptr, const int64_t* __restrict__ e_ptr,
@@ -101,7 +102,7 @@ struct ItemSet {
 
 struct FusedA {
   bool ready = false;
-  int n_tiles = 0, tobs = FA_TOBS_DEFAULT, kmax = 0, cap = 0, threads = FA_THREADS_DEFAULT, threads2 = FA_THREADS_DEFAULT, ch_cam = 16;
+  int n_tiles = 0, tobs = FA_TOBS_DEFAULT, kmax = 0, cap = 0, threads = FA_THREADS_DEFAULT, threads2 = FA_THREADS_DEFAULT, ch_cam = 16, ch_pair = FA_CH_PAIR;
   DVec<int64_t> tile_pt_ptr;    // n_tiles + 1
   DVec<int64_t> tile_pent_ptr;  // n_tiles + 1: the tile's slice of pairs.ent (entries are tile-major)
   DVec<int64_t> tile_cent_ptr;  // n_tiles + 1: the tile's slice of cams.ent
@@ -219,10 +220,61 @@ __global__ void k_fa_tile_stats(int n_tiles, const int64_t* __restrict__ tile_pt
   atomicMax(stat + 2, (int)min(tile_pent_ptr[t + 1] - tile_pent_ptr[t], (int64_t)INT32_MAX));
 }
 
+inline int env_int(const char* name, int lo, int hi, int fallback) {
+  if (const char* env = std::getenv(name)) { const int v = std::atoi(env); if (v >= lo && v <= hi) return v; }
+  return fallback;
+}
+
+// Bank-aware order of the entries inside the work items.  In phase B of pass 1 the eight lanes of a quarter warp
+// gather 16-byte pieces of eight different observation records; two records whose indices agree modulo 8 sit in the
+// same banks (record stride 22 doubles = 11 x 16 B), and with entries in arbitrary order 60 % of the shared-memory
+// wavefronts of the kernel were such replays (ncu, profiles/).  The order of the entries inside an item is free, so
+// for every eight items that share a quarter warp (consecutive item indices of a tile) the entries are permuted
+// greedily: in step t the lanes pick, in turn, a remaining entry whose record classes are still unused in that step.
+// One warp per tile, lane = group of eight items.  Static, so the sums stay in a fixed order.
+__global__ void k_fa_bank_order(int n_tiles, const int64_t* __restrict__ tile_item_ptr, const int64_t* __restrict__ item_begin,
+                                const int64_t* __restrict__ item_end, int32_t* __restrict__ ent, int is_pair) {
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  const int64_t i0 = tile_item_ptr[tile], i1 = tile_item_ptr[tile + 1];
+  const int full = is_pair ? 2 : 1;
+  for (int64_t g0 = i0 + 8 * lane; g0 < i1; g0 += 8 * 32) {
+    int64_t b[8];
+    int len[8], maxlen = 0;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      const bool on = g0 + l < i1;
+      b[l] = on ? item_begin[g0 + l] : 0;
+      len[l] = on ? (int)(item_end[g0 + l] - b[l]) : 0;
+      maxlen = max(maxlen, len[l]);
+    }
+    for (int t = 0; t < maxlen; ++t) {
+      unsigned used_i = 0, used_j = 0;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        if (t >= len[l]) continue;
+        int32_t* E = ent + b[l];
+        int best = t, best_score = -1;
+        for (int c = t; c < len[l] && best_score < full; ++c) {
+          const int32_t e = E[c];
+          int score = ((used_i >> (e & 7)) & 1) ? 0 : 1;
+          if (is_pair) score += ((used_j >> ((e >> 16) & 7)) & 1) ? 0 : 1;
+          if (score > best_score) { best_score = score; best = c; }
+        }
+        const int32_t e = E[best];
+        if (best != t) { E[best] = E[t]; E[t] = e; }
+        used_i |= 1u << (e & 7);
+        if (is_pair) used_j |= 1u << ((e >> 16) & 7);
+      }
+    }
+  }
+}
+
 // keys (tile * n_targets + target) with their entries -> sorted entries, groups, items of <= ch entries ordered by
 // (tile, descending length), reduction lists
 inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, int64_t n, int n_tiles, int64_t n_targets, int ch,
-                       cudaStream_t st) {
+                       bool is_pair, cudaStream_t st) {
   I.n_ent = n; I.n_targets = (int)n_targets;
   DVec<uint64_t> ks, gkey;
   DVec<int64_t> gcnt;
@@ -270,6 +322,8 @@ inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, in
   k_fa_key_tile<<<grid_for(ni, 256), 256, 0, st>>>(skey_sorted.p, ni, item_tile.p);
   BA_TRY(I.tile_item_ptr.alloc((size_t)n_tiles + 1));
   k_seg_ptr<int32_t><<<grid_for(ni > n_tiles + 1 ? ni : n_tiles + 1, 256), 256, 0, st>>>(item_tile.p, ni, n_tiles, I.tile_item_ptr.p);
+  if (env_int("BA_FA_BANK_ORDER", 0, 1, 1))
+    k_fa_bank_order<<<grid_for(n_tiles, 4), 128, 0, st>>>(n_tiles, I.tile_item_ptr.p, I.item_begin.p, I.item_end.p, I.ent.p, is_pair ? 1 : 0);
   BA_TRY(sort_to_csr(I.item_target.p, iota.p, ni, n_targets, I.tgt_ptr, I.red_items, st));
   BA_TRY(build_chunks(I.red_ch, I.tgt_ptr.p, (int)n_targets, FA_CH_RED, st));
   BA_CUDA_TRY(cudaStreamSynchronize(st));
@@ -279,11 +333,6 @@ inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, in
 
 // Returns BA_ERR_UNSUPPORTED when the problem does not fit the fused path (a point with more than FA_KMAX
 // observations, or nothing to do): the caller then keeps the generic pipeline.
-inline int env_int(const char* name, int lo, int hi, int fallback) {
-  if (const char* env = std::getenv(name)) { const int v = std::atoi(env); if (v >= lo && v <= hi) return v; }
-  return fallback;
-}
-
 inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, int tobs);
 
 // Tile geometry: measured on B200 (profiles/README.md), a problem whose points carry many observation pairs
@@ -309,7 +358,8 @@ inline int build_fused_a(FusedA& F, const Structure& S, cudaStream_t st) {
   for (;; tobs /= 2) {
     F.threads = env_int("BA_FA_THREADS", 32, FA_MAX_THREADS, tobs >= 768 ? 512 : 256) / 32 * 32;
     F.threads2 = env_int("BA_FA_THREADS2", 32, FA_MAX_THREADS, tobs >= 768 ? 256 : 128) / 32 * 32;
-    F.ch_cam = env_int("BA_FA_CH_CAM", 1, 64, 16);
+    F.ch_cam = env_int("BA_FA_CH_CAM", 1, 63, 16);
+    F.ch_pair = env_int("BA_FA_CH_PAIR", 1, 63, dense_pairs ? FA_CH_PAIR : 12);  // measured: cfg4 12, cfg5 16
     const int rc = build_fused_a_tobs(F, S, st, tobs);
     if (rc != BA_ERR_UNSUPPORTED || tobs <= 128 || F.kmax > FA_KMAX) return rc;
   }
@@ -348,7 +398,7 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
     BA_TRY(keys.alloc(np)); BA_TRY(vals.alloc(np));
     k_fa_pair_fill<<<grid_for(ne, 128), 128, 0, st>>>(S.e_ptr.p, S.ob_f0.p, ne, nf, off.p, tile_of_pt.p, F.tile_pt_ptr.p, S.dest_keys.p,
                                                       S.ndest, keys.p, vals.p);
-    BA_TRY(build_items(F.pairs, keys, vals, np, F.n_tiles, S.ndest, FA_CH_PAIR, st));
+    BA_TRY(build_items(F.pairs, keys, vals, np, F.n_tiles, S.ndest, F.ch_pair, true, st));
   }
   // camera items, the tile camera lists and the per-observation camera slot
   {
@@ -356,7 +406,7 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
     DVec<int32_t> vals, group_tile;
     BA_TRY(keys.alloc(nb)); BA_TRY(vals.alloc(nb));
     k_fa_cam_fill<<<grid_for(nb, 256), 256, 0, st>>>(S.ob_e.p, S.ob_f0.p, nb, nf, S.e_ptr.p, tile_of_pt.p, F.tile_pt_ptr.p, keys.p, vals.p);
-    BA_TRY(build_items(F.cams, keys, vals, nb, F.n_tiles, nf, F.ch_cam, st));
+    BA_TRY(build_items(F.cams, keys, vals, nb, F.n_tiles, nf, F.ch_cam, false, st));
     const int ng = F.cams.n_groups;
     BA_TRY(group_tile.alloc(ng)); BA_TRY(F.ob_slot.alloc(nb));
     // group -> tile from the tile_group_ptr CSR (groups are tile-major)
@@ -481,29 +531,42 @@ __device__ __forceinline__ FaTile fa_load_tile(const FaTile* __restrict__ p) {
   return T;
 }
 
-// The tile's camera tables -> shared memory, SoA [field][slot] so that lanes with different cameras hit different
-// banks.  One warp per camera row: the (uniform) camera ids of four rows are fetched first, then lane f copies field f
-// of each row with an 8-byte cp.async, so nothing of this waits in a register; the caller commits and waits on the
+// The tile's camera tables -> shared memory as 32-bit planes [2 * field + half][slot]: a thread reads field f of ITS
+// camera with two 4-byte loads, and the lanes of a warp (different cameras of the tile) then hit different banks for
+// up to 32 slots; as 8-byte words only 16 slots are conflict free and the table reads replayed 1.9x (ncu).
+// One warp per camera row: the (uniform) camera ids of four rows are fetched first, then lane f copies field f of
+// each row with two 4-byte cp.async, so nothing of this waits in a register; the caller commits and waits on the
 // pipeline.  nfields <= 32; field_map = nullptr copies fields 0 .. nfields-1.
 __device__ __forceinline__ void fa_stage_tables_async(const FaParams& P, const FaTile& T, const double* __restrict__ tab, double* tabs,
                                                       int nfields, const int* field_map) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int ncam = min(T.ncam, P.tcam);
   const int src_f = lane < nfields ? (field_map ? field_map[lane] : lane) : 0;
+  uint32_t* planes = reinterpret_cast<uint32_t*>(tabs);
   for (int s0 = warp; s0 < ncam; s0 += 4 * nw) {
     int32_t cam[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) { const int s = s0 + u * nw; cam[u] = s < ncam ? __ldg(P.tile_cams + T.cam0 + s) : -1; }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (cam[u] >= 0 && lane < nfields) __pipeline_memcpy_async(tabs + lane * P.tcs + (s0 + u * nw), tab + (int64_t)TAB * cam[u] + src_f, 8);
+      if (cam[u] >= 0 && lane < nfields) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tab + (int64_t)TAB * cam[u] + src_f);
+        uint32_t* dst = planes + (size_t)(2 * lane) * P.tcs + (s0 + u * nw);
+        __pipeline_memcpy_async(dst, src, 4);
+        __pipeline_memcpy_async(dst + P.tcs, src + 1, 4);
+      }
   }
+}
+__device__ __forceinline__ double fa_table_field(const double* tabs, int tcs, int f, int slot) {
+  const uint32_t* planes = reinterpret_cast<const uint32_t*>(tabs);
+  const uint32_t lo = planes[(size_t)(2 * f) * tcs + slot], hi = planes[(size_t)(2 * f + 1) * tcs + slot];
+  return __hiloint2double((int)hi, (int)lo);
 }
 __device__ __forceinline__ void fa_get_table(const FaParams& P, const double* tabs, const double* __restrict__ tab, int slot, int32_t cam,
                                              double* T) {
   if (slot < P.tcam) {
 #pragma unroll
-    for (int f = 0; f < TAB; ++f) T[f] = tabs[f * P.tcs + slot];
+    for (int f = 0; f < TAB; ++f) T[f] = fa_table_field(tabs, P.tcs, f, slot);
   } else {
     load_tab(tab, cam, T);
   }
@@ -596,7 +659,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
     double Tt[TAB];
     if (slot < P.tcam) {
 #pragma unroll
-      for (int f = 0; f < TAB; ++f) Tt[f] = tabs[f * P.tcs + slot];
+      for (int f = 0; f < TAB; ++f) Tt[f] = fa_table_field(tabs, P.tcs, f, slot);
     } else {
       load_tab(P.tab_f, P.ob_f[ob0 + l], Tt);
     }
@@ -878,7 +941,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass2(FaParams P) {
     double C[16];
     if (slot < P.tcam) {
 #pragma unroll
-      for (int f = 0; f < 16; ++f) C[f] = tabc[f * P.tcs + slot];
+      for (int f = 0; f < 16; ++f) C[f] = fa_table_field(tabc, P.tcs, f, slot);
     } else {
       const double* Tc = P.tabc_f + TAB * (int64_t)c;
 #pragma unroll
@@ -935,7 +998,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_jac(FaParams P) {
     double Tt[TAB];
     if (slot < P.tcam) {
 #pragma unroll
-      for (int f = 0; f < TAB; ++f) Tt[f] = tabs[f * P.tcs + slot];
+      for (int f = 0; f < TAB; ++f) Tt[f] = fa_table_field(tabs, P.tcs, f, slot);
     } else {
       load_tab(P.tab_f, P.ob_f[ob0 + l], Tt);
     }
