@@ -341,7 +341,7 @@ def main():
             jms = float(t.item())
         jac_mobs = job.n_obs / 1e6 / (jms * 1e-3)   # whole job: shards run concurrently
         gbs = job.jac_bytes_per_obs * job.n_obs / world / (jms * 1e-3) / 1e9
-        jacobian = {"kernel": "k_jac_a" if job.model == "A" else "k_jac_b", "ms": jms, "mobs_per_sec": jac_mobs,
+        jacobian = {"kernel": "k_fa_jac" if job.model == "A" else "k_jac_b", "ms": jms, "mobs_per_sec": jac_mobs,
                     "unit_of_obs": "corner observation (2 residuals)" if job.model == "A" else "marker observation (8 residuals)",
                     "algorithmic_bytes_per_obs": job.jac_bytes_per_obs, "achieved_gbs_per_gpu": gbs, "frac_of_hbm_peak": gbs / peak}
 

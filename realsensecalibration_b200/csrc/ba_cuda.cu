@@ -338,7 +338,7 @@ int run_jacobian(ba_cuda_problem* p) {
     ba_cuda_options_init(&o);
     const FaParams P = fa_params(p, o);
     grid = p->FA.n_tiles;
-    BA_LAUNCH(p, KT_JAC, k_fa_jac, grid, p->FA.threads, p->FA.smemj(), P);
+    BA_LAUNCH(p, KT_JAC, k_fa_jac, grid, FA_JAC_THREADS, p->FA.smemj(FA_JAC_THREADS), P);
     BA_CUDA_TRY(cudaGetLastError());
     return fold(p, p->fa_part.p, grid, S_COST);
   }

@@ -47,7 +47,8 @@ constexpr int FA_PENT_MAX = 6144;            // pair entries staged in shared me
 constexpr size_t FA_SMEM_MAX = 231000;      // dynamic shared memory per CTA (232448 opt-in limit minus the static part)
 constexpr int FA_LS = 10;                    // per point in shared memory: L10 L20 L21 | 1/L00 1/L11 1/L22 | z (3) | pad
 constexpr int FA_PS2 = 7;                    // pass 2 / k_fa_jac, per point in shared memory: x_e (3, then the candidate) | scale (3) | pad (odd stride)
-constexpr int FA_RECJ = 18;                  // k_fa_jac record: J_e (6) | J_f (12); 9 x 16 B: odd, conflict free for double2
+constexpr int FA_JAC_THREADS = 128;          // k_fa_jac: four CTAs per SM
+constexpr int FA_RECJ = 18;                  // k_fa_jac: doubles staged per observation (J_e 6 | J_f 12), in a per-warp buffer
 
 // Everything a CTA needs to know about its tile in one 96-byte record (one L2 round trip instead of a chain of
 // dependent pointer loads): built once per problem by k_fa_tile_desc.
@@ -119,7 +120,7 @@ struct FusedA {
     return ((size_t)cap * FA_REC + (size_t)pts_cap * FA_LS + (size_t)tcs * TAB) * 8 + ((size_t)pent_cap + cap) * 4 + (size_t)cap * 2;
   }
   size_t smem2() const { return ((size_t)cap * FA_REC2 + (size_t)pts_cap * FA_PS2 + (size_t)tcs * (TAB + 16)) * 8; }
-  size_t smemj() const { return ((size_t)cap * FA_RECJ + (size_t)pts_cap * FA_PS2 + (size_t)tcs * TAB) * 8; }
+  size_t smemj(int threads) const { return ((size_t)threads * FA_RECJ + (size_t)pts_cap * FA_PS2 + (size_t)tcs * TAB) * 8; }
 };
 
 __global__ void k_fa_tile_flags(const int64_t* __restrict__ e_ptr, int64_t ne, int tobs, int32_t* __restrict__ flag, int* __restrict__ kmax) {
@@ -434,7 +435,7 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
       const size_t excess = (F.smem1() - FA_SMEM_MAX + 7) / 8 * 2;
       F.pent_cap = (size_t)F.pent_cap > excess ? F.pent_cap - (int)excess : 0;
     }
-    if (F.smem1() > FA_SMEM_MAX || F.smem2() > FA_SMEM_MAX || F.smemj() > FA_SMEM_MAX) return BA_ERR_UNSUPPORTED;
+    if (F.smem1() > FA_SMEM_MAX || F.smem2() > FA_SMEM_MAX || F.smemj(FA_JAC_THREADS) > FA_SMEM_MAX) return BA_ERR_UNSUPPORTED;
   }
   BA_TRY(F.tiles.alloc((size_t)F.n_tiles));
   k_fa_tile_desc<<<grid_for(F.n_tiles, 256), 256, 0, st>>>(F.n_tiles, F.tile_pt_ptr.p, S.e_ptr.p, F.cams.tile_group_ptr.p, F.tile_pent_ptr.p,
@@ -963,16 +964,22 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass2(FaParams P) {
 }
 
 // Standalone residual + Jacobian of Model A (what ba_cuda_eval and the generic pipeline materialise): the tile
-// prologue of pass 1, then r leaves directly (16 B per thread, contiguous) and the J_e / J_f records leave through
-// shared memory as full lines.  Replaces k_jac_a whenever the tile structure exists: k_jac_a reads a 256-byte table
-// per observation through L1 (32 different lines per warp load) and is bound by that, not by HBM.
-__global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_jac(FaParams P) {
+// prologue of pass 1 (descriptor, tables and points by cp.async, the first observation in registers), then every warp
+// works on its own: 32 consecutive observations per round, r leaves directly (16 B per thread, contiguous), the J_e and
+// J_f records go through a per-warp staging buffer (__syncwarp only) and leave as full 128-byte lines.  The staging
+// buffers are packed exactly like the global arrays, so the copy-out reads consecutive 16-byte units; the writes are
+// conflict free too (J_e: 3 units per lane, odd stride; J_f: 6 units per lane, the lanes with bit 2 set write their
+// units one step ahead of the others).  ~31 KB of shared memory, 128 registers: four CTAs of 128 threads per SM.
+// Replaces k_jac_a whenever the tile structure exists: k_jac_a reads a 256-byte table per observation through L1
+// (32 different lines per warp load) and is bound by that, not by HBM.
+__global__ void __launch_bounds__(FA_JAC_THREADS, 4) k_fa_jac(FaParams P) {
   extern __shared__ double smem[];
-  double* rec = smem;                                   // [cap][FA_RECJ]
-  double* Xs = rec + (size_t)P.cap * FA_RECJ;           // [pts_cap][FA_PS2]
-  double* tabs = Xs + (size_t)P.pts_cap * FA_PS2;       // [TAB][tcs]
+  const int tile = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  double* wje = smem + (size_t)warp * (32 * FA_RECJ);   // [32][6] of this warp
+  double* wjf = wje + 32 * 6;                           // [32][12]
+  double* Xs = smem + (size_t)(nthr >> 5) * (32 * FA_RECJ);   // [pts_cap][FA_PS2]
+  double* tabs = Xs + (size_t)P.pts_cap * FA_PS2;       // table planes
   __shared__ double red[32];
-  const int tile = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
   const FaTile T = fa_load_tile(P.tiles + tile);
   const int64_t pt0 = T.pt0, ob0 = T.ob0;
   const int nobs = T.nobs, npts = T.npts;
@@ -991,36 +998,50 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_jac(FaParams P) {
   __syncthreads();
   double sq = 0.0;
   double2* RES2 = reinterpret_cast<double2*>(P.RES);
-  for (int l = tid; l < nobs; l += nthr) {
+  const bool ahead = (lane & 4) != 0;
+  for (int base = warp * 32; base < nobs; base += nthr) {   // warp-uniform: 32 consecutive observations per round
+    const int l = base + lane;
+    const bool on = l < nobs;
     const int lp = (int)(e_n - pt0), slot = slot_n;
     const double2 ob = uv_n;
     if (l + nthr < nobs) { const int64_t o = ob0 + l + nthr; e_n = P.ob_e[o]; slot_n = P.ob_slot[o]; uv_n = P.uv[o]; }
-    double Tt[TAB];
-    if (slot < P.tcam) {
+    if (on) {
+      double Tt[TAB];
+      if (slot < P.tcam) {
 #pragma unroll
-      for (int f = 0; f < TAB; ++f) Tt[f] = fa_table_field(tabs, P.tcs, f, slot);
-    } else {
-      load_tab(P.tab_f, P.ob_f[ob0 + l], Tt);
+        for (int f = 0; f < TAB; ++f) Tt[f] = fa_table_field(tabs, P.tcs, f, slot);
+      } else {
+        load_tab(P.tab_f, P.ob_f[ob0 + l], Tt);
+      }
+      const double* xs = Xs + lp * FA_PS2;
+      const double X[3] = {xs[0], xs[1], xs[2]};
+      const double s[3] = {xs[3], xs[4], xs[5]};
+      double r[2], je[6], jf[12];
+      fa_linearize(Tt, X, s, ob, r, je, jf);
+      sq += r[0] * r[0] + r[1] * r[1];
+      RES2[ob0 + l] = make_double2(r[0], r[1]);
+      double2* E2 = reinterpret_cast<double2*>(wje) + 3 * lane;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) E2[k] = make_double2(je[2 * k], je[2 * k + 1]);
+      double2* F2 = reinterpret_cast<double2*>(wjf) + 6 * lane;
+#pragma unroll
+      for (int st = 0; st < 6; ++st) {
+        const int k0 = st, k1 = (st + 1) % 6;
+        F2[ahead ? k1 : k0] = ahead ? make_double2(jf[2 * k1], jf[2 * k1 + 1]) : make_double2(jf[2 * k0], jf[2 * k0 + 1]);
+      }
     }
-    const double* xs = Xs + lp * FA_PS2;
-    const double X[3] = {xs[0], xs[1], xs[2]};
-    const double s[3] = {xs[3], xs[4], xs[5]};
-    double r[2], je[6], jf[12];
-    fa_linearize(Tt, X, s, ob, r, je, jf);
-    sq += r[0] * r[0] + r[1] * r[1];
-    RES2[ob0 + l] = make_double2(r[0], r[1]);
-    double2* R2 = reinterpret_cast<double2*>(rec + (size_t)l * FA_RECJ);
+    __syncwarp();
+    const int nv = min(32, nobs - base);
+    const double2* se2 = reinterpret_cast<const double2*>(wje);
+    const double2* sf2 = reinterpret_cast<const double2*>(wjf);
+    double2* je_out = reinterpret_cast<double2*>(P.JE + 6 * (ob0 + base));
+    double2* jf_out = reinterpret_cast<double2*>(P.JF + 12 * (ob0 + base));
 #pragma unroll
-    for (int k = 0; k < 3; ++k) R2[k] = make_double2(je[2 * k], je[2 * k + 1]);
+    for (int m = 0; m < 3; ++m) { const int g = lane + 32 * m; if (g < 3 * nv) je_out[g] = se2[g]; }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) R2[3 + k] = make_double2(jf[2 * k], jf[2 * k + 1]);
+    for (int m = 0; m < 6; ++m) { const int g = lane + 32 * m; if (g < 6 * nv) jf_out[g] = sf2[g]; }
+    __syncwarp();
   }
-  __syncthreads();
-  const double2* src = reinterpret_cast<const double2*>(rec);
-  double2* je_out = reinterpret_cast<double2*>(P.JE + 6 * ob0);
-  double2* jf_out = reinterpret_cast<double2*>(P.JF + 12 * ob0);
-  for (int g = tid; g < 3 * nobs; g += nthr) { const int l = g / 3; je_out[g] = src[l * (FA_RECJ / 2) + (g - 3 * l)]; }
-  for (int g = tid; g < 6 * nobs; g += nthr) { const int l = g / 6; jf_out[g] = src[l * (FA_RECJ / 2) + 3 + (g - 6 * l)]; }
   sq = block_sum(sq, red);
   if (tid == 0) P.cost_partial[tile] = sq;
 }
