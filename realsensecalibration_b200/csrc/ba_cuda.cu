@@ -533,7 +533,7 @@ FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt) {
   FusedA& F = p->FA;
   const size_t nt = (size_t)F.n_tiles;
   FaParams P;
-  P.tiles = F.tiles.p; P.e_ptr = S.e_ptr.p; P.ob_e = S.ob_e.p; P.ob_f = S.ob_f0.p; P.ob_slot = F.ob_slot.p; P.uv = p->uv.p;
+  P.tiles = F.tiles.p; P.e_ptr = S.e_ptr.p; P.ob_f = S.ob_f0.p; P.ob_meta = F.ob_meta.p; P.uv = p->uv.p;
   P.tile_cams = F.cams.group_target.p; P.cap = F.cap;
   P.pts_cap = F.pts_cap; P.tcam = F.tcam; P.tcs = F.tcs; P.pent_cap = F.pent_cap;
   P.pitem_begin = F.pairs.item_begin.p; P.pitem_end = F.pairs.item_end.p; P.pent = F.pairs.ent.p;

@@ -108,7 +108,7 @@ struct FusedA {
   DVec<int64_t> tile_pent_ptr;  // n_tiles + 1: the tile's slice of pairs.ent (entries are tile-major)
   DVec<int64_t> tile_cent_ptr;  // n_tiles + 1: the tile's slice of cams.ent
   ItemSet pairs, cams;
-  DVec<uint16_t> ob_slot;       // per observation: slot of its camera in the tile's camera list
+  DVec<uint32_t> ob_meta;       // per observation: local point | camera slot << 16 (k_fa_ob_meta)
   DVec<FaTile> tiles;           // n_tiles descriptors
   DVec<double> partP, partC, red1P, red1C, camacc, Lz;
   // shared-memory geometry, from the maxima over the tiles of this problem (so that small tiles co-reside on an SM)
@@ -120,7 +120,7 @@ struct FusedA {
     return ((size_t)cap * FA_REC + (size_t)pts_cap * FA_LS + (size_t)tcs * TAB) * 8 + ((size_t)pent_cap + cap) * 4 + (size_t)cap * 2;
   }
   size_t smem2() const { return ((size_t)cap * FA_REC2 + (size_t)pts_cap * FA_PS2 + (size_t)tcs * (TAB + 16)) * 8; }
-  size_t smemj(int threads) const { return ((size_t)threads * FA_RECJ + (size_t)pts_cap * FA_PS2 + (size_t)tcs * TAB) * 8; }
+  size_t smemj(int threads) const { return ((size_t)threads * FA_RECJ + (size_t)pts_cap * FA_PS2 + (size_t)tcs * TAB) * 8 + (size_t)cap * 20; }
 };
 
 __global__ void k_fa_tile_flags(const int64_t* __restrict__ e_ptr, int64_t ne, int tobs, int32_t* __restrict__ flag, int* __restrict__ kmax) {
@@ -193,16 +193,22 @@ __global__ void k_fa_group_tile(int n_tiles, const int64_t* __restrict__ tile_gr
   if (t >= n_tiles) return;
   for (int64_t g = tile_group_ptr[t]; g < tile_group_ptr[t + 1]; ++g) group_tile[g] = t;
 }
-// slot of every observation's camera inside its tile's camera list (= rank of its (tile, camera) group in the tile)
-__global__ void k_fa_ob_slot(int ng, const int64_t* __restrict__ group_ptr, const int32_t* __restrict__ group_tile,
+// per observation: local point index inside its tile (low 16 bits) | slot of its camera in the tile's camera list
+// (= rank of its (tile, camera) group in the tile; high 16 bits): everything pass 1 / pass 2 / k_fa_jac need to know
+// about an observation besides its image point, in one 4-byte load
+__global__ void k_fa_ob_meta(int ng, const int64_t* __restrict__ group_ptr, const int32_t* __restrict__ group_tile,
                              const int64_t* __restrict__ tile_group_ptr, const int32_t* __restrict__ ent, const int64_t* __restrict__ e_ptr,
-                             const int64_t* __restrict__ tile_pt_ptr, uint16_t* __restrict__ ob_slot) {
+                             const int64_t* __restrict__ tile_pt_ptr, const int32_t* __restrict__ ob_e, uint32_t* __restrict__ ob_meta) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ng) return;
   const int tile = group_tile[g];
-  const int64_t ob0 = e_ptr[tile_pt_ptr[tile]];
-  const uint16_t slot = (uint16_t)min((int64_t)65535, (int64_t)g - tile_group_ptr[tile]);
-  for (int64_t q = group_ptr[g]; q < group_ptr[g + 1]; ++q) ob_slot[ob0 + ent[q]] = slot;
+  const int64_t pt0 = tile_pt_ptr[tile];
+  const int64_t ob0 = e_ptr[pt0];
+  const uint32_t slot = (uint32_t)min((int64_t)65535, (int64_t)g - tile_group_ptr[tile]);
+  for (int64_t q = group_ptr[g]; q < group_ptr[g + 1]; ++q) {
+    const int64_t o = ob0 + ent[q];
+    ob_meta[o] = (uint32_t)(ob_e[o] - pt0) | (slot << 16);
+  }
 }
 
 // per tile: slice of an entry list (entries are sorted tile-major, groups are tile-major) and the maxima the
@@ -409,11 +415,11 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
     k_fa_cam_fill<<<grid_for(nb, 256), 256, 0, st>>>(S.ob_e.p, S.ob_f0.p, nb, nf, S.e_ptr.p, tile_of_pt.p, F.tile_pt_ptr.p, keys.p, vals.p);
     BA_TRY(build_items(F.cams, keys, vals, nb, F.n_tiles, nf, F.ch_cam, false, st));
     const int ng = F.cams.n_groups;
-    BA_TRY(group_tile.alloc(ng)); BA_TRY(F.ob_slot.alloc(nb));
+    BA_TRY(group_tile.alloc(ng)); BA_TRY(F.ob_meta.alloc(nb));
     // group -> tile from the tile_group_ptr CSR (groups are tile-major)
     k_fa_group_tile<<<grid_for(F.n_tiles, 256), 256, 0, st>>>(F.n_tiles, F.cams.tile_group_ptr.p, group_tile.p);
-    k_fa_ob_slot<<<grid_for(ng, 256), 256, 0, st>>>(ng, F.cams.group_ptr.p, group_tile.p, F.cams.tile_group_ptr.p, F.cams.ent.p, S.e_ptr.p,
-                                                    F.tile_pt_ptr.p, F.ob_slot.p);
+    k_fa_ob_meta<<<grid_for(ng, 256), 256, 0, st>>>(ng, F.cams.group_ptr.p, group_tile.p, F.cams.tile_group_ptr.p, F.cams.ent.p, S.e_ptr.p,
+                                                    F.tile_pt_ptr.p, S.ob_e.p, F.ob_meta.p);
   }
   {  // per-tile slices of the entry lists; shared-memory geometry from the fullest tile
     const int nt = F.n_tiles;
@@ -504,7 +510,7 @@ __device__ __forceinline__ void fa_bwd3(const double* Lp, double* x) {  // x <- 
 struct FaParams {
   // structure
   const FaTile* tiles;
-  const int64_t* e_ptr; const int32_t* ob_e; const int32_t* ob_f; const uint16_t* ob_slot; const double2* uv;
+  const int64_t* e_ptr; const int32_t* ob_f; const uint32_t* ob_meta; const double2* uv;
   const int32_t* tile_cams;
   const int64_t* pitem_begin; const int64_t* pitem_end; const int32_t* pent;
   const int64_t* citem_begin; const int64_t* citem_end; const int32_t* cent;
@@ -645,18 +651,17 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
     pl0 = (int)(P.e_ptr[pt0 + tid] - ob0);
     pl1 = (int)(P.e_ptr[pt0 + tid + 1] - ob0);
   }
-  int32_t e_n = 0;
-  int slot_n = 0;
+  uint32_t m_n = 0;
   double2 uv_n = make_double2(0.0, 0.0);
-  if (tid < nobs) { e_n = P.ob_e[ob0 + tid]; slot_n = P.ob_slot[ob0 + tid]; uv_n = P.uv[ob0 + tid]; }
+  if (tid < nobs) { m_n = P.ob_meta[ob0 + tid]; uv_n = P.uv[ob0 + tid]; }
   __pipeline_wait_prior(1);
   __syncthreads();
   // ---- A1: one thread per observation (the next round's inputs are in flight while this one computes) ----
   double sq = 0.0;
   for (int l = tid; l < nobs; l += nthr) {
-    const int lp = (int)(e_n - pt0), slot = slot_n;
+    const int lp = (int)(m_n & 0xffffu), slot = (int)(m_n >> 16);
     const double2 ob = uv_n;
-    if (l + nthr < nobs) { const int64_t o = ob0 + l + nthr; e_n = P.ob_e[o]; slot_n = P.ob_slot[o]; uv_n = P.uv[o]; }
+    if (l + nthr < nobs) { const int64_t o = ob0 + l + nthr; m_n = P.ob_meta[o]; uv_n = P.uv[o]; }
     double Tt[TAB];
     if (slot < P.tcam) {
 #pragma unroll
@@ -854,17 +859,17 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass2(FaParams P) {
     pl0 = (int)(P.e_ptr[pt0 + tid] - ob0);
     pl1 = (int)(P.e_ptr[pt0 + tid + 1] - ob0);
   }
-  int32_t e_n = 0, c_n = 0;
-  int slot_n = 0;
+  uint32_t m_n = 0;
+  int32_t c_n = 0;
   double2 uv_n = make_double2(0.0, 0.0);
-  if (tid < nobs) { e_n = P.ob_e[ob0 + tid]; c_n = P.ob_f[ob0 + tid]; slot_n = P.ob_slot[ob0 + tid]; uv_n = P.uv[ob0 + tid]; }
+  if (tid < nobs) { m_n = P.ob_meta[ob0 + tid]; c_n = P.ob_f[ob0 + tid]; uv_n = P.uv[ob0 + tid]; }
   __pipeline_wait_prior(1);
   __syncthreads();
   for (int l = tid; l < nobs; l += nthr) {
-    const int lp = (int)(e_n - pt0), slot = slot_n;
+    const int lp = (int)(m_n & 0xffffu), slot = (int)(m_n >> 16);
     const int32_t c = c_n;
     const double2 ob = uv_n;
-    if (l + nthr < nobs) { const int64_t o = ob0 + l + nthr; e_n = P.ob_e[o]; c_n = P.ob_f[o]; slot_n = P.ob_slot[o]; uv_n = P.uv[o]; }
+    if (l + nthr < nobs) { const int64_t o = ob0 + l + nthr; m_n = P.ob_meta[o]; c_n = P.ob_f[o]; uv_n = P.uv[o]; }
     double y[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) y[k] = __ldg(P.yf + 6 * (int64_t)c + k);
@@ -885,10 +890,9 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass2(FaParams P) {
     R2[4] = make_double2(q0, q1);
   }
   // the last loop's first observation: in flight across the point phase
-  int32_t e2 = 0, c2 = 0;
-  int slot2 = 0;
+  uint32_t m2 = 0;
   double2 uv2 = make_double2(0.0, 0.0);
-  if (tid < nobs) { e2 = P.ob_e[ob0 + tid]; c2 = P.ob_f[ob0 + tid]; slot2 = P.ob_slot[ob0 + tid]; uv2 = P.uv[ob0 + tid]; }
+  if (tid < nobs) { m2 = P.ob_meta[ob0 + tid]; uv2 = P.uv[ob0 + tid]; }
   __syncthreads();
   double mcc = 0.0, x2 = 0.0, d2 = 0.0;
   for (int lp = tid; lp < npts; lp += nthr) {
@@ -935,16 +939,15 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass2(FaParams P) {
   __syncthreads();
   double sq = 0.0;
   for (int l = tid; l < nobs; l += nthr) {
-    const int lp = (int)(e2 - pt0), slot = slot2;
-    const int32_t c = c2;
+    const int lp = (int)(m2 & 0xffffu), slot = (int)(m2 >> 16);
     const double2 ob = uv2;
-    if (l + nthr < nobs) { const int64_t o = ob0 + l + nthr; e2 = P.ob_e[o]; c2 = P.ob_f[o]; slot2 = P.ob_slot[o]; uv2 = P.uv[o]; }
+    if (l + nthr < nobs) { const int64_t o = ob0 + l + nthr; m2 = P.ob_meta[o]; uv2 = P.uv[o]; }
     double C[16];
     if (slot < P.tcam) {
 #pragma unroll
       for (int f = 0; f < 16; ++f) C[f] = fa_table_field(tabc, P.tcs, f, slot);
     } else {
-      const double* Tc = P.tabc_f + TAB * (int64_t)c;
+      const double* Tc = P.tabc_f + TAB * (int64_t)P.ob_f[ob0 + l];
 #pragma unroll
       for (int f = 0; f < 16; ++f) C[f] = __ldg(Tc + kFaCandFields[f]);
     }
@@ -977,23 +980,26 @@ __global__ void __launch_bounds__(FA_JAC_THREADS, 4) k_fa_jac(FaParams P) {
   const int tile = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   double* wje = smem + (size_t)warp * (32 * FA_RECJ);   // [32][6] of this warp
   double* wjf = wje + 32 * 6;                           // [32][12]
-  double* Xs = smem + (size_t)(nthr >> 5) * (32 * FA_RECJ);   // [pts_cap][FA_PS2]
+  double2* uv_s = reinterpret_cast<double2*>(smem + (size_t)(nthr >> 5) * (32 * FA_RECJ));   // [cap] image points of the tile
+  double* Xs = reinterpret_cast<double*>(uv_s + P.cap);  // [pts_cap][FA_PS2]
   double* tabs = Xs + (size_t)P.pts_cap * FA_PS2;       // table planes
+  uint32_t* meta_s = reinterpret_cast<uint32_t*>(tabs + (size_t)P.tcs * TAB);   // [cap] local point | camera slot << 16
   __shared__ double red[32];
   const FaTile T = fa_load_tile(P.tiles + tile);
   const int64_t pt0 = T.pt0, ob0 = T.ob0;
   const int nobs = T.nobs, npts = T.npts;
+  // everything the tile reads arrives by cp.async: the loop below touches global memory only to store
   fa_stage_tables_async(P, T, P.tab_f, tabs, TAB, nullptr);
   for (int i = tid; i < 3 * npts; i += nthr) {
     const int lp = i / 3, k = i - 3 * lp;
     __pipeline_memcpy_async(Xs + lp * FA_PS2 + k, P.xe + 3 * pt0 + i, 8);
     __pipeline_memcpy_async(Xs + lp * FA_PS2 + 3 + k, P.se + 3 * pt0 + i, 8);
   }
+  for (int i = tid; i < nobs; i += nthr) {
+    __pipeline_memcpy_async(uv_s + i, P.uv + ob0 + i, 16);
+    __pipeline_memcpy_async(meta_s + i, P.ob_meta + ob0 + i, 4);
+  }
   __pipeline_commit();
-  int32_t e_n = 0;
-  int slot_n = 0;
-  double2 uv_n = make_double2(0.0, 0.0);
-  if (tid < nobs) { e_n = P.ob_e[ob0 + tid]; slot_n = P.ob_slot[ob0 + tid]; uv_n = P.uv[ob0 + tid]; }
   __pipeline_wait_prior(0);
   __syncthreads();
   double sq = 0.0;
@@ -1002,10 +1008,10 @@ __global__ void __launch_bounds__(FA_JAC_THREADS, 4) k_fa_jac(FaParams P) {
   for (int base = warp * 32; base < nobs; base += nthr) {   // warp-uniform: 32 consecutive observations per round
     const int l = base + lane;
     const bool on = l < nobs;
-    const int lp = (int)(e_n - pt0), slot = slot_n;
-    const double2 ob = uv_n;
-    if (l + nthr < nobs) { const int64_t o = ob0 + l + nthr; e_n = P.ob_e[o]; slot_n = P.ob_slot[o]; uv_n = P.uv[o]; }
     if (on) {
+      const uint32_t m = meta_s[l];
+      const int lp = (int)(m & 0xffffu), slot = (int)(m >> 16);
+      const double2 ob = uv_s[l];
       double Tt[TAB];
       if (slot < P.tcam) {
 #pragma unroll
