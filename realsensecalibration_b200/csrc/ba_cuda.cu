@@ -90,6 +90,8 @@ struct LmState {  // TrustRegionMinimizer's loop variables, kept between ba_cuda
 struct ba_cuda_problem {
   int device = 0;
   cudaStream_t st = nullptr, own_st = nullptr;
+  cudaStream_t copy_st = nullptr;             // H2D of the observations runs here, beside the structure build
+  cudaEvent_t copy_go = nullptr, copy_done = nullptr;
   int model = -1;  // 0 = A, 1 = B
   int32_t n_cam = 0, n_time = 0, n_marker = 0;
   int64_t n_pt = 0, n_params = 0;
@@ -986,12 +988,22 @@ int alloc_workspace(ba_cuda_problem* p, int RD, int DE) {
 
 // the materialised residual / Jacobian / Schur buffers of the generic pipeline (Model B always; Model A only when the
 // fused path is not used, and for the ba_cuda_eval test hook)
-int ensure_generic_workspace(ba_cuda_problem* p) {
-  if (p->generic_ws) return BA_OK;
+// the materialised residual / Jacobian arrays alone (what ba_cuda_eval fills)
+int ensure_jacobian_buffers(ba_cuda_problem* p) {
   const Structure& S = p->S;
   const int RD = p->model == 0 ? 2 : 8, DE = p->model == 0 ? 3 : 6;
+  if (p->RES.n == (size_t)(S.nb * RD) && p->JE.n == (size_t)(S.nb * RD * DE) && p->JF0.n == (size_t)(S.nb * RD * 6)) return BA_OK;
   BA_TRY(p->RES.alloc(S.nb * RD)); BA_TRY(p->JE.alloc(S.nb * RD * DE)); BA_TRY(p->JF0.alloc(S.nb * RD * 6));
   BA_TRY(p->JF1.alloc(p->model == 1 ? S.nb * RD * 6 : 0));
+  return BA_OK;
+}
+
+int ensure_generic_workspace(ba_cuda_problem* p) {
+  if (p->generic_ws) return BA_OK;
+  BA_TRY(ensure_pair_lists(p->S, p->st));   // Model A builds only the destination set up front (ba_structure.cuh)
+  const Structure& S = p->S;
+  const int DE = p->model == 0 ? 3 : 6;
+  BA_TRY(ensure_jacobian_buffers(p));
   BA_TRY(p->ME.alloc(S.ne * (DE * (DE + 1) / 2 + DE))); BA_TRY(p->HG.alloc(S.nf * NV_F + 2 + kMaxWorld));
   BA_TRY(p->Wt.alloc(p->model == 1 ? S.ninc * 36 : 0));
   BA_TRY(p->Lb.alloc(S.ne * DE * DE)); BA_TRY(p->zb.alloc(S.ne * DE));
@@ -1145,6 +1157,9 @@ int ba_cuda_create(ba_cuda_problem** out, int device_id) {
   p->st = p->own_st;
   for (int f = 0; f < F_COUNT; ++f) { BA_CUDA_TRY(cudaEventCreate(&p->ev[f][0])); BA_CUDA_TRY(cudaEventCreate(&p->ev[f][1])); }
   BA_CUDA_TRY(cudaEventCreate(&p->k0)); BA_CUDA_TRY(cudaEventCreate(&p->k1));
+  BA_CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_st, cudaStreamNonBlocking));
+  BA_CUDA_TRY(cudaEventCreateWithFlags(&p->copy_go, cudaEventDisableTiming));
+  BA_CUDA_TRY(cudaEventCreateWithFlags(&p->copy_done, cudaEventDisableTiming));
   BA_CUDA_TRY(cudaMallocHost((void**)&p->h_scal, sizeof(double) * S_COUNT));
   BA_CUDA_TRY(cudaMallocHost((void**)&p->h_status, sizeof(int)));
   *out = p;
@@ -1162,6 +1177,9 @@ void ba_cuda_destroy(ba_cuda_problem* p) {
   for (int f = 0; f < F_COUNT; ++f) { if (p->ev[f][0]) cudaEventDestroy(p->ev[f][0]); if (p->ev[f][1]) cudaEventDestroy(p->ev[f][1]); }
   if (p->k0) cudaEventDestroy(p->k0);
   if (p->k1) cudaEventDestroy(p->k1);
+  if (p->copy_st) { cudaStreamSynchronize(p->copy_st); cudaStreamDestroy(p->copy_st); }
+  if (p->copy_go) cudaEventDestroy(p->copy_go);
+  if (p->copy_done) cudaEventDestroy(p->copy_done);
   if (p->h_scal) cudaFreeHost(p->h_scal);
   if (p->h_status) cudaFreeHost(p->h_status);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
@@ -1224,8 +1242,17 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
   T.lap("reset");
   p->n_cam = n_cam; p->n_pt = n_pt; p->n_time = 0; p->n_marker = 0;
   p->n_params = 6 * (int64_t)n_cam + 3 * n_pt;
+  // The image points (16 B per observation, two thirds of the upload) travel on a second stream while the index
+  // structure is built from the indices: the copy is queued behind the index uploads (so those reach the device
+  // first) and joined again just before the gather into sorted order.
+  DVec<double> obs_tmp;
+  BA_TRY(obs_tmp.alloc(2 * (size_t)n_obs));
   {
     const int rc = build_structure(p->S, n_obs, n_pt, n_cam, pt_idx, cam_idx, nullptr, p->st, [&](const int32_t* d_pt, const int32_t* d_cam) {
+      BA_CUDA_TRY(cudaEventRecord(p->copy_go, p->st));
+      BA_CUDA_TRY(cudaStreamWaitEvent(p->copy_st, p->copy_go, 0));
+      if (n_obs > 0) BA_CUDA_TRY(cudaMemcpyAsync(obs_tmp.p, obs_xy, sizeof(double) * 2 * n_obs, cudaMemcpyHostToDevice, p->copy_st));
+      BA_CUDA_TRY(cudaEventRecord(p->copy_done, p->copy_st));
       // the uploaded index arrays are checked on the device before anything is built from them
       DVec<unsigned long long> bad;
       BA_TRY(bad.alloc(1));
@@ -1238,16 +1265,15 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
         return fail(BA_ERR_INVALID_ARGUMENT, "observation %lld references camera %d / point %d out of range", (long long)h, cam_idx[h], pt_idx[h]);
       return (int)BA_OK;
     });
-    if (rc != BA_OK) { reset_problem(p); return rc; }
+    if (rc != BA_OK) { cudaStreamSynchronize(p->copy_st); reset_problem(p); return rc; }
   }
   T.lap("upload + validate + build_structure");
   p->model = 0;
   // observations in sorted order, intrinsics per f-block
   {
-    DVec<double> tmp;
-    BA_TRY(tmp.upload(obs_xy, 2 * n_obs, p->st));
+    BA_CUDA_TRY(cudaStreamWaitEvent(p->st, p->copy_done, 0));
     BA_TRY(p->uv.alloc(n_obs));
-    k_gather_uv<<<grid_for(2 * n_obs, 256), 256, 0, p->st>>>(tmp.p, p->S.perm.p, n_obs, 2, reinterpret_cast<double*>(p->uv.p));
+    k_gather_uv<<<grid_for(2 * n_obs, 256), 256, 0, p->st>>>(obs_tmp.p, p->S.perm.p, n_obs, 2, reinterpret_cast<double*>(p->uv.p));
     std::vector<double> K(4 * (size_t)n_cam);
     for (int32_t c = 0; c < n_cam; ++c)
       for (int q = 0; q < 4; ++q) K[4 * c + q] = intr[(size_t)intr_stride * c + q];
@@ -1495,7 +1521,7 @@ int ba_cuda_eval(ba_cuda_problem* p, double* cost, double* residuals, double* ja
   BA_TRY(use_device(p));
   const Structure& S = p->S;
   const int RD = p->model == 0 ? 2 : 8, DE = p->model == 0 ? 3 : 6;
-  BA_TRY(ensure_generic_workspace(p));
+  BA_TRY(ensure_jacobian_buffers(p));
   BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.ne * DE, 256), 256, 0, p->se.p, S.ne * DE, 1.0);
   BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.nf * 6, 256), 256, 0, p->sf.p, S.nf * 6, 1.0);
   BA_TRY(build_tables(p, false));  // warm the tables outside the timed kernel

@@ -27,6 +27,9 @@
 #pragma once
 #include <cuda_pipeline.h>
 
+#include <chrono>
+#include <cstdio>
+
 #include "ba_kernels.cuh"
 #include "ba_structure.cuh"
 
@@ -135,7 +138,9 @@ __global__ void k_fa_tile_flags(const int64_t* __restrict__ e_ptr, int64_t ne, i
 // ordered observation pairs of a point, keyed by (tile, destination block)
 __global__ void k_fa_pair_fill(const int64_t* __restrict__ e_ptr, const int32_t* __restrict__ ob_f, int64_t ne, int64_t nf,
                                const int64_t* __restrict__ off, const int32_t* __restrict__ tile_of_pt, const int64_t* __restrict__ tile_pt_ptr,
-                               const uint64_t* __restrict__ dest_keys, int ndest, uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+                               const uint64_t* __restrict__ dest_keys, int ndest, const uint64_t* __restrict__ dh_keys,
+                               const int32_t* __restrict__ dh_val, uint64_t dh_mask, int dh_shift, uint64_t* __restrict__ keys,
+                               int32_t* __restrict__ vals) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= ne) return;
   int64_t o = off[e];
@@ -144,7 +149,8 @@ __global__ void k_fa_pair_fill(const int64_t* __restrict__ e_ptr, const int32_t*
   for (int64_t i = e_ptr[e]; i < e_ptr[e + 1]; ++i)
     for (int64_t j = e_ptr[e]; j < e_ptr[e + 1]; ++j)
       if (ob_f[i] <= ob_f[j]) {
-        const int64_t d = lower_bound_u64(dest_keys, ndest, (uint64_t)ob_f[i] * nf + ob_f[j]);
+        const uint64_t fk = (uint64_t)ob_f[i] * nf + ob_f[j];
+        const int64_t d = dh_keys ? (int64_t)dh_find(dh_keys, dh_val, dh_mask, dh_shift, fk) : lower_bound_u64(dest_keys, ndest, fk);
         keys[o] = (uint64_t)tile * (uint64_t)ndest + (uint64_t)d;
         vals[o] = (int32_t)(i - ob0) | ((int32_t)(j - ob0) << 16);
         ++o;
@@ -227,6 +233,23 @@ __global__ void k_fa_tile_stats(int n_tiles, const int64_t* __restrict__ tile_pt
   atomicMax(stat + 2, (int)min(tile_pent_ptr[t + 1] - tile_pent_ptr[t], (int64_t)INT32_MAX));
 }
 
+struct FaLap {  // BA_CUDA_TIMING=2: wall clock of the build phases on stderr (synchronises the stream at every lap)
+  cudaStream_t st;
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  explicit FaLap(cudaStream_t s) : st(s), t(std::chrono::steady_clock::now()) {
+    const char* e = std::getenv("BA_CUDA_TIMING");
+    on = e && std::atoi(e) >= 2;
+  }
+  void lap(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto n = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[ba_cuda timing]   fused: %-24s %9.3f ms\n", what, 1e3 * std::chrono::duration<double>(n - t).count());
+    t = n;
+  }
+};
+
 inline int env_int(const char* name, int lo, int hi, int fallback) {
   if (const char* env = std::getenv(name)) { const int v = std::atoi(env); if (v >= lo && v <= hi) return v; }
   return fallback;
@@ -283,6 +306,7 @@ __global__ void k_fa_bank_order(int n_tiles, const int64_t* __restrict__ tile_it
 inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, int64_t n, int n_tiles, int64_t n_targets, int ch,
                        bool is_pair, cudaStream_t st) {
   I.n_ent = n; I.n_targets = (int)n_targets;
+  FaLap L(st);
   DVec<uint64_t> ks, gkey;
   DVec<int64_t> gcnt;
   DVec<int32_t> nruns, group_tile;
@@ -292,6 +316,7 @@ inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, in
       return cub::DeviceRadixSort::SortPairs(t, b, keys.p, ks.p, vals.p, I.ent.p, (int)n, 0, bits_for((uint64_t)n_tiles * (uint64_t)n_targets), st);
     }));
   keys.release(); vals.release();
+  L.lap("items: sort entries");
   BA_TRY(gkey.alloc(n)); BA_TRY(gcnt.alloc(n + 1)); BA_TRY(nruns.alloc(1));
   int32_t ng = 0;
   if (n > 0) {
@@ -307,8 +332,10 @@ inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, in
   k_fa_group_meta<<<grid_for(ng, 256), 256, 0, st>>>(ng, gkey.p, (uint64_t)n_targets, I.group_target.p, group_tile.p);
   BA_TRY(I.tile_group_ptr.alloc((size_t)n_tiles + 1));
   k_seg_ptr<int32_t><<<grid_for(ng > n_tiles + 1 ? ng : n_tiles + 1, 256), 256, 0, st>>>(group_tile.p, ng, n_tiles, I.tile_group_ptr.p);
+  L.lap("items: groups");
   Chunks C;
   BA_TRY(build_chunks(C, I.group_ptr.p, ng, ch, st));
+  L.lap("items: chunks");
   const int ni = C.n;
   I.n_items = ni;
   DVec<int64_t> end0;
@@ -329,10 +356,13 @@ inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, in
   k_fa_key_tile<<<grid_for(ni, 256), 256, 0, st>>>(skey_sorted.p, ni, item_tile.p);
   BA_TRY(I.tile_item_ptr.alloc((size_t)n_tiles + 1));
   k_seg_ptr<int32_t><<<grid_for(ni > n_tiles + 1 ? ni : n_tiles + 1, 256), 256, 0, st>>>(item_tile.p, ni, n_tiles, I.tile_item_ptr.p);
+  L.lap("items: sort items");
   if (env_int("BA_FA_BANK_ORDER", 0, 1, 1))
     k_fa_bank_order<<<grid_for(n_tiles, 4), 128, 0, st>>>(n_tiles, I.tile_item_ptr.p, I.item_begin.p, I.item_end.p, I.ent.p, is_pair ? 1 : 0);
+  L.lap("items: bank order");
   BA_TRY(sort_to_csr(I.item_target.p, iota.p, ni, n_targets, I.tgt_ptr, I.red_items, st));
   BA_TRY(build_chunks(I.red_ch, I.tgt_ptr.p, (int)n_targets, FA_CH_RED, st));
+  L.lap("items: reduction lists");
   BA_CUDA_TRY(cudaStreamSynchronize(st));
   BA_CUDA_TRY(cudaGetLastError());
   return BA_OK;
@@ -376,6 +406,7 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
   F.ready = false;
   const int64_t ne = S.ne, nb = S.nb, nf = S.nf;
   F.tobs = tobs;
+  FaLap L(st);
   DVec<int32_t> flag, tile_of_pt;
   DVec<int> kmax;
   BA_TRY(flag.alloc(ne)); BA_TRY(tile_of_pt.alloc(ne)); BA_TRY(kmax.alloc_zero(1, st));
@@ -390,6 +421,7 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
   F.n_tiles = last_tile + 1;
   BA_TRY(F.tile_pt_ptr.alloc((size_t)F.n_tiles + 1));
   k_seg_ptr<int32_t><<<grid_for(ne > F.n_tiles + 1 ? ne : F.n_tiles + 1, 256), 256, 0, st>>>(tile_of_pt.p, ne, F.n_tiles, F.tile_pt_ptr.p);
+  L.lap("tiles");
   // pair items
   {
     DVec<int64_t> cnt, off;
@@ -404,7 +436,9 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
     DVec<int32_t> vals;
     BA_TRY(keys.alloc(np)); BA_TRY(vals.alloc(np));
     k_fa_pair_fill<<<grid_for(ne, 128), 128, 0, st>>>(S.e_ptr.p, S.ob_f0.p, ne, nf, off.p, tile_of_pt.p, F.tile_pt_ptr.p, S.dest_keys.p,
-                                                      S.ndest, keys.p, vals.p);
+                                                      S.ndest, S.dh_keys.n ? S.dh_keys.p : nullptr, S.dh_val.p, S.dh_mask, S.dh_shift, keys.p,
+                                                      vals.p);
+    L.lap("pair fill");
     BA_TRY(build_items(F.pairs, keys, vals, np, F.n_tiles, S.ndest, F.ch_pair, true, st));
   }
   // camera items, the tile camera lists and the per-observation camera slot
@@ -443,6 +477,7 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
     }
     if (F.smem1() > FA_SMEM_MAX || F.smem2() > FA_SMEM_MAX || F.smemj(FA_JAC_THREADS) > FA_SMEM_MAX) return BA_ERR_UNSUPPORTED;
   }
+  L.lap("camera items, geometry");
   BA_TRY(F.tiles.alloc((size_t)F.n_tiles));
   k_fa_tile_desc<<<grid_for(F.n_tiles, 256), 256, 0, st>>>(F.n_tiles, F.tile_pt_ptr.p, S.e_ptr.p, F.cams.tile_group_ptr.p, F.tile_pent_ptr.p,
                                                           F.tile_cent_ptr.p, F.pairs.tile_item_ptr.p, F.cams.tile_item_ptr.p, F.tiles.p);

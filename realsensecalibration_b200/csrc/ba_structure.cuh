@@ -42,6 +42,12 @@ struct Structure {
   DVec<int32_t> finc, fobs;  // fobs entries are (obs << 1 | slot)
   DVec<int32_t> dest_fa, dest_fb, diag_dest;
   DVec<uint64_t> dest_keys;  // fa * nf + fb, ascending (the RCS pattern of this rank's shard)
+  // open-addressing map key -> destination index (nslots == 1: built instead of sorting every incidence pair)
+  DVec<uint64_t> dh_keys;
+  DVec<int32_t> dh_val;
+  uint64_t dh_mask = 0;
+  int dh_shift = 0;
+  bool pair_lists = false;   // dpair_ptr / pairs / ch_pairs exist (generic pipeline only; built on demand for Model A)
   DVec<int64_t> dpair_ptr;
   DVec<int2> pairs;
   DVec<int64_t> dobs_ptr;  // nslots == 2 only: dest -> obs having (f0,f1) == (fa,fb)
@@ -147,6 +153,62 @@ __global__ void k_dest_finish(const uint64_t* ukeys, int ndest, int64_t nf, int3
   fa[d] = a; fb[d] = b;
   if (a == b) diag_dest[a] = d;
 }
+// ---- destination blocks as a hash set ---------------------------------------------------
+// Model A at BAL scale has ~5 incidence pairs per observation (144 M on the 30 M-observation problem) but only ~16
+// destination blocks per camera: the set of distinct (fa, fb) keys is collected in an open-addressing table (almost
+// every insertion is a read that finds its key), sorted once, and the table then maps key -> destination index for
+// the tile builder of the fused path.  The full per-destination pair lists are only needed by the generic pipeline.
+constexpr uint64_t DH_EMPTY = ~0ull;
+__device__ __forceinline__ uint64_t dh_slot(uint64_t key, int shift) { return (key * 0x9E3779B97F4A7C15ull) >> shift; }
+__device__ __forceinline__ bool dh_insert(uint64_t* table, uint64_t mask, int shift, uint64_t key, unsigned long long* count) {
+  uint64_t h = dh_slot(key, shift);
+  for (uint64_t probe = 0; probe <= mask; ++probe, h = (h + 1) & mask) {
+    const uint64_t cur = __ldcg(table + h);
+    if (cur == key) return true;
+    if (cur == DH_EMPTY) {
+      const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long*>(table + h), (unsigned long long)DH_EMPTY, (unsigned long long)key);
+      if (old == DH_EMPTY) { atomicAdd(count, 1ull); return true; }
+      if (old == key) return true;
+    }
+  }
+  return false;
+}
+__device__ __forceinline__ int32_t dh_find(const uint64_t* __restrict__ table, const int32_t* __restrict__ val, uint64_t mask, int shift,
+                                           uint64_t key) {
+  uint64_t h = dh_slot(key, shift);
+  for (uint64_t probe = 0; probe <= mask; ++probe, h = (h + 1) & mask) {
+    const uint64_t cur = table[h];
+    if (cur == key) return val[h];
+    if (cur == DH_EMPTY) return -1;
+  }
+  return -1;
+}
+__global__ void k_dh_insert_pairs(const int64_t* __restrict__ einc_ptr, const int32_t* __restrict__ inc_f, int64_t ne, int64_t nf,
+                                  uint64_t* table, uint64_t mask, int shift, unsigned long long* count, int* overflow) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int64_t b = einc_ptr[e], n = einc_ptr[e + 1];
+  for (int64_t i = b; i < n; ++i) {
+    const int32_t fi = inc_f[i];
+    for (int64_t j = b; j < n; ++j) {
+      const int32_t fj = inc_f[j];
+      if (fi <= fj && !dh_insert(table, mask, shift, (uint64_t)fi * nf + fj, count)) *overflow = 1;
+    }
+  }
+}
+__global__ void k_dh_insert_diag(int64_t nf, uint64_t* table, uint64_t mask, int shift, unsigned long long* count, int* overflow) {
+  const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f < nf && !dh_insert(table, mask, shift, (uint64_t)f * nf + f, count)) *overflow = 1;   // the (f,f) destination always exists
+}
+__global__ void k_dh_map(const uint64_t* __restrict__ dest_keys, int ndest, const uint64_t* __restrict__ table, uint64_t mask, int shift,
+                         int32_t* __restrict__ val) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= ndest) return;
+  uint64_t h = dh_slot(dest_keys[d], shift);
+  while (table[h] != dest_keys[d]) h = (h + 1) & mask;
+  val[h] = d;
+}
+
 __global__ void k_unpack_pairs(const uint64_t* vals, int64_t n, int2* pairs) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -211,6 +273,127 @@ inline int sort_to_csr(const int32_t* keys_in, const int32_t* vals_in, int64_t n
     }));
   k_seg_ptr<int32_t><<<grid_for(n > nseg + 1 ? n : nseg + 1, 256), 256, 0, st>>>(keys_sorted.p, n, nseg, ptr.p);
   BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
+// destination blocks (fa <= fb) with the list of incidence pairs contributing to each: every ordered pair is
+// materialised and sorted by destination key.  Model B always; Model A only for the generic pipeline (on demand).
+inline int build_pair_lists(Structure& S, cudaStream_t st) {
+  const int64_t ne = S.ne, nf = S.nf;
+  const int B = 256;
+  DVec<uint64_t> dest_keys;
+  {
+    DVec<int64_t> cnt, off;
+    BA_TRY(cnt.alloc(ne + 1)); BA_TRY(off.alloc(ne + 1));
+    k_pair_count<<<grid_for(ne + 1, 128), 128, 0, st>>>(S.einc_ptr, S.inc_f, ne, cnt.p);
+    BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt.p, off.p, (int)(ne + 1), st); }));
+    int64_t np = 0;
+    BA_CUDA_TRY(cudaMemcpyAsync(&np, off.p + ne, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+    S.npairs = np + nf;
+    if (S.npairs >= (int64_t)INT32_MAX) return fail(BA_ERR_UNSUPPORTED, "too many incidence pairs (%lld) for one GPU", (long long)S.npairs);
+    DVec<uint64_t> pk, pv, pks, pvs;
+    BA_TRY(pk.alloc(S.npairs)); BA_TRY(pv.alloc(S.npairs)); BA_TRY(pks.alloc(S.npairs)); BA_TRY(pvs.alloc(S.npairs));
+    if (ne > 0) k_pair_fill<<<grid_for(ne, 128), 128, 0, st>>>(S.einc_ptr, S.inc_f, ne, nf, off.p, pk.p, pv.p);
+    k_pair_diag_sentinels<<<grid_for(nf, B), B, 0, st>>>(nf, np, pk.p, pv.p);
+    BA_TRY(cub_call([&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, pk.p, pks.p, pv.p, pvs.p, (int)S.npairs, 0, bits_for((uint64_t)nf * nf), st);
+    }));
+    pk.release(); pv.release();
+    DVec<int64_t> run_cnt;
+    DVec<int32_t> nruns;
+    BA_TRY(dest_keys.alloc(S.npairs)); BA_TRY(run_cnt.alloc(S.npairs + 1)); BA_TRY(nruns.alloc(1));
+    BA_TRY(cub_call([&](void* t, size_t& b) {
+      return cub::DeviceRunLengthEncode::Encode(t, b, pks.p, dest_keys.p, run_cnt.p, nruns.p, (int)S.npairs, st);
+    }));
+    int32_t nd = 0;
+    BA_CUDA_TRY(cudaMemcpyAsync(&nd, nruns.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+    const bool have_dest = S.dest_keys.n != 0;   // the hashed set exists already: same keys, same (ascending) order
+    if (have_dest && nd != S.ndest) return fail(BA_ERR_CUDA, "destination sets disagree (%d hashed, %d sorted)", S.ndest, nd);
+    S.ndest = nd;
+    BA_TRY(S.dpair_ptr.alloc(nd + 1));
+    BA_CUDA_TRY(cudaMemsetAsync(run_cnt.p + nd, 0, sizeof(int64_t), st));
+    BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, run_cnt.p, S.dpair_ptr.p, nd + 1, st); }));
+    if (!have_dest) {
+      BA_TRY(S.dest_fa.alloc(nd)); BA_TRY(S.dest_fb.alloc(nd)); BA_TRY(S.diag_dest.alloc(nf));
+      k_dest_finish<<<grid_for(nd, B), B, 0, st>>>(dest_keys.p, nd, nf, S.dest_fa.p, S.dest_fb.p, S.diag_dest.p);
+      BA_TRY(S.dest_keys.alloc(nd));   // exactly ndest keys
+      BA_CUDA_TRY(cudaMemcpyAsync(S.dest_keys.p, dest_keys.p, sizeof(uint64_t) * nd, cudaMemcpyDeviceToDevice, st));
+    }
+    BA_TRY(S.pairs.alloc(S.npairs));
+    k_unpack_pairs<<<grid_for(S.npairs, B), B, 0, st>>>(pvs.p, S.npairs, S.pairs.p);
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  S.pair_lists = true;
+  return BA_OK;
+}
+
+// destination blocks only (see "destination blocks as a hash set" above); nslots == 1
+inline int build_dest_hashed(Structure& S, cudaStream_t st) {
+  const int64_t ne = S.ne, nf = S.nf;
+  const int B = 256;
+  int64_t np = 0;
+  {
+    DVec<int64_t> cnt, off;
+    BA_TRY(cnt.alloc(ne + 1)); BA_TRY(off.alloc(ne + 1));
+    k_pair_count<<<grid_for(ne + 1, 128), 128, 0, st>>>(S.einc_ptr, S.inc_f, ne, cnt.p);
+    BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt.p, off.p, (int)(ne + 1), st); }));
+    BA_CUDA_TRY(cudaMemcpyAsync(&np, off.p + ne, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  S.npairs = np + nf;
+  const int64_t bound = std::min<int64_t>(np + nf, nf < ((int64_t)1 << 20) ? nf * (nf + 1) / 2 : INT64_MAX);   // distinct keys at most
+  int64_t cap = 1024;
+  while (cap < 2 * std::min<int64_t>(bound, 48 * nf)) cap <<= 1;
+  DVec<unsigned long long> count;
+  DVec<int> overflow;
+  BA_TRY(count.alloc(1)); BA_TRY(overflow.alloc(1));
+  unsigned long long h_count = 0;
+  for (;;) {
+    int bits = 0;
+    while (((int64_t)1 << bits) < cap) ++bits;
+    S.dh_mask = (uint64_t)cap - 1; S.dh_shift = 64 - bits;
+    BA_TRY(S.dh_keys.alloc((size_t)cap));
+    BA_CUDA_TRY(cudaMemsetAsync(S.dh_keys.p, 0xff, sizeof(uint64_t) * cap, st));
+    BA_CUDA_TRY(cudaMemsetAsync(count.p, 0, sizeof(unsigned long long), st));
+    BA_CUDA_TRY(cudaMemsetAsync(overflow.p, 0, sizeof(int), st));
+    if (ne > 0)
+      k_dh_insert_pairs<<<grid_for(ne, 128), 128, 0, st>>>(S.einc_ptr, S.inc_f, ne, nf, S.dh_keys.p, S.dh_mask, S.dh_shift, count.p, overflow.p);
+    k_dh_insert_diag<<<grid_for(nf, B), B, 0, st>>>(nf, S.dh_keys.p, S.dh_mask, S.dh_shift, count.p, overflow.p);
+    int h_over = 0;
+    BA_CUDA_TRY(cudaMemcpyAsync(&h_count, count.p, sizeof(h_count), cudaMemcpyDeviceToHost, st));
+    BA_CUDA_TRY(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+    if (!h_over && (int64_t)h_count * 10 <= cap * 7) break;     // load factor <= 0.7
+    if (cap >= 4 * bound + 1024) return fail(BA_ERR_CUDA, "destination hash set overflowed at capacity %lld", (long long)cap);
+    cap <<= 3;
+  }
+  if ((int64_t)h_count >= (int64_t)INT32_MAX) return fail(BA_ERR_UNSUPPORTED, "reduced camera system pattern too large");
+  S.ndest = (int)h_count;
+  {  // ascending keys: the empty slots (~0) sort to the end
+    DVec<uint64_t> sorted;
+    BA_TRY(sorted.alloc((size_t)cap));
+    BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, S.dh_keys.p, sorted.p, (int)cap, 0, 64, st); }));
+    BA_TRY(S.dest_keys.alloc(S.ndest));
+    BA_CUDA_TRY(cudaMemcpyAsync(S.dest_keys.p, sorted.p, sizeof(uint64_t) * S.ndest, cudaMemcpyDeviceToDevice, st));
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  BA_TRY(S.dh_val.alloc((size_t)cap));
+  k_dh_map<<<grid_for(S.ndest, B), B, 0, st>>>(S.dest_keys.p, S.ndest, S.dh_keys.p, S.dh_mask, S.dh_shift, S.dh_val.p);
+  BA_TRY(S.dest_fa.alloc(S.ndest)); BA_TRY(S.dest_fb.alloc(S.ndest)); BA_TRY(S.diag_dest.alloc(nf));
+  k_dest_finish<<<grid_for(S.ndest, B), B, 0, st>>>(S.dest_keys.p, S.ndest, nf, S.dest_fa.p, S.dest_fb.p, S.diag_dest.p);
+  BA_CUDA_TRY(cudaGetLastError());
+  S.pair_lists = false;
+  return BA_OK;
+}
+
+// the pair lists and their chunk table for a structure that was built without them (Model A, generic pipeline)
+inline int ensure_pair_lists(Structure& S, cudaStream_t st) {
+  if (S.pair_lists) return BA_OK;
+  BA_TRY(build_pair_lists(S, st));
+  BA_TRY(build_chunks(S.ch_pairs, S.dpair_ptr.p, S.ndest, 256, st));
+  BA_CUDA_TRY(cudaStreamSynchronize(st));
   return BA_OK;
 }
 
@@ -296,45 +479,9 @@ inline int build_structure(Structure& S, int64_t nb, int64_t ne, int64_t nf, con
     }
   }
 
-  // 4. destination blocks of the reduced system and their incidence-pair lists
-  DVec<uint64_t>& dest_keys = S.dest_keys;
-  {
-    DVec<int64_t> cnt, off;
-    BA_TRY(cnt.alloc(ne + 1)); BA_TRY(off.alloc(ne + 1));
-    k_pair_count<<<grid_for(ne + 1, 128), 128, 0, st>>>(S.einc_ptr, S.inc_f, ne, cnt.p);
-    BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt.p, off.p, (int)(ne + 1), st); }));
-    int64_t np = 0;
-    BA_CUDA_TRY(cudaMemcpyAsync(&np, off.p + ne, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    BA_CUDA_TRY(cudaStreamSynchronize(st));
-    S.npairs = np + nf;
-    if (S.npairs >= (int64_t)INT32_MAX) return fail(BA_ERR_UNSUPPORTED, "too many incidence pairs (%lld) for one GPU", (long long)S.npairs);
-    DVec<uint64_t> pk, pv, pks, pvs;
-    BA_TRY(pk.alloc(S.npairs)); BA_TRY(pv.alloc(S.npairs)); BA_TRY(pks.alloc(S.npairs)); BA_TRY(pvs.alloc(S.npairs));
-    if (ne > 0) k_pair_fill<<<grid_for(ne, 128), 128, 0, st>>>(S.einc_ptr, S.inc_f, ne, nf, off.p, pk.p, pv.p);
-    k_pair_diag_sentinels<<<grid_for(nf, B), B, 0, st>>>(nf, np, pk.p, pv.p);
-    BA_TRY(cub_call([&](void* t, size_t& b) {
-      return cub::DeviceRadixSort::SortPairs(t, b, pk.p, pks.p, pv.p, pvs.p, (int)S.npairs, 0, bits_for((uint64_t)nf * nf), st);
-    }));
-    pk.release(); pv.release();
-    DVec<int64_t> run_cnt;
-    DVec<int32_t> nruns;
-    BA_TRY(dest_keys.alloc(S.npairs)); BA_TRY(run_cnt.alloc(S.npairs + 1)); BA_TRY(nruns.alloc(1));
-    BA_TRY(cub_call([&](void* t, size_t& b) {
-      return cub::DeviceRunLengthEncode::Encode(t, b, pks.p, dest_keys.p, run_cnt.p, nruns.p, (int)S.npairs, st);
-    }));
-    int32_t nd = 0;
-    BA_CUDA_TRY(cudaMemcpyAsync(&nd, nruns.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    BA_CUDA_TRY(cudaStreamSynchronize(st));
-    S.ndest = nd;
-    BA_TRY(S.dpair_ptr.alloc(nd + 1));
-    BA_CUDA_TRY(cudaMemsetAsync(run_cnt.p + nd, 0, sizeof(int64_t), st));
-    BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, run_cnt.p, S.dpair_ptr.p, nd + 1, st); }));
-    BA_TRY(S.dest_fa.alloc(nd)); BA_TRY(S.dest_fb.alloc(nd)); BA_TRY(S.diag_dest.alloc(nf));
-    k_dest_finish<<<grid_for(nd, B), B, 0, st>>>(dest_keys.p, nd, nf, S.dest_fa.p, S.dest_fb.p, S.diag_dest.p);
-    BA_TRY(S.pairs.alloc(S.npairs));
-    k_unpack_pairs<<<grid_for(S.npairs, B), B, 0, st>>>(pvs.p, S.npairs, S.pairs.p);
-    BA_CUDA_TRY(cudaStreamSynchronize(st));
-  }
+  // 4. destination blocks of the reduced system (and, for the generic pipeline, their incidence-pair lists)
+  if (S.nslots == 1) BA_TRY(build_dest_hashed(S, st));
+  else BA_TRY(build_pair_lists(S, st));
   // 5. Model B: observations whose (f0,f1) is a destination block (off-diagonal F^T F terms)
   if (S.nslots == 2) {
     DVec<uint64_t> k, ks;
@@ -345,20 +492,13 @@ inline int build_structure(Structure& S, int64_t nb, int64_t ne, int64_t nf, con
     if (nb > 0)
       BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortPairs(t, b, k.p, ks.p, v.p, S.dobs.p, (int)nb, 0, 64, st); }));
     BA_TRY(S.dobs_ptr.alloc(S.ndest + 1));
-    k_dobs_ptr<<<grid_for(S.ndest + 1, B), B, 0, st>>>(ks.p, nb, dest_keys.p, S.ndest, S.dobs_ptr.p);
+    k_dobs_ptr<<<grid_for(S.ndest + 1, B), B, 0, st>>>(ks.p, nb, S.dest_keys.p, S.ndest, S.dobs_ptr.p);
     BA_CUDA_TRY(cudaStreamSynchronize(st));
-  }
-  {  // keep exactly ndest keys
-    DVec<uint64_t> exact;
-    BA_TRY(exact.alloc(S.ndest));
-    BA_CUDA_TRY(cudaMemcpyAsync(exact.p, dest_keys.p, sizeof(uint64_t) * S.ndest, cudaMemcpyDeviceToDevice, st));
-    BA_CUDA_TRY(cudaStreamSynchronize(st));
-    dest_keys.swap(exact);
   }
   // 6. chunk tables of the gather reductions
   BA_TRY(build_chunks(S.ch_fobs, S.fobs_ptr.p, (int)nf, 256, st));
   BA_TRY(build_chunks(S.ch_finc, S.finc_ptr.p, (int)nf, 512, st));
-  BA_TRY(build_chunks(S.ch_pairs, S.dpair_ptr.p, S.ndest, 256, st));
+  if (S.pair_lists) BA_TRY(build_chunks(S.ch_pairs, S.dpair_ptr.p, S.ndest, 256, st));
   if (S.nslots == 2) BA_TRY(build_chunks(S.ch_dobs, S.dobs_ptr.p, S.ndest, 128, st));
   BA_CUDA_TRY(cudaStreamSynchronize(st));
   BA_CUDA_TRY(cudaGetLastError());
