@@ -109,17 +109,36 @@ struct PcgParams {
   int* out_iters; int* status;
 };
 
-// sum of n per-warp partials, identical (bitwise) in every thread of every CTA
-__device__ __forceinline__ double pcg_total(const double* __restrict__ partial, int n, double* sm) {
-  double v = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) v += __ldcg(partial + i);
-  v = block_sum(v, sm);
+// sums of n per-warp partials (K arrays at once), identical (bitwise) in every thread of every CTA: strided per-thread
+// sums, warp trees, then EVERY warp folds the per-warp values with the same tree -- two barriers per call
+template <int K>
+__device__ __forceinline__ void pcg_totals(const double* const* partial, int n, double* sm /* K * 32 */, double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  double v[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] += __ldcg(partial[k] + i);
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    v[k] = warp_sum(v[k]);
+    if (lane == 0) sm[32 * k + warp] = v[k];
+  }
   __syncthreads();
-  if (threadIdx.x == 0) sm[0] = v;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double x = warp_sum(lane < nw ? sm[32 * k + lane] : 0.0);
+    out[k] = __shfl_sync(0xffffffffu, x, 0);
+  }
   __syncthreads();
-  v = sm[0];
-  __syncthreads();
-  return v;
+}
+__device__ __forceinline__ double pcg_total(const double* partial, int n, double* sm) {
+  const double* arr[1] = {partial};
+  double out[1];
+  pcg_totals<1>(arr, n, sm, out);
+  return out[0];
 }
 
 // (S v)_f with v = a + beta * b2 (b2 may be null); result valid in every lane
@@ -156,59 +175,105 @@ __device__ __forceinline__ void pcg_spmv_row(const PcgParams& P, int f, const do
   }
 }
 
-__global__ void __launch_bounds__(256) k_pcg(PcgParams P) {
-  __shared__ double sm[33];
+// K tile sums of a CTA (fixed tree); result valid in thread 0
+template <int K>
+__device__ __forceinline__ void pcg_block_sums(double* v, double* sm /* K * 32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    v[k] = warp_sum(v[k]);
+    if (lane == 0) sm[32 * k + warp] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(lane < nw ? sm[32 * k + lane] : 0.0);
+  }
+  __syncthreads();
+}
+
+// r, z = M^-1 r and the partial sums of one block row, by the six lanes base .. base + 5 of a warp (lane base + c owns
+// component c and holds x_c, r_c); every lane of the warp must call (shuffles), `on` says whether this lane has a row
+__device__ __forceinline__ void pcg_finish_row(const PcgParams& P, int f, bool on, int base, int c, double xv, double rv,
+                                               double& s_q, double& s_rz, double& s_rr) {
+  const int64_t o = 6 * (int64_t)f + c;
+  const double* Mi = P.Minv + 36 * (int64_t)f + 6 * c;
+  double m[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) m[j] = on ? Mi[j] : 0.0;
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) s += m[j] * __shfl_sync(0xffffffffu, rv, base + j);
+  if (on) {
+    P.r[o] = rv;
+    P.z[o] = s;
+    s_q += xv * (P.b[o] + rv);
+    s_rr += rv * rv;
+    s_rz += rv * s;
+  }
+}
+
+// One cooperative launch per linear solve.  Block rows are dealt one per WARP for the products with S (lane = stored
+// block of the row) and one per THREAD / per six lanes for everything that is local to a row (block-Jacobi factors,
+// vector updates), so no phase runs on one lane of a warp; the dot products leave every CTA as one partial each.
+__global__ void __launch_bounds__(256, 2) k_pcg(PcgParams P) {
+  __shared__ double sm[128];
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int gw = blockIdx.x * wpb + (threadIdx.x >> 5);
   const int GW = gridDim.x * wpb;
-  double* pa = P.partial; double* pb = pa + GW; double* pc = pb + GW; double* pd = pc + GW;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, GT = gridDim.x * blockDim.x;
+  const int NB = gridDim.x;
+  double* pa = P.partial; double* pb = pa + NB; double* pc = pb + NB; double* pd = pc + NB;
+  const int grp = lane / 6, comp = lane - 6 * grp;   // six lanes per row, five rows per warp (lanes 30, 31 idle)
 
-  // ---- setup: block-Jacobi preconditioner, x = 0, r = b, z = M^-1 r ----
+  // ---- setup: block-Jacobi preconditioner, x = 0, r = b, z = M^-1 r (one thread per block row) ----
   {
-    double s_bb = 0.0, s_rz = 0.0;
-    for (int f = gw; f < P.nf; f += GW) {
-      if (lane == 0) {
-        double L[36];
-        const double* D = P.Sb + 36 * (int64_t)P.diag[f];
+    double v[2] = {0.0, 0.0};   // b.b, r.z
+    for (int f = gt; f < P.nf; f += GT) {
+      double L[36];
+      const double* D = P.Sb + 36 * (int64_t)P.diag[f];
 #pragma unroll
-        for (int k = 0; k < 36; ++k) L[k] = D[k];
-        double* Mi = P.Minv + 36 * (int64_t)f;
-        if (!chol_small<6>(L)) {
-          atomicOr(P.status, 8);
+      for (int k = 0; k < 36; ++k) L[k] = D[k];
+      double* Mi = P.Minv + 36 * (int64_t)f;
+      double rv[6], zv[6];
 #pragma unroll
-          for (int k = 0; k < 36; ++k) Mi[k] = 0.0;
-        } else {
+      for (int i = 0; i < 6; ++i) { rv[i] = P.b[6 * (int64_t)f + i]; v[0] += rv[i] * rv[i]; zv[i] = 0.0; }
+      if (!chol_small<6>(L)) {
+        atomicOr(P.status, 8);
 #pragma unroll
-          for (int c = 0; c < 6; ++c) {
-            double col[6];
+        for (int k = 0; k < 36; ++k) Mi[k] = 0.0;
+      } else {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) col[i] = (i == c) ? 1.0 : 0.0;
-            fwd_small<6>(L, col);
-            bwd_small<6>(L, col);
+        for (int c = 0; c < 6; ++c) {
+          double col[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) Mi[i * 6 + c] = col[i];
-          }
-        }
-        double rv[6];
+          for (int i = 0; i < 6; ++i) col[i] = (i == c) ? 1.0 : 0.0;
+          fwd_small<6>(L, col);
+          bwd_small<6>(L, col);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { rv[i] = P.b[6 * (int64_t)f + i]; s_bb += rv[i] * rv[i]; }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          double s = 0.0;
-#pragma unroll
-          for (int j = 0; j < 6; ++j) s += Mi[i * 6 + j] * rv[j];
-          P.x[6 * (int64_t)f + i] = 0.0; P.r[6 * (int64_t)f + i] = rv[i]; P.z[6 * (int64_t)f + i] = s; P.p0[6 * (int64_t)f + i] = 0.0;
-          s_rz += rv[i] * s;
+          for (int i = 0; i < 6; ++i) { Mi[i * 6 + c] = col[i]; zv[i] += col[i] * rv[c]; }
         }
       }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int64_t o = 6 * (int64_t)f + i;
+        P.x[o] = 0.0; P.r[o] = rv[i]; P.z[o] = zv[i]; P.p0[o] = 0.0;
+        v[1] += rv[i] * zv[i];
+      }
     }
-    if (lane == 0) { pa[gw] = s_bb; pc[gw] = s_rz; }
+    pcg_block_sums<2>(v, sm);
+    if (threadIdx.x == 0) { pa[blockIdx.x] = v[0]; pc[blockIdx.x] = v[1]; }
   }
   grid.sync();
-  const double norm_b = sqrt(pcg_total(pa, GW, sm));
-  double rho = pcg_total(pc, GW, sm), last_rho = 1.0, Q0 = 0.0;
+  double tot0[2];
+  {
+    const double* arr[2] = {pa, pc};
+    pcg_totals<2>(arr, NB, sm, tot0);
+  }
+  const double norm_b = sqrt(tot0[0]);
+  double rho = tot0[1], last_rho = 1.0, Q0 = 0.0;
   const double tol_r = P.r_tol * norm_b;
   int iters = 0;
   bool failed = false;
@@ -226,69 +291,71 @@ __global__ void __launch_bounds__(256) k_pcg(PcgParams P) {
       double* pnew = cur ? P.p0 : P.p1;
       // ---- phase 1: p = z + beta p_old (formed on the fly for the neighbours), q = S p, partial p.q ----
       {
-        double s_pq = 0.0;
+        double v[1] = {0.0};
         for (int f = gw; f < P.nf; f += GW) {
           double acc[6];
           pcg_spmv_row(P, f, P.z, it > 1 ? pold : nullptr, beta, lane, acc);
-          if (lane == 0) {
+          double a = acc[0];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-              const double pv = P.z[6 * (int64_t)f + i] + (it > 1 ? beta * pold[6 * (int64_t)f + i] : 0.0);
-              pnew[6 * (int64_t)f + i] = pv;
-              P.q[6 * (int64_t)f + i] = acc[i];
-              s_pq += pv * acc[i];
-            }
+          for (int i = 1; i < 6; ++i) a = (lane == i) ? acc[i] : a;
+          if (lane < 6) {
+            const int64_t o = 6 * (int64_t)f + lane;
+            const double pv = P.z[o] + (it > 1 ? beta * pold[o] : 0.0);
+            pnew[o] = pv;
+            P.q[o] = a;
+            v[0] += pv * a;
           }
         }
-        if (lane == 0) pb[gw] = s_pq;
+        pcg_block_sums<1>(v, sm);
+        if (threadIdx.x == 0) pb[blockIdx.x] = v[0];
       }
       grid.sync();
-      const double pq = pcg_total(pb, GW, sm);
+      const double pq = pcg_total(pb, NB, sm);
       if (pq <= 0.0 || !isfinite(pq)) break;  // keep the current x (Ceres: LINEAR_SOLVER_NO_CONVERGENCE)
       const double alpha = rho / pq;
       if (!isfinite(alpha)) { failed = true; break; }
       const bool reset = (it % P.reset_period) == 0;
       // ---- phase 2: x += alpha p ; r ; z = M^-1 r ; partial sums ----
-      if (reset) {
-        for (int f = gw; f < P.nf; f += GW)
-          if (lane < 6) P.x[6 * (int64_t)f + lane] += alpha * pnew[6 * (int64_t)f + lane];
-        grid.sync();
-      }
       {
-        double s_q = 0.0, s_rz = 0.0, s_rr = 0.0;
-        for (int f = gw; f < P.nf; f += GW) {
-          double acc[6];
-          if (reset) pcg_spmv_row(P, f, P.x, nullptr, 0.0, lane, acc);
-          if (lane == 0) {
-            double rv[6], xv[6];
-            const double* Mi = P.Minv + 36 * (int64_t)f;
+        double v[3] = {0.0, 0.0, 0.0};   // x.(b + r), r.z, r.r
+        if (reset) {  // r = b - S x from scratch
+          for (int i = gt; i < 6 * P.nf; i += GT) P.x[i] += alpha * pnew[i];
+          grid.sync();
+          for (int f = gw; f < P.nf; f += GW) {
+            double acc[6];
+            pcg_spmv_row(P, f, P.x, nullptr, 0.0, lane, acc);
+            double a = acc[0];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-              const int64_t o = 6 * (int64_t)f + i;
-              if (reset) { xv[i] = P.x[o]; rv[i] = P.b[o] - acc[i]; }
-              else { xv[i] = P.x[o] + alpha * pnew[o]; P.x[o] = xv[i]; rv[i] = P.r[o] - alpha * P.q[o]; }
-              P.r[o] = rv[i];
-              s_q += xv[i] * (P.b[o] + rv[i]);
-              s_rr += rv[i] * rv[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-              double s = 0.0;
-#pragma unroll
-              for (int j = 0; j < 6; ++j) s += Mi[i * 6 + j] * rv[j];
-              P.z[6 * (int64_t)f + i] = s;
-              s_rz += rv[i] * s;
-            }
+            for (int i = 1; i < 6; ++i) a = (lane == i) ? acc[i] : a;
+            const bool on = lane < 6;
+            const int64_t o = 6 * (int64_t)f + (on ? lane : 0);
+            const double xv = on ? P.x[o] : 0.0, rv = on ? P.b[o] - a : 0.0;
+            pcg_finish_row(P, f, on, 0, on ? lane : 0, xv, rv, v[0], v[1], v[2]);
+          }
+        } else {      // r -= alpha q: five rows per warp, six lanes each
+          for (int f0 = 5 * gw; f0 < P.nf; f0 += 5 * GW) {
+            const int f = f0 + grp;
+            const bool on = lane < 30 && f < P.nf;
+            const int64_t o = 6 * (int64_t)(on ? f : 0) + comp;
+            double xv = 0.0, rv = 0.0;
+            if (on) { xv = P.x[o] + alpha * pnew[o]; P.x[o] = xv; rv = P.r[o] - alpha * P.q[o]; }
+            pcg_finish_row(P, on ? f : 0, on, 6 * (grp < 5 ? grp : 0), comp, xv, rv, v[0], v[1], v[2]);
           }
         }
-        if (lane == 0) { pa[gw] = s_q; pc[gw] = s_rz; pd[gw] = s_rr; }
+        pcg_block_sums<3>(v, sm);
+        if (threadIdx.x == 0) { pa[blockIdx.x] = v[0]; pc[blockIdx.x] = v[1]; pd[blockIdx.x] = v[2]; }
       }
       grid.sync();
-      const double Q1 = -pcg_total(pa, GW, sm);
+      double tot[3];
+      {
+        const double* arr[3] = {pa, pc, pd};
+        pcg_totals<3>(arr, NB, sm, tot);
+      }
+      const double Q1 = -tot[0];
       const double zeta = it * (Q1 - Q0) / Q1;
       last_rho = rho;
-      rho = pcg_total(pc, GW, sm);
-      const double rr = pcg_total(pd, GW, sm);
+      rho = tot[1];
+      const double rr = tot[2];
       cur ^= 1;
       if (zeta < P.eta && it >= P.min_it) break;
       Q0 = Q1;
@@ -301,8 +368,7 @@ __global__ void __launch_bounds__(256) k_pcg(PcgParams P) {
     if (failed) atomicOr(P.status, 16);
   }
   if (failed) {  // invalid step: make sure nothing non-finite leaks into the back-substitution
-    for (int f = gw; f < P.nf; f += GW)
-      if (lane < 6) P.x[6 * (int64_t)f + lane] = 0.0;
+    for (int i = gt; i < 6 * P.nf; i += GT) P.x[i] = 0.0;
   }
 }
 
