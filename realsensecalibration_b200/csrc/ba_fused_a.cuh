@@ -156,6 +156,29 @@ __global__ void k_fa_pair_fill(const int64_t* __restrict__ e_ptr, const int32_t*
         ++o;
       }
 }
+// the same pairs keyed by (tile, camera slot of i, camera slot of j) in 32 bits (GroupDecode mode 1)
+__global__ void k_fa_pair_fill32(const int64_t* __restrict__ e_ptr, const int32_t* __restrict__ ob_f, int64_t ne, const int64_t* __restrict__ off,
+                                 const int32_t* __restrict__ tile_of_pt, const int64_t* __restrict__ tile_pt_ptr,
+                                 const uint32_t* __restrict__ ob_meta, int sb, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int64_t o = off[e];
+  const uint32_t tile = (uint32_t)tile_of_pt[e];
+  const int64_t ob0 = e_ptr[tile_pt_ptr[tile]];
+  for (int64_t i = e_ptr[e]; i < e_ptr[e + 1]; ++i) {
+    const uint32_t si = ob_meta[i] >> 16;
+    for (int64_t j = e_ptr[e]; j < e_ptr[e + 1]; ++j)
+      if (ob_f[i] <= ob_f[j]) {
+        keys[o] = (tile << (2 * sb)) | (si << sb) | (ob_meta[j] >> 16);
+        vals[o] = (int32_t)(i - ob0) | ((int32_t)(j - ob0) << 16);
+        ++o;
+      }
+  }
+}
+__global__ void k_fa_max_diff(int n, const int64_t* __restrict__ ptr, int* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) atomicMax(out, (int)min(ptr[t + 1] - ptr[t], (int64_t)INT32_MAX));
+}
 __global__ void k_fa_cam_fill(const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f, int64_t nb, int64_t nf,
                               const int64_t* __restrict__ e_ptr, const int32_t* __restrict__ tile_of_pt, const int64_t* __restrict__ tile_pt_ptr,
                               uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
@@ -165,12 +188,37 @@ __global__ void k_fa_cam_fill(const int32_t* __restrict__ ob_e, const int32_t* _
   keys[o] = (uint64_t)tile * (uint64_t)nf + (uint64_t)ob_f[o];
   vals[o] = (int32_t)(o - e_ptr[tile_pt_ptr[tile]]);
 }
-__global__ void k_fa_group_meta(int ng, const uint64_t* __restrict__ group_key, uint64_t n_targets, int32_t* __restrict__ group_target,
+// How a group key splits into (tile, target).  mode 0: key = tile * n_targets + target (64-bit keys).  mode 1 (pair items
+// when the camera slots of a tile fit sb bits): key = tile << 2 sb | slot_i << sb | slot_j in 32 bits -- two thirds of the
+// sort traffic and one radix pass less on the 144 M pair entries of the 30 M-observation problem; the destination block
+// is then looked up once per GROUP (camera pair of the tile) instead of once per pair.
+struct GroupDecode {
+  int mode = 0, sb = 0, key_bits = 64;
+  uint64_t n_targets = 1, nf = 0;
+  const int64_t* tile_cam_ptr = nullptr;
+  const int32_t* tile_cams = nullptr;
+  const uint64_t* dh_keys = nullptr;
+  const int32_t* dh_val = nullptr;
+  uint64_t dh_mask = 0;
+  int dh_shift = 0;
+};
+template <typename K>
+__global__ void k_fa_group_meta(int ng, const K* __restrict__ group_key, GroupDecode D, int32_t* __restrict__ group_target,
                                 int32_t* __restrict__ group_tile) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ng) return;
-  group_target[g] = (int32_t)(group_key[g] % n_targets);
-  group_tile[g] = (int32_t)(group_key[g] / n_targets);
+  const uint64_t key = (uint64_t)group_key[g];
+  if (D.mode == 0) {
+    group_target[g] = (int32_t)(key % D.n_targets);
+    group_tile[g] = (int32_t)(key / D.n_targets);
+  } else {
+    const uint64_t m = ((uint64_t)1 << D.sb) - 1;
+    const int tile = (int)(key >> (2 * D.sb));
+    const int64_t c0 = D.tile_cam_ptr[tile];
+    const uint64_t ci = (uint64_t)D.tile_cams[c0 + (int64_t)((key >> D.sb) & m)], cj = (uint64_t)D.tile_cams[c0 + (int64_t)(key & m)];
+    group_target[g] = dh_find(D.dh_keys, D.dh_val, D.dh_mask, D.dh_shift, ci * D.nf + cj);
+    group_tile[g] = tile;
+  }
 }
 // per item: end, target, and the key (tile, descending length) the items are re-ordered by
 __global__ void k_fa_item_meta(int n_items, const int32_t* __restrict__ seg, const int64_t* __restrict__ begin, int ch,
@@ -303,17 +351,18 @@ __global__ void k_fa_bank_order(int n_tiles, const int64_t* __restrict__ tile_it
 
 // keys (tile * n_targets + target) with their entries -> sorted entries, groups, items of <= ch entries ordered by
 // (tile, descending length), reduction lists
-inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, int64_t n, int n_tiles, int64_t n_targets, int ch,
-                       bool is_pair, cudaStream_t st) {
+template <typename K>
+inline int build_items(ItemSet& I, DVec<K>& keys, DVec<int32_t>& vals, int64_t n, int n_tiles, int64_t n_targets, int ch,
+                       bool is_pair, const GroupDecode& D, cudaStream_t st) {
   I.n_ent = n; I.n_targets = (int)n_targets;
   FaLap L(st);
-  DVec<uint64_t> ks, gkey;
+  DVec<K> ks, gkey;
   DVec<int64_t> gcnt;
   DVec<int32_t> nruns, group_tile;
   BA_TRY(ks.alloc(n)); BA_TRY(I.ent.alloc(n));
   if (n > 0)
     BA_TRY(cub_call([&](void* t, size_t& b) {
-      return cub::DeviceRadixSort::SortPairs(t, b, keys.p, ks.p, vals.p, I.ent.p, (int)n, 0, bits_for((uint64_t)n_tiles * (uint64_t)n_targets), st);
+      return cub::DeviceRadixSort::SortPairs(t, b, keys.p, ks.p, vals.p, I.ent.p, (int)n, 0, D.key_bits, st);
     }));
   keys.release(); vals.release();
   L.lap("items: sort entries");
@@ -329,7 +378,7 @@ inline int build_items(ItemSet& I, DVec<uint64_t>& keys, DVec<int32_t>& vals, in
   BA_TRY(I.group_ptr.alloc(ng + 1)); BA_TRY(I.group_target.alloc(ng)); BA_TRY(group_tile.alloc(ng));
   BA_CUDA_TRY(cudaMemsetAsync(gcnt.p + ng, 0, sizeof(int64_t), st));
   BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, gcnt.p, I.group_ptr.p, ng + 1, st); }));
-  k_fa_group_meta<<<grid_for(ng, 256), 256, 0, st>>>(ng, gkey.p, (uint64_t)n_targets, I.group_target.p, group_tile.p);
+  k_fa_group_meta<K><<<grid_for(ng, 256), 256, 0, st>>>(ng, gkey.p, D, I.group_target.p, group_tile.p);
   BA_TRY(I.tile_group_ptr.alloc((size_t)n_tiles + 1));
   k_seg_ptr<int32_t><<<grid_for(ng > n_tiles + 1 ? ng : n_tiles + 1, 256), 256, 0, st>>>(group_tile.p, ng, n_tiles, I.tile_group_ptr.p);
   L.lap("items: groups");
@@ -422,6 +471,28 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
   BA_TRY(F.tile_pt_ptr.alloc((size_t)F.n_tiles + 1));
   k_seg_ptr<int32_t><<<grid_for(ne > F.n_tiles + 1 ? ne : F.n_tiles + 1, 256), 256, 0, st>>>(tile_of_pt.p, ne, F.n_tiles, F.tile_pt_ptr.p);
   L.lap("tiles");
+  // camera items, the tile camera lists and the per-observation word (local point | camera slot)
+  int max_tile_cams = 0;
+  {
+    DVec<uint64_t> keys;
+    DVec<int32_t> vals, group_tile;
+    DVec<int> mx;
+    BA_TRY(keys.alloc(nb)); BA_TRY(vals.alloc(nb)); BA_TRY(mx.alloc_zero(1, st));
+    k_fa_cam_fill<<<grid_for(nb, 256), 256, 0, st>>>(S.ob_e.p, S.ob_f0.p, nb, nf, S.e_ptr.p, tile_of_pt.p, F.tile_pt_ptr.p, keys.p, vals.p);
+    GroupDecode D;
+    D.n_targets = (uint64_t)nf; D.key_bits = bits_for((uint64_t)F.n_tiles * (uint64_t)nf);
+    BA_TRY(build_items<uint64_t>(F.cams, keys, vals, nb, F.n_tiles, nf, F.ch_cam, false, D, st));
+    const int ng = F.cams.n_groups;
+    BA_TRY(group_tile.alloc(ng)); BA_TRY(F.ob_meta.alloc(nb));
+    // group -> tile from the tile_group_ptr CSR (groups are tile-major)
+    k_fa_group_tile<<<grid_for(F.n_tiles, 256), 256, 0, st>>>(F.n_tiles, F.cams.tile_group_ptr.p, group_tile.p);
+    k_fa_ob_meta<<<grid_for(ng, 256), 256, 0, st>>>(ng, F.cams.group_ptr.p, group_tile.p, F.cams.tile_group_ptr.p, F.cams.ent.p, S.e_ptr.p,
+                                                    F.tile_pt_ptr.p, S.ob_e.p, F.ob_meta.p);
+    k_fa_max_diff<<<grid_for(F.n_tiles, 256), 256, 0, st>>>(F.n_tiles, F.cams.tile_group_ptr.p, mx.p);
+    BA_CUDA_TRY(cudaMemcpyAsync(&max_tile_cams, mx.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BA_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  L.lap("camera items");
   // pair items
   {
     DVec<int64_t> cnt, off;
@@ -432,28 +503,32 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
     BA_CUDA_TRY(cudaMemcpyAsync(&np, off.p + ne, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     BA_CUDA_TRY(cudaStreamSynchronize(st));
     if (np >= (int64_t)INT32_MAX) return BA_ERR_UNSUPPORTED;
-    DVec<uint64_t> keys;
     DVec<int32_t> vals;
-    BA_TRY(keys.alloc(np)); BA_TRY(vals.alloc(np));
-    k_fa_pair_fill<<<grid_for(ne, 128), 128, 0, st>>>(S.e_ptr.p, S.ob_f0.p, ne, nf, off.p, tile_of_pt.p, F.tile_pt_ptr.p, S.dest_keys.p,
-                                                      S.ndest, S.dh_keys.n ? S.dh_keys.p : nullptr, S.dh_val.p, S.dh_mask, S.dh_shift, keys.p,
-                                                      vals.p);
-    L.lap("pair fill");
-    BA_TRY(build_items(F.pairs, keys, vals, np, F.n_tiles, S.ndest, F.ch_pair, true, st));
-  }
-  // camera items, the tile camera lists and the per-observation camera slot
-  {
-    DVec<uint64_t> keys;
-    DVec<int32_t> vals, group_tile;
-    BA_TRY(keys.alloc(nb)); BA_TRY(vals.alloc(nb));
-    k_fa_cam_fill<<<grid_for(nb, 256), 256, 0, st>>>(S.ob_e.p, S.ob_f0.p, nb, nf, S.e_ptr.p, tile_of_pt.p, F.tile_pt_ptr.p, keys.p, vals.p);
-    BA_TRY(build_items(F.cams, keys, vals, nb, F.n_tiles, nf, F.ch_cam, false, st));
-    const int ng = F.cams.n_groups;
-    BA_TRY(group_tile.alloc(ng)); BA_TRY(F.ob_meta.alloc(nb));
-    // group -> tile from the tile_group_ptr CSR (groups are tile-major)
-    k_fa_group_tile<<<grid_for(F.n_tiles, 256), 256, 0, st>>>(F.n_tiles, F.cams.tile_group_ptr.p, group_tile.p);
-    k_fa_ob_meta<<<grid_for(ng, 256), 256, 0, st>>>(ng, F.cams.group_ptr.p, group_tile.p, F.cams.tile_group_ptr.p, F.cams.ent.p, S.e_ptr.p,
-                                                    F.tile_pt_ptr.p, S.ob_e.p, F.ob_meta.p);
+    BA_TRY(vals.alloc(np));
+    const int sb = bits_for((uint64_t)std::max(max_tile_cams - 1, 1));
+    const int tb = bits_for((uint64_t)std::max(F.n_tiles - 1, 1));
+    GroupDecode D;
+    D.n_targets = (uint64_t)S.ndest; D.nf = (uint64_t)nf;
+    if (S.dh_keys.n && 2 * sb + tb <= 32 && env_int("BA_FA_KEY32", 0, 1, 1)) {   // 32-bit keys (tile, camera slot i, camera slot j)
+      DVec<uint32_t> keys;
+      BA_TRY(keys.alloc(np));
+      k_fa_pair_fill32<<<grid_for(ne, 128), 128, 0, st>>>(S.e_ptr.p, S.ob_f0.p, ne, off.p, tile_of_pt.p, F.tile_pt_ptr.p, F.ob_meta.p, sb, keys.p,
+                                                          vals.p);
+      L.lap("pair fill (32-bit keys)");
+      D.mode = 1; D.sb = sb; D.key_bits = 2 * sb + tb;
+      D.tile_cam_ptr = F.cams.tile_group_ptr.p; D.tile_cams = F.cams.group_target.p;
+      D.dh_keys = S.dh_keys.p; D.dh_val = S.dh_val.p; D.dh_mask = S.dh_mask; D.dh_shift = S.dh_shift;
+      BA_TRY(build_items<uint32_t>(F.pairs, keys, vals, np, F.n_tiles, S.ndest, F.ch_pair, true, D, st));
+    } else {
+      DVec<uint64_t> keys;
+      BA_TRY(keys.alloc(np));
+      k_fa_pair_fill<<<grid_for(ne, 128), 128, 0, st>>>(S.e_ptr.p, S.ob_f0.p, ne, nf, off.p, tile_of_pt.p, F.tile_pt_ptr.p, S.dest_keys.p,
+                                                        S.ndest, S.dh_keys.n ? S.dh_keys.p : nullptr, S.dh_val.p, S.dh_mask, S.dh_shift, keys.p,
+                                                        vals.p);
+      L.lap("pair fill");
+      D.key_bits = bits_for((uint64_t)F.n_tiles * (uint64_t)S.ndest);
+      BA_TRY(build_items<uint64_t>(F.pairs, keys, vals, np, F.n_tiles, S.ndest, F.ch_pair, true, D, st));
+    }
   }
   {  // per-tile slices of the entry lists; shared-memory geometry from the fullest tile
     const int nt = F.n_tiles;
@@ -477,7 +552,7 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
     }
     if (F.smem1() > FA_SMEM_MAX || F.smem2() > FA_SMEM_MAX || F.smemj(FA_JAC_THREADS) > FA_SMEM_MAX) return BA_ERR_UNSUPPORTED;
   }
-  L.lap("camera items, geometry");
+  L.lap("pair items, geometry");
   BA_TRY(F.tiles.alloc((size_t)F.n_tiles));
   k_fa_tile_desc<<<grid_for(F.n_tiles, 256), 256, 0, st>>>(F.n_tiles, F.tile_pt_ptr.p, S.e_ptr.p, F.cams.tile_group_ptr.p, F.tile_pent_ptr.p,
                                                           F.tile_cent_ptr.p, F.pairs.tile_item_ptr.p, F.cams.tile_item_ptr.p, F.tiles.p);
