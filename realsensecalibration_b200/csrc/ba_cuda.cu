@@ -69,13 +69,13 @@ enum Family { F_JAC = 0, F_SCHUR, F_SOLVE, F_UPDATE, F_COST, F_COLL, F_COUNT };
 // one entry per kernel (family member) of the solve path; names are what ba_cuda_get_kernel_stats() reports
 enum KT {
   KT_TABLES = 0, KT_JAC, KT_COST, KT_FOBS, KT_EM, KT_INCW, KT_DOBS, KT_ECHOL, KT_INCY, KT_FINC, KT_PAIRS, KT_SEGFIN,
-  KT_ASSEMBLE, KT_RCS, KT_BACKSUB, KT_MODELCOST, KT_CANDIDATE, KT_GRADNORM, KT_FOLD, KT_MISC, KT_FA_P1, KT_FA_RED, KT_FA_P2, KT_COUNT
+  KT_ASSEMBLE, KT_RCS, KT_BACKSUB, KT_MODELCOST, KT_CANDIDATE, KT_GRADNORM, KT_FOLD, KT_MISC, KT_FA_P1, KT_FA_RED, KT_FA_P2, KT_FA_P1L, KT_COUNT
 };
 const char* const kKtName[KT_COUNT] = {
   "k1_tables", "k1_residual_jacobian", "k5_cost", "k2_fobs_partial", "k2_e_normal", "k2_inc_w", "k2_dobs_partial",
   "k2_e_cholesky", "k2_inc_y", "k2_finc_partial", "k2_pairs_partial", "k2_seg_final", "k2_assemble", "k3_rcs_solve",
   "k4_backsub", "k4_model_cost", "k4_candidate", "k4_gradient_norm", "fold_partials", "misc",
-  "k1k2_fused_pass1", "k2_reduce_items", "k4k5_fused_pass2"};
+  "k1k2_fused_pass1", "k2_reduce_items", "k4k5_fused_pass2", "k1_fused_pass1_light"};
 }  // namespace
 
 struct LmState {  // TrustRegionMinimizer's loop variables, kept between ba_cuda_solve_iterate() calls
@@ -556,8 +556,9 @@ int fa_set_smem_attr() {
   static bool done = false;
   if (!done) {
     const int kMax = (int)FA_SMEM_MAX;  // dynamic part; the kernels also hold a little static shared memory
-    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
-    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<FA_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<FA_NORMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<FA_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_jac, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     done = true;
@@ -588,8 +589,9 @@ int fa_reduce(ba_cuda_problem* p, bool cams, bool pairs) {
 
 // r, J, cost, gradient norms at x AND the eliminated Schur system for the radius in scal[S_RADIUS]
 // (TrustRegionMinimizer::EvaluateGradientAndJacobian + SchurEliminator::Eliminate in one pass).
-// norms = true: iteration 0, computes the Jacobi scaling only.
-int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms) {
+// norms = true: iteration 0, computes the Jacobi scaling only.  grad_only = true: no further step can follow (the
+// iteration limit is reached), so only what the row of the progress table needs is computed: cost and gradient.
+int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms, bool grad_only = false) {
   const Structure& S = p->S;
   FusedA& F = p->FA;
   BA_TRY(fa_set_smem_attr());
@@ -602,7 +604,7 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms) {
   const FaParams P = fa_params(p, opt);
   const int nt = F.n_tiles;
   if (norms) {
-    BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<true>), nt, F.threads, F.smem1(), P);
+    BA_LAUNCH(p, KT_FA_P1L, (k_fa_pass1<FA_NORMS>), nt, F.threads, F.smem1(), P);
     BA_TRY(fa_reduce(p, true, false));
     BA_TRY(allreduce(p, F.camacc.p, (size_t)S.nf * FA_NVC, kNcclSum));
     BA_LAUNCH(p, KT_MISC, (k_jacobi_scale<6, FA_NVC>), grid_for(S.nf * 6, 256), 256, 0, S.nf, F.camacc.p, p->sf.p);
@@ -611,14 +613,15 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms) {
     return BA_OK;
   }
   BA_CUDA_TRY(cudaMemsetAsync(p->status.p, 0, sizeof(int), p->st));
-  BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<false>), nt, F.threads, F.smem1(), P);
+  if (grad_only) BA_LAUNCH(p, KT_FA_P1L, (k_fa_pass1<FA_GRAD>), nt, F.threads, F.smem1(), P);
+  else BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<FA_FULL>), nt, F.threads, F.smem1(), P);
   {
     FoldJob J = {{P.cost_partial, P.g2_partial, P.gmax_partial, nullptr}, {S_COST, S_G2E, S_GMAXE, 0}, {0, 0, 1, 0}};
     BA_LAUNCH(p, KT_FOLD, k_fold_multi, 3, 1024, 0, J, nt, p->scal.p);
   }
   fam_end(p, F_JAC);
   fam_begin(p, F_SCHUR);
-  BA_TRY(fa_reduce(p, true, true));
+  BA_TRY(fa_reduce(p, true, !grad_only));
   fam_end(p, F_SCHUR);
   if (p->world > 1) {  // camera sums and the shard-local gradient scalars in one collective
     fam_begin(p, F_COLL);
@@ -782,7 +785,7 @@ int lm_begin(ba_cuda_problem* p, const ba_cuda_options& opt) {
   if (lm_fused(p)) {
     if (opt.jacobi_scaling) BA_TRY(fa_linearize(p, opt, true));
     BA_CUDA_TRY(cudaMemcpyAsync(p->scal.p + S_RADIUS, &L.radius, sizeof(double), cudaMemcpyHostToDevice, p->st));
-    BA_TRY(fa_linearize(p, opt, false));
+    BA_TRY(fa_linearize(p, opt, false, opt.max_num_iterations <= 0));
   } else {
     BA_TRY((eval_gradient_and_jacobian<RD, DE, GE>(p, true, opt.jacobi_scaling != 0)));
   }
@@ -871,7 +874,7 @@ int lm_iterate(ba_cuda_problem* p, int32_t max_new) {
       L.decrease_factor = 2.0;
       if (fused) {  // the next step's radius is known: linearize and eliminate in the same pass
         BA_CUDA_TRY(cudaMemcpyAsync(p->scal.p + S_RADIUS, &L.radius, sizeof(double), cudaMemcpyHostToDevice, p->st));
-        BA_TRY(fa_linearize(p, opt, false));
+        BA_TRY(fa_linearize(p, opt, false, row.iteration >= opt.max_num_iterations));   // the last row: nothing to eliminate for
       } else {
         BA_TRY((eval_gradient_and_jacobian<RD, DE, GE>(p, false, opt.jacobi_scaling != 0)));
       }
@@ -1474,6 +1477,9 @@ static double algorithmic_bytes(const ba_cuda_problem* p, int kt) {
     // fused Model A passes, accounted with the bytes of the materialised layout they replace:
     // pass 1 = K1 (184 B/obs) + K2 (168 B/obs read, 72 B/point, 336 B/camera, 288 B/stored block written)
     case KT_FA_P1: return nb * (184.0 + 168.0) + ne * (24.0 + 72.0) + nf * (80.0 + 336.0) + (double)S.ndest * 288.0;
+    // the light variants of pass 1 (Jacobi scaling at iteration 0; cost + gradient after the last step): K1 + the F^T F / F^T r
+    // and E^T E / E^T r accumulations, nothing eliminated
+    case KT_FA_P1L: return nb * (184.0 + 116.0 + 64.0) + ne * (24.0 + 72.0) + nf * (80.0 + 216.0);
     // pass 2 = K4 (152 B/obs + 72 B/point read, 24 B/point + 48 B/camera written) + cost-only evaluation (24 B/obs)
     case KT_FA_P2: return nb * (152.0 + 24.0) + ne * (72.0 + 24.0 + 24.0) + nf * (48.0 + 80.0);
     default: return 0.0;

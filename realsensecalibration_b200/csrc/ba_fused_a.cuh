@@ -50,6 +50,7 @@ constexpr int FA_PENT_MAX = 6144;            // pair entries staged in shared me
 constexpr size_t FA_SMEM_MAX = 231000;      // dynamic shared memory per CTA (232448 opt-in limit minus the static part)
 constexpr int FA_LS = 10;                    // per point in shared memory: L10 L20 L21 | 1/L00 1/L11 1/L22 | z (3) | pad
 constexpr int FA_PS2 = 7;                    // pass 2 / k_fa_jac, per point in shared memory: x_e (3, then the candidate) | scale (3) | pad (odd stride)
+constexpr int FA_FULL = 0, FA_NORMS = 1, FA_GRAD = 2;   // modes of k_fa_pass1
 constexpr int FA_JAC_THREADS = 128;          // k_fa_jac: four CTAs per SM
 constexpr int FA_RECJ = 18;                  // k_fa_jac: doubles staged per observation (J_e 6 | J_f 12), in a per-warp buffer
 
@@ -712,15 +713,18 @@ __device__ __forceinline__ int fa_item_index(int r, bool reverse) {
   return r * n + ((((r & 1) != 0) != reverse) ? n - 1 - t : t);
 }
 
-// NORMS = true: iteration 0 only, unscaled Jacobian; writes the Jacobi scaling of the points and the camera items
-// (their F^T F diagonals are the camera column norms); no Schur products.
+// MODE FA_FULL: linearise and eliminate.  MODE FA_NORMS: iteration 0 only, unscaled Jacobian; writes the Jacobi scaling
+// of the points and the camera items (their F^T F diagonals are the camera column norms); no Schur products.
+// MODE FA_GRAD: cost and gradient only (scaled Jacobian, camera items, no Cholesky, no Schur products) -- the
+// evaluation after the last step of a solve, where Ceres evaluates the Jacobian too but never eliminates it.
 //
 // Latency plan (the kernel is bound by dependent round trips, not by bytes or flops): the tile descriptor is one
 // load; the camera tables, the tile's points (x_e, scale) and the work-item entry lists arrive by cp.async while the
 // threads fetch, into registers, the first observation, the first point range and the first work items they will
 // handle -- so every phase after the first barrier starts from shared memory or registers.
-template <bool NORMS>
+template <int MODE>
 __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
+  constexpr bool NORMS = MODE == FA_NORMS, FULL = MODE == FA_FULL;
   extern __shared__ double smem[];
   double* rec = smem;                                   // [cap][FA_REC]: U (6) | Jf (12) | r (2) | w (2)
   double* Ls = rec + (size_t)P.cap * FA_REC;            // [pts_cap][FA_LS]: x_e (3) | scale (3), then L (6) | z (3)
@@ -733,7 +737,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
   const FaTile T = fa_load_tile(P.tiles + tile);
   const int64_t pt0 = T.pt0, ob0 = T.ob0, pe0 = T.pe0, ce0 = T.ce0;
   const int nobs = T.nobs, npts = T.npts;
-  const int npe = NORMS ? 0 : min(T.npe, P.pent_cap);
+  const int npe = FULL ? min(T.npe, P.pent_cap) : 0;
   const int nce = min(T.nce, P.cap);
   // group 1 (needed by A1): camera tables, points
   fa_stage_tables_async(P, T, P.tab_f, tabs, TAB, nullptr);
@@ -749,7 +753,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
   __pipeline_commit();
   // registers: first work items, first point range, first observation of this thread
   int pq0 = 0, pq1 = 0, cq0 = 0, cq1 = 0, pl0 = 0, pl1 = 0;
-  if (!NORMS && tid < T.npitem) {
+  if (FULL && tid < T.npitem) {
     pq0 = (int)(P.pitem_begin[T.pitem0 + tid] - pe0);
     pq1 = (int)(P.pitem_end[T.pitem0 + tid] - pe0);
   }
@@ -826,6 +830,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
         gmx = fmax(gmx, fabs(d)); g2 += d * d;
       }
     }
+    if (!FULL) continue;
     {
       const double da = sqrt(fmin(fmax(M[0], P.min_diag), P.max_diag) / radius);
       const double db = sqrt(fmin(fmax(M[3], P.min_diag), P.max_diag) / radius);
@@ -846,7 +851,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
   __pipeline_wait_prior(0);
   __syncthreads();
   // ---- A2b: one thread per observation: U = L^-1 J_e^T (rows), w = U^T z; L | z of the tile leave as full lines ----
-  if (!NORMS) {
+  if (FULL) {
     for (int i = tid; i < 9 * npts; i += nthr) { const int lp = i / 9; P.Lz[9 * pt0 + i] = Ls[lp * FA_LS + (i - 9 * lp)]; }
     for (int l = tid; l < nobs; l += nthr) {
       double* R = rec + (size_t)l * FA_REC;
@@ -867,7 +872,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
     __syncthreads();
   }
   // ---- B: one thread per work item ----
-  if (!NORMS) {
+  if (FULL) {
     for (int r = 0; r * nthr < T.npitem; ++r) {
       const int idx = fa_item_index(r, false);
       if (idx >= T.npitem) continue;
