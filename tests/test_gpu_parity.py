@@ -173,6 +173,47 @@ def test_solve_synthetic_vs_oracle(gpu, oracle, name):
         assert np.abs(x - xo).max() < POSE_ATOL
 
 
+def test_model_a_generic_pipeline_matches_fused_and_oracle(gpu, oracle):
+    # force_generic_path sends Model A through the materialised-Jacobian pipeline (K1 by k_fa_jac, the per-destination
+    # incidence-pair lists built on demand): same rows as the fused two-pass path and as the oracle
+    pr = S.bal_like(60, 5000, 6, 16, 13, variable_degree=True)
+    gpu.set_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr)
+    gpu.set_parameters(pr.params)
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params)
+    s_f, rows_f = gpu.solve()
+    x_f = gpu.get_parameters()
+    opt = cuda.default_options()
+    opt.force_generic_path = 1
+    gpu.set_parameters(pr.params)
+    s_g, rows_g = gpu.solve(opt)
+    x_g = gpu.get_parameters()
+    _check_rows(rows_g, rows_o)
+    _check_rows(rows_f, rows_o)
+    assert np.abs(x_g - xo).max() < POSE_ATOL and np.abs(x_g - x_f).max() < POSE_ATOL
+    assert (s_g.termination_type, s_g.termination_reason) == (so.termination_type, so.termination_reason)
+
+
+def test_tiles_with_more_cameras_than_the_staged_tables(gpu, oracle):
+    # window = all cameras: a 480-observation tile sees ~100 different cameras, more than the 48 tables the fused kernels
+    # stage in shared memory, so most observations take the read-the-table-from-L2 branch of pass 1 / pass 2 / k_fa_jac
+    pr = S.bal_like(120, 4000, 5, 120, 31)
+    gpu.set_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr)
+    gpu.set_parameters(pr.params)
+    cost, res, jac = gpu.eval()
+    co, ro, jo = oracle.eval_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params)
+    assert H.rel(cost, co) < 1e-12
+    assert np.abs(res - ro).max() < 1e-8
+    assert _jac_close(jac, jo) < 1e-10
+    opt_g, opt_o = cuda.default_options(), oracle.default_options()
+    for o in (opt_g, opt_o):
+        o.max_num_iterations = 6
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
+    s, rows = gpu.solve(opt_g)
+    x = gpu.get_parameters()
+    _check_rows(rows, rows_o)
+    assert np.abs(x - xo).max() < POSE_ATOL
+
+
 @pytest.mark.parametrize("name", ["balA_n720", "rigB_n384", "balA_n1806_forced"])
 def test_blocked_dense_cholesky_vs_oracle(gpu, oracle, name):
     # reduced camera systems too large for one CTA's shared memory (n > 160): blocked DMMA Cholesky over the whole GPU
