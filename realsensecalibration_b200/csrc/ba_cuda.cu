@@ -559,6 +559,7 @@ int fa_set_smem_attr() {
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<FA_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<FA_NORMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<FA_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<FA_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_jac, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     done = true;
@@ -591,12 +592,14 @@ int fa_reduce(ba_cuda_problem* p, bool cams, bool pairs) {
 // (TrustRegionMinimizer::EvaluateGradientAndJacobian + SchurEliminator::Eliminate in one pass).
 // norms = true: iteration 0, computes the Jacobi scaling only.  grad_only = true: no further step can follow (the
 // iteration limit is reached), so only what the row of the progress table needs is computed: cost and gradient.
-int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms, bool grad_only = false) {
+// first = true: iteration 0 with Jacobi scaling in one pass (FA_FIRST): the point scaling is applied inside the pass, the
+// camera scaling to the reduced results.
+int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms, bool grad_only = false, bool first = false) {
   const Structure& S = p->S;
   FusedA& F = p->FA;
   BA_TRY(fa_set_smem_attr());
   fam_begin(p, F_JAC);
-  if (norms) {
+  if (norms || first) {
     BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.nf * 6, 256), 256, 0, p->sf.p, S.nf * 6, 1.0);
     BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.ne * 3, 256), 256, 0, p->se.p, S.ne * 3, 1.0);
   }
@@ -614,6 +617,7 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms, boo
   }
   BA_CUDA_TRY(cudaMemsetAsync(p->status.p, 0, sizeof(int), p->st));
   if (grad_only) BA_LAUNCH(p, KT_FA_P1L, (k_fa_pass1<FA_GRAD>), nt, F.threads, F.smem1(), P);
+  else if (first) BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<FA_FIRST>), nt, F.threads, F.smem1(), P);
   else BA_LAUNCH(p, KT_FA_P1, (k_fa_pass1<FA_FULL>), nt, F.threads, F.smem1(), P);
   {
     FoldJob J = {{P.cost_partial, P.g2_partial, P.gmax_partial, nullptr}, {S_COST, S_G2E, S_GMAXE, 0}, {0, 0, 1, 0}};
@@ -627,6 +631,12 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms, boo
     fam_begin(p, F_COLL);
     BA_TRY(allreduce_with_grad_tail(p, F.camacc.p, (size_t)S.nf * FA_NVC));
     fam_end(p, F_COLL);
+  }
+  if (first) {  // camera scaling from the (global) unscaled column norms, then everything reduced so far into scaled columns
+    BA_LAUNCH(p, KT_MISC, (k_jacobi_scale<6, FA_NVC>), grid_for(S.nf * 6, 256), 256, 0, S.nf, F.camacc.p, p->sf.p);
+    BA_LAUNCH(p, KT_MISC, k_fa_scale_cams, grid_for(S.nf * FA_NVC, 256), 256, 0, S.nf, p->sf.p, F.camacc.p);
+    BA_LAUNCH(p, KT_MISC, k_fa_scale_pairs, grid_for((int64_t)S.ndest * 36, 256), 256, 0, S.ndest, S.dest_fa.p, S.dest_fb.p, p->sf.p, p->Pacc.p);
+    BA_TRY(build_tables(p, false));   // pass 2 linearises with the scaled camera columns
   }
   const int gf = (int)grid_for(S.nf * 6, 256);
   BA_LAUNCH(p, KT_GRADNORM, (k_gradient_norm<6, FA_NVC, 21>), gf, 256, 0, S.nf, p->f_act_ptr.p, p->xf.p, p->sf.p, F.camacc.p, p->bp0.p, p->bp1.p);
@@ -783,9 +793,11 @@ int lm_begin(ba_cuda_problem* p, const ba_cuda_options& opt) {
   L.began = true;
   const double iter_t0 = now_s();
   if (lm_fused(p)) {
-    if (opt.jacobi_scaling) BA_TRY(fa_linearize(p, opt, true));
+    static const bool one_pass = env_int("BA_FA_FIRST", 0, 1, 1) != 0;
+    const bool first = opt.jacobi_scaling && opt.max_num_iterations > 0 && one_pass;
+    if (opt.jacobi_scaling && !first) BA_TRY(fa_linearize(p, opt, true));
     BA_CUDA_TRY(cudaMemcpyAsync(p->scal.p + S_RADIUS, &L.radius, sizeof(double), cudaMemcpyHostToDevice, p->st));
-    BA_TRY(fa_linearize(p, opt, false, opt.max_num_iterations <= 0));
+    BA_TRY(fa_linearize(p, opt, false, opt.max_num_iterations <= 0, first));
   } else {
     BA_TRY((eval_gradient_and_jacobian<RD, DE, GE>(p, true, opt.jacobi_scaling != 0)));
   }

@@ -50,7 +50,7 @@ constexpr int FA_PENT_MAX = 6144;            // pair entries staged in shared me
 constexpr size_t FA_SMEM_MAX = 231000;      // dynamic shared memory per CTA (232448 opt-in limit minus the static part)
 constexpr int FA_LS = 10;                    // per point in shared memory: L10 L20 L21 | 1/L00 1/L11 1/L22 | z (3) | pad
 constexpr int FA_PS2 = 7;                    // pass 2 / k_fa_jac, per point in shared memory: x_e (3, then the candidate) | scale (3) | pad (odd stride)
-constexpr int FA_FULL = 0, FA_NORMS = 1, FA_GRAD = 2;   // modes of k_fa_pass1
+constexpr int FA_FULL = 0, FA_NORMS = 1, FA_GRAD = 2, FA_FIRST = 3;   // modes of k_fa_pass1
 constexpr int FA_JAC_THREADS = 128;          // k_fa_jac: four CTAs per SM
 constexpr int FA_RECJ = 18;                  // k_fa_jac: doubles staged per observation (J_e 6 | J_f 12), in a per-warp buffer
 
@@ -717,6 +717,10 @@ __device__ __forceinline__ int fa_item_index(int r, bool reverse) {
 // of the points and the camera items (their F^T F diagonals are the camera column norms); no Schur products.
 // MODE FA_GRAD: cost and gradient only (scaled Jacobian, camera items, no Cholesky, no Schur products) -- the
 // evaluation after the last step of a solve, where Ceres evaluates the Jacobian too but never eliminates it.
+// MODE FA_FIRST: iteration 0 in ONE pass.  The Jacobi scaling of a point is local to its tile: it is computed from the
+// unscaled E^T E, written out, and applied to the point's records before anything is eliminated.  The cameras' scaling
+// needs the global column norms, so the camera side stays unscaled here (scale fields of the tables = 1) and the reduced
+// results (F^T F, F^T r, sum v, Schur products) are scaled afterwards, per block (k_fa_scale_cams / k_fa_scale_pairs).
 //
 // Latency plan (the kernel is bound by dependent round trips, not by bytes or flops): the tile descriptor is one
 // load; the camera tables, the tile's points (x_e, scale) and the work-item entry lists arrive by cp.async while the
@@ -724,7 +728,7 @@ __device__ __forceinline__ int fa_item_index(int r, bool reverse) {
 // handle -- so every phase after the first barrier starts from shared memory or registers.
 template <int MODE>
 __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
-  constexpr bool NORMS = MODE == FA_NORMS, FULL = MODE == FA_FULL;
+  constexpr bool NORMS = MODE == FA_NORMS, FIRST = MODE == FA_FIRST, FULL = MODE == FA_FULL || FIRST, UNIT = NORMS || FIRST;
   extern __shared__ double smem[];
   double* rec = smem;                                   // [cap][FA_REC]: U (6) | Jf (12) | r (2) | w (2)
   double* Ls = rec + (size_t)P.cap * FA_REC;            // [pts_cap][FA_LS]: x_e (3) | scale (3), then L (6) | z (3)
@@ -744,7 +748,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
   for (int i = tid; i < 3 * npts; i += nthr) {
     const int lp = i / 3, k = i - 3 * lp;
     __pipeline_memcpy_async(Ls + lp * FA_LS + k, P.xe + 3 * pt0 + i, 8);
-    if (!NORMS) __pipeline_memcpy_async(Ls + lp * FA_LS + 3 + k, P.se + 3 * pt0 + i, 8);
+    if (!UNIT) __pipeline_memcpy_async(Ls + lp * FA_LS + 3 + k, P.se + 3 * pt0 + i, 8);
   }
   __pipeline_commit();
   // group 2 (needed by B): the work-item entry lists
@@ -786,7 +790,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
     const double* xs = Ls + lp * FA_LS;
     const double X[3] = {xs[0], xs[1], xs[2]};
     double s[3] = {1.0, 1.0, 1.0};
-    if (!NORMS) { s[0] = xs[3]; s[1] = xs[4]; s[2] = xs[5]; }
+    if (!UNIT) { s[0] = xs[3]; s[1] = xs[4]; s[2] = xs[5]; }
     double r[2], je[6], jf[12];
     fa_linearize(Tt, X, s, ob, r, je, jf);
     sq += r[0] * r[0] + r[1] * r[1];
@@ -822,6 +826,18 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
       continue;
     }
     double* ls = Ls + lp * FA_LS;
+    if (FIRST) {  // Jacobi scaling of this point from the unscaled column norms; E^T E, E^T r and the records in scaled columns
+      const double s0 = 1.0 / (1.0 + sqrt(M[0])), s1 = 1.0 / (1.0 + sqrt(M[3])), s2 = 1.0 / (1.0 + sqrt(M[5]));
+      P.se_out[3 * e] = s0; P.se_out[3 * e + 1] = s1; P.se_out[3 * e + 2] = s2;
+      ls[3] = s0; ls[4] = s1; ls[5] = s2;
+      M[0] *= s0 * s0; M[1] *= s0 * s1; M[2] *= s0 * s2; M[3] *= s1 * s1; M[4] *= s1 * s2; M[5] *= s2 * s2;
+      g[0] *= s0; g[1] *= s1; g[2] *= s2;
+      for (int l = l0; l < l1; ++l) {
+        double* R = rec + (size_t)l * FA_REC;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) { R[3 * rr] *= s0; R[3 * rr + 1] *= s1; R[3 * rr + 2] *= s2; }
+      }
+    }
     if (l1 > l0) {  // |x - Plus(x, -g)| of the unscaled gradient (TrustRegionMinimizer::EvaluateGradientAndJacobian)
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -1165,6 +1181,30 @@ __global__ void __launch_bounds__(FA_JAC_THREADS, 4) k_fa_jac(FaParams P) {
   }
   sq = block_sum(sq, red);
   if (tid == 0) P.cost_partial[tile] = sq;
+}
+
+// FA_FIRST: the reduced camera-side results of the unscaled pass, brought to Jacobi-scaled camera columns
+__global__ void k_fa_scale_cams(int64_t nf, const double* __restrict__ sf, double* __restrict__ camacc) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nf * FA_NVC) return;
+  const int64_t c = t / FA_NVC;
+  const int v = (int)(t % FA_NVC);
+  double f;
+  if (v < 21) {  // packed upper (a <= b) of F^T F
+    int a = 0, rem = v;
+    while (rem >= 6 - a) { rem -= 6 - a; ++a; }
+    f = sf[6 * c + a] * sf[6 * c + a + rem];
+  } else {
+    f = sf[6 * c + (v - 21) % 6];   // F^T r, sum of v
+  }
+  camacc[t] *= f;
+}
+__global__ void k_fa_scale_pairs(int ndest, const int32_t* __restrict__ dest_fa, const int32_t* __restrict__ dest_fb,
+                                 const double* __restrict__ sf, double* __restrict__ Pacc) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (int64_t)ndest * 36) return;
+  const int d = (int)(t / 36), v = (int)(t % 36);
+  Pacc[t] *= sf[6 * (int64_t)dest_fa[d] + v / 6] * sf[6 * (int64_t)dest_fb[d] + v % 6];
 }
 
 // first level: one warp per chunk of <= ch partial blocks of one target, lane = value, sequential over the blocks
