@@ -6,19 +6,25 @@
 // Jacobian of an observation (~150 flops) is cheaper than re-reading its 160 bytes, and the Schur complement's
 // pair products are the only heavy arithmetic.  So:
 //
-//   pass 1  k_fa_pass1   per tile of points (a window of ~256 observations, <= 128 points):
-//             A0  the tile's camera tables -> shared memory (SoA, conflict free)
-//             A1  one thread per observation: r, J_e, J_f in registers -> shared memory
+//   pass 1  k_fa_pass1   per tile of points (a window of 480 or 1024 observations, all observations of a point in one
+//                        tile), one CTA per tile:
+//             A0  one 96-byte tile descriptor; the tile's camera tables (32-bit planes), points and work-item entry
+//                 lists -> shared memory by cp.async; first observation / point range / work items -> registers
+//             A1  one thread per observation: r, J_e, J_f in registers -> shared-memory record (22 doubles)
 //             A2  one thread per point: E^T E, E^T r, LM diagonal, 3x3 Cholesky in registers, z = L^-1 E^T r
-//                 (L, 1/diag, z -> shared memory and HBM, 72 B / point); then one thread per observation:
-//                 U_i = L^-1 J_e,i^T, w_i = U_i^T z
-//             B   one thread per WORK ITEM (a fixed list of <= 16 observation pairs of one camera pair, or
-//                 <= 4 observations of one camera, all inside the tile; items sorted by length and dealt
-//                 boustrophedon so that the lanes of a warp run equally long loops): operands from shared
-//                 memory, 36 resp. 33 accumulators in registers, one partial block -> HBM
+//                 (L, 1/diag, z -> shared memory and, as full lines, HBM: 72 B / point); then one thread per
+//                 observation: U_i = L^-1 J_e,i^T, w_i = U_i^T z
+//             B   one thread per WORK ITEM (a fixed list of <= 16 observation pairs of one camera pair, or <= 16
+//                 observations of one camera, all inside the tile; items sorted by length and dealt boustrophedon so
+//                 that the lanes of a warp run equally long loops; entries ordered once so that the lanes of a quarter
+//                 warp gather from different banks): operands from shared memory, 36 resp. 33 accumulators in
+//                 registers, one partial block -> HBM
+//             modes: FA_FULL; FA_FIRST (iteration 0, Jacobi scaling inside the pass); FA_GRAD (cost and gradient only,
+//                 after the last step of a solve); FA_NORMS (column norms only)
 //   reduce  k_reduce_items   fixed-order sum of the partial blocks per camera pair / camera (two levels)
 //   pass 2  k_fa_pass2   per tile: r, J again, back-substitution, Ceres' model cost change, candidate point,
 //                        candidate cost -- one pass instead of four
+//   K1      k_fa_jac     the standalone residual + Jacobian (ba_cuda_eval, generic pipeline) on the same tiles
 //
 // Every list is static (built once per problem with stable radix sorts) and every sum runs in a fixed order:
 // deterministic segmented reduction with shared-memory staging, no floating-point atomics.
