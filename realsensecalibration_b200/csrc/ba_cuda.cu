@@ -795,6 +795,10 @@ int lm_begin(ba_cuda_problem* p, const ba_cuda_options& opt) {
   if (lm_fused(p)) {
     static const bool one_pass = env_int("BA_FA_FIRST", 0, 1, 1) != 0;
     const bool first = opt.jacobi_scaling && opt.max_num_iterations > 0 && one_pass;
+    if (!opt.jacobi_scaling) {  // a previous solve of this problem may have left its scaling behind
+      BA_LAUNCH(p, KT_MISC, k_fill, grid_for(p->S.nf * 6, 256), 256, 0, p->sf.p, p->S.nf * 6, 1.0);
+      BA_LAUNCH(p, KT_MISC, k_fill, grid_for(p->S.ne * 3, 256), 256, 0, p->se.p, p->S.ne * 3, 1.0);
+    }
     if (opt.jacobi_scaling && !first) BA_TRY(fa_linearize(p, opt, true));
     BA_CUDA_TRY(cudaMemcpyAsync(p->scal.p + S_RADIUS, &L.radius, sizeof(double), cudaMemcpyHostToDevice, p->st));
     BA_TRY(fa_linearize(p, opt, false, opt.max_num_iterations <= 0, first));

@@ -337,6 +337,40 @@ def test_max_iterations_and_determinism(gpu):
     assert np.array_equal(xs[0], xs[1])   # no floating-point atomics: bitwise reproducible
 
 
+def test_solve_again_on_the_same_problem_and_without_jacobi_scaling(gpu, oracle):
+    # bench.py restarts solves on one problem (restore + solve_begin): the second solve must repeat the first bit for
+    # bit; then the same problem without Jacobi scaling (the scaling of the earlier solves must not leak into it), and
+    # in steps through solve_begin / solve_iterate with an iteration limit that ends on the cost + gradient only pass
+    pr = S.bal_like(40, 3000, 5, 12, 29)
+    gpu.set_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr)
+    gpu.set_parameters(pr.params)
+    gpu.save_parameters()
+    s1, rows1 = gpu.solve()
+    x1 = gpu.get_parameters()
+    gpu.restore_parameters()
+    s2, rows2 = gpu.solve()
+    assert np.array_equal(x1, gpu.get_parameters()) and [r["cost"] for r in rows1] == [r["cost"] for r in rows2]
+    opt_g, opt_o = cuda.default_options(), oracle.default_options()
+    for o in (opt_g, opt_o):
+        o.jacobi_scaling = 0
+        o.max_num_iterations = 4
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
+    gpu.restore_parameters()
+    s3, rows3 = gpu.solve(opt_g)
+    _check_rows(rows3, rows_o)
+    assert np.abs(gpu.get_parameters() - xo).max() < POSE_ATOL
+    # the same limit reached in two calls of solve_iterate, with scaling
+    opt_g.jacobi_scaling = 1; opt_o.jacobi_scaling = 1
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
+    gpu.restore_parameters()
+    gpu.solve_begin(opt_g)
+    gpu.solve_iterate(2)
+    gpu.solve_iterate(10)
+    s4, rows4 = gpu.solve_end()
+    _check_rows(rows4, rows_o)
+    assert np.abs(gpu.get_parameters() - xo).max() < POSE_ATOL
+
+
 # ---- K5 and the post-BA outputs ------------------------------------------------------------------
 def test_outputs_and_reprojection_hongo(gpu, oracle, golden_dir):
     pb, intr, side, fix0 = H.hongo()
