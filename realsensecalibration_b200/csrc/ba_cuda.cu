@@ -777,7 +777,6 @@ void lm_read_gradient(ba_cuda_problem* p) {
 // TrustRegionMinimizer::IterationZero
 template <int RD, int DE, int GE, int NSLOT>
 int lm_begin(ba_cuda_problem* p, const ba_cuda_options& opt) {
-  const Structure& S = p->S;
   LmState& L = p->lm;
   L = LmState();
   L.opt = opt;

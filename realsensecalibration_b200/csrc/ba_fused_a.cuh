@@ -163,24 +163,31 @@ __global__ void k_fa_pair_fill(const int64_t* __restrict__ e_ptr, const int32_t*
         ++o;
       }
 }
-// the same pairs keyed by (tile, camera slot of i, camera slot of j) in 32 bits (GroupDecode mode 1)
-__global__ void k_fa_pair_fill32(const int64_t* __restrict__ e_ptr, const int32_t* __restrict__ ob_f, int64_t ne, const int64_t* __restrict__ off,
-                                 const int32_t* __restrict__ tile_of_pt, const int64_t* __restrict__ tile_pt_ptr,
-                                 const uint32_t* __restrict__ ob_meta, int sb, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= ne) return;
+// the same pairs keyed by (tile, camera slot of i, camera slot of j) in 32 bits (GroupDecode mode 1); one thread per
+// observation i (a thread per point walks up to 64^2 pairs alone), output in the same order as k_fa_pair_fill
+__global__ void k_fa_pair_fill32(const int64_t* __restrict__ e_ptr, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f,
+                                 int64_t nb, const int64_t* __restrict__ off, const int32_t* __restrict__ tile_of_pt,
+                                 const int64_t* __restrict__ tile_pt_ptr, const uint32_t* __restrict__ ob_meta, int sb,
+                                 uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const int64_t e = ob_e[i];
+  const int64_t b = e_ptr[e], n = e_ptr[e + 1];
+  const int32_t fi = ob_f[i];
   int64_t o = off[e];
+  for (int64_t ii = b; ii < i; ++ii) {   // pairs of the earlier observations of this point
+    const int32_t f = ob_f[ii];
+    for (int64_t j = b; j < n; ++j) o += (f <= ob_f[j]) ? 1 : 0;
+  }
   const uint32_t tile = (uint32_t)tile_of_pt[e];
   const int64_t ob0 = e_ptr[tile_pt_ptr[tile]];
-  for (int64_t i = e_ptr[e]; i < e_ptr[e + 1]; ++i) {
-    const uint32_t si = ob_meta[i] >> 16;
-    for (int64_t j = e_ptr[e]; j < e_ptr[e + 1]; ++j)
-      if (ob_f[i] <= ob_f[j]) {
-        keys[o] = (tile << (2 * sb)) | (si << sb) | (ob_meta[j] >> 16);
-        vals[o] = (int32_t)(i - ob0) | ((int32_t)(j - ob0) << 16);
-        ++o;
-      }
-  }
+  const uint32_t head = (tile << (2 * sb)) | ((ob_meta[i] >> 16) << sb);
+  for (int64_t j = b; j < n; ++j)
+    if (fi <= ob_f[j]) {
+      keys[o] = head | (ob_meta[j] >> 16);
+      vals[o] = (int32_t)(i - ob0) | ((int32_t)(j - ob0) << 16);
+      ++o;
+    }
 }
 __global__ void k_fa_max_diff(int n, const int64_t* __restrict__ ptr, int* __restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -436,15 +443,7 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
 inline int build_fused_a(FusedA& F, const Structure& S, cudaStream_t st) {
   F.ready = false;
   if (S.ne == 0 || S.nb == 0 || S.nslots != 1) return BA_ERR_UNSUPPORTED;
-  int64_t np = 0;
-  {
-    DVec<int64_t> cnt, off;
-    BA_TRY(cnt.alloc(S.ne + 1)); BA_TRY(off.alloc(S.ne + 1));
-    k_pair_count<<<grid_for(S.ne + 1, 128), 128, 0, st>>>(S.e_ptr.p, S.ob_f0.p, S.ne, cnt.p);
-    BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt.p, off.p, (int)(S.ne + 1), st); }));
-    BA_CUDA_TRY(cudaMemcpyAsync(&np, off.p + S.ne, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    BA_CUDA_TRY(cudaStreamSynchronize(st));
-  }
+  const int64_t np = S.npairs - S.nf;   // ordered incidence pairs, counted when the structure was built
   if (np >= (int64_t)INT32_MAX) return BA_ERR_UNSUPPORTED;
   const bool dense_pairs = (double)np >= 4.0 * (double)S.nb;
   int tobs = env_int("BA_FA_TOBS", 64, 1024, dense_pairs ? 1024 : 480);
@@ -519,8 +518,8 @@ inline int build_fused_a_tobs(FusedA& F, const Structure& S, cudaStream_t st, in
     if (S.dh_keys.n && 2 * sb + tb <= 32 && env_int("BA_FA_KEY32", 0, 1, 1)) {   // 32-bit keys (tile, camera slot i, camera slot j)
       DVec<uint32_t> keys;
       BA_TRY(keys.alloc(np));
-      k_fa_pair_fill32<<<grid_for(ne, 128), 128, 0, st>>>(S.e_ptr.p, S.ob_f0.p, ne, off.p, tile_of_pt.p, F.tile_pt_ptr.p, F.ob_meta.p, sb, keys.p,
-                                                          vals.p);
+      k_fa_pair_fill32<<<grid_for(nb, 256), 256, 0, st>>>(S.e_ptr.p, S.ob_e.p, S.ob_f0.p, nb, off.p, tile_of_pt.p, F.tile_pt_ptr.p, F.ob_meta.p,
+                                                          sb, keys.p, vals.p);
       L.lap("pair fill (32-bit keys)");
       D.mode = 1; D.sb = sb; D.key_bits = 2 * sb + tb;
       D.tile_cam_ptr = F.cams.tile_group_ptr.p; D.tile_cams = F.cams.group_target.p;

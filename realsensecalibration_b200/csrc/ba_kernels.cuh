@@ -320,14 +320,10 @@ k_cost_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict
          const int32_t* __restrict__ ob_cam, const double* __restrict__ obs8, const double* __restrict__ tab_f,
          const double* __restrict__ tab_e, double half, double* __restrict__ cost_partial) {
   __shared__ double sm[32];
-  __shared__ __align__(16) double stage[128 * 14];
-  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x;   // (marker observation, corner) records are contiguous: 12 doubles each
-  const int64_t t = t0 + threadIdx.x;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per (marker observation, corner)
   const int64_t o = t >> 2;
   const int corner = (int)(t & 3);
-  const int n_valid = (int)min((int64_t)blockDim.x, 4 * nb - t0);
   double sq = 0.0;
-  double je12[12], jc12[12], jm12[12];
   if (o < nb) {
     const int32_t f0 = ob_f0[o], f1 = ob_f1[o];
     double Tc[TAB], Tt[TAB], Tm[TAB];
