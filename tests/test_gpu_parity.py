@@ -146,6 +146,15 @@ def test_solve_two_cam(gpu, oracle):
     assert H.rel(rows[1]["cost"], rows_o[1]["cost"]) < 1e-7   # cost ~1e-4 of 32 residuals: near cancellation
     assert rows[2]["cost"] < 1e-10                            # exact fit: under-determined problem, cost -> 0
     assert np.abs(x - xo).max() < 1e-6
+    # Test1's tail check (Test1_BundleAdjustment/main.cpp:89-126): the optimised points through the optimised camera
+    err, rms = gpu.reprojection_error()
+    assert 0.0 <= err < 1e-9
+    pts = x[6 * pa.n_cam:].reshape(-1, 3)[pa.pt_idx]
+    rt = x[:6 * pa.n_cam].reshape(-1, 6)
+    img = np.asarray(pa.obs_xy, np.float64).reshape(-1, 2).astype(np.float32)
+    e_g, r_g, rep_g = gpu.project_points_error(pts, pa.cam_idx, rt, np.asarray(intr, np.float64).reshape(-1, 4), img)
+    e_o, r_o, rep_o = oracle.project_points_error(pts, pa.cam_idx, rt, np.asarray(intr, np.float64).reshape(-1, 4), img)
+    assert np.abs(rep_g - rep_o).max() < 1e-9 and np.abs(rep_g - img).max() < 1e-3
 
 
 @pytest.mark.parametrize("name", ["cfg1", "rigA", "balA", "rigB", "rigB_sparse"])
