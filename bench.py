@@ -24,6 +24,7 @@ over-reports.
 --impl reference times that CPU oracle alone, with all host threads, on the same workload/metric.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -41,6 +42,12 @@ ITERS_PER_SOLVE = 5
 
 # name -> (description, model, generator kwargs, rcs solver)
 WORKLOADS = {
+    "hongo": dict(desc="the reference's own fixture Common/Correspondence/hongo/correspondence.txt (Model B, Main_Calibration dispatch): "
+                       "4 cameras x 6 frames x 11 markers, 68 marker observations (272 corner observations)",
+                  kind="hongo", args=()),
+    "cfg1": dict(desc="Test1_BundleAdjustment-shaped synthetic (Model A): 2 cameras (one relative pose), 1 ArUco marker (4 corners) x 50 frames "
+                      "= 200 points, 200 observations",
+                 kind="two_cam", args=(50, 0xBA01)),
     "cfg3a": dict(desc="large rig, Model A reading: 8 cameras x 100 markers x 1000 frames = 400k corner points, 3.2M observations",
                   kind="rig_a", args=(8, 100, 1000, 0xBA03)),
     "cfg4": dict(desc="BAL-shaped synthetic: 1000 cameras x 1M points x 5M observations (window 20)",
@@ -60,9 +67,39 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "cfg5"
 
 
+def host_threads():
+    """Host threads the CPU arm may use: the process' CPU affinity, NOT omp_get_max_threads() -- torch.distributed.run
+    exports OMP_NUM_THREADS=1 to its workers, which would turn "all host cores" into one."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def kernel_source_hash():
+    """Identifies the kernels a profile was taken on (profiles/traffic.json): sha256 over csrc/*.cu*."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "realsensecalibration_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def make_workload(name):
     from realsensecalibration_b200 import synthetic as S
     w = WORKLOADS[name]
+    if w["kind"] == "hongo":
+        from realsensecalibration_b200 import formats as F
+        from tests import helpers as H
+        pb, intr, side, fix0 = H.hongo()
+        counts = np.zeros((pb.n_time, pb.n_cam), np.int32)
+        np.add.at(counts, (pb.time_idx, pb.cam_idx), 1)
+        return S.ModelB(pb.n_cam, pb.n_time, pb.n_marker, pb.time_idx, pb.cam_idx, pb.marker_idx, pb.obs8, np.asarray(intr, np.float64),
+                        pb.params, pb.params, side, counts)
+    if w["kind"] == "two_cam":
+        return S.two_cam_like(*w["args"])
     if w["kind"] == "rig_a":
         return S.marker_rig_a(*w["args"])
     if w["kind"] == "rig_b":
@@ -76,7 +113,7 @@ class Job:
     def __init__(self, name, rank, world):
         from realsensecalibration_b200 import sharding
         self.pr = pr = make_workload(name)
-        self.model = "B" if WORKLOADS[name]["kind"] == "rig_b" else "A"
+        self.model = "B" if WORKLOADS[name]["kind"] in ("rig_b", "hongo") else "A"
         if self.model == "A":
             sh = sharding.shard_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.params, rank, world)
             self.local = (sh.n_pt, sh.cam_idx, sh.pt_idx, np.asarray(sh.obs_xy), sh.params)
@@ -119,8 +156,9 @@ class Job:
             P.set_model_b(pr.n_cam, n_time, pr.n_marker, ti, ci, mi, obs8, pr.intr, pr.marker_side, True)
 
     def oracle_solver(self, O):
+        # the rule BA_RCS_AUTO applies (ba_cuda.cu, kDenseAutoMaxN): dense Cholesky up to dimension 1536, PCG above
         n_kept = self.pr.n_cam if self.model == "A" else self.pr.n_cam + self.pr.n_marker
-        return O.SCHUR_DENSE if 6 * n_kept <= 768 else O.SCHUR_PCG
+        return O.SCHUR_DENSE if 6 * n_kept <= 1536 else O.SCHUR_PCG
 
     def oracle_solve(self, O, opts, threads):
         pr = self.pr
@@ -214,7 +252,28 @@ def oracle_steps(job, k, threads):
         _, s, rows = job.oracle_solve(O, o, threads)
         t += time.perf_counter() - t0
         done += n
-    return t, rows
+    return t, rows, s
+
+
+def config_of(job, name, n_gpus, rcs_solver, rcs_dim):
+    """The `config` object both arms print (the driver compares them key by key)."""
+    ws_mb = job.n_obs * (job.jac_bytes_per_obs if job.model == "B" else 72) / 1e6 / n_gpus
+    l2_note = ("per-step working set of %.0f MB per rank exceeds the 126 MB L2; no explicit flush" % ws_mb if ws_mb > 126 else
+               "per-step working set of %.0f MB per rank fits the 126 MB L2 (this is the reference's own problem size); no flush: the "
+               "real workload is L2 resident too" % ws_mb)
+    return {"workload": name, "description": WORKLOADS[name]["desc"], **job.blocks, "iters_per_solve": ITERS_PER_SOLVE,
+            "parallelism": "%s sharded over %d rank(s), kept blocks (cameras%s) replicated" %
+                           (job.sharded, n_gpus, "" if job.model == "A" else ", markers"),
+            "l2": l2_note, "rcs_solver": {1: "dense_cholesky", 2: "pcg"}.get(int(rcs_solver), "?"), "rcs_dim": int(rcs_dim)}
+
+
+def committed_trace(name):
+    """Oracle rows of the bench solve (ITERS_PER_SOLVE iterations from the bench start), tests/golden/synth_traces.json."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "synth_traces.json")) as f:
+            return json.load(f).get(name)
+    except (OSError, ValueError):
+        return None
 
 
 def main():
@@ -240,16 +299,19 @@ def main():
             return 0
         from oracle import oracle_py as O
         job = Job(a.workload, 0, 1)
-        threads = O.max_threads()
+        threads = host_threads()
         if W > 0:
             oracle_steps(job, min(W, 1), threads)
-        secs, rows = oracle_steps(job, K, threads)
+        secs, rows, osum = oracle_steps(job, K, threads)
         v = K / secs
         print(json.dumps({
             "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": a.workload, "description": wl["desc"], "iters_per_solve": ITERS_PER_SOLVE},
+            "data": "synthetic" if wl["kind"] != "hongo" else "reference fixture (tests/golden)",
+            "config": config_of(job, a.workload, a.gpus, 1 if job.oracle_solver(O) == O.SCHUR_DENSE else 2, osum.rcs_dim),
             "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port",
+                             "threads_from": "CPU affinity of the process, passed to the oracle's num_threads clauses (OMP_NUM_THREADS is ignored)",
+                             "final_cost": float(osum.final_cost),
                              "sample": "full workload, %d LM iterations in solves of %d (problem construction + initial evaluation "
                                        "of each solve included)" % (K, ITERS_PER_SOLVE)},
             "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -358,7 +420,8 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 ent = json.load(f).get(a.workload, {}).get(top["name"])
-            if ent and world == 1:
+            # only a capture of THESE kernels counts: the profile records the hash of the kernel sources it was taken on
+            if ent and world == 1 and ent.get("kernel_source_hash") == kernel_source_hash():
                 traffic, traffic_src = ent["bytes"], ent["source"]
         except (OSError, ValueError):
             pass
@@ -405,29 +468,36 @@ def main():
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import oracle_py as O
-        threads = O.max_threads()
+        threads = host_threads()
         kc = min(K, ITERS_PER_SOLVE)
-        secs, _ = oracle_steps(job, kc, threads)
+        secs, _, osum = oracle_steps(job, kc, threads)
         cpu = {"value": kc / secs, "unit": unit, "cores": threads, "kind": "port",
+               "threads_from": "CPU affinity of the process, passed to the oracle's num_threads clauses",
+               "final_cost": float(osum.final_cost),
                "sample": "full workload, one solve of %d LM iterations (problem construction + initial evaluation included), "
                          "oracle/ba_oracle.cpp with OpenMP" % kc}
+        if kc == ITERS_PER_SOLVE and K >= ITERS_PER_SOLVE:
+            parity = {"oracle_final_cost": float(osum.final_cost), "gpu_final_cost": float(summary.final_cost),
+                      "rel": abs(float(summary.final_cost) - float(osum.final_cost)) / abs(float(osum.final_cost)),
+                      "source": "cpu_baseline leg of this run (same options, same start, %d LM iterations)" % kc}
+    if parity is None and rank == 0 and K >= ITERS_PER_SOLVE and K % ITERS_PER_SOLVE == 0:
+        tr = committed_trace(a.workload)
+        if tr:
+            oc = float(tr["rows"][-1]["cost"])
+            parity = {"oracle_final_cost": oc, "gpu_final_cost": float(summary.final_cost),
+                      "rel": abs(float(summary.final_cost) - oc) / abs(oc), "source": "tests/golden/synth_traces.json (oracle, %s)" % tr["how"]}
 
-    ws_mb = job.n_obs * (job.jac_bytes_per_obs if job.model == "B" else 72) / 1e6 / world
-    l2_note = ("per-step working set of %.0f MB per rank exceeds the 126 MB L2; no explicit flush" % ws_mb if ws_mb > 126 else
-               "per-step working set of %.0f MB per rank fits the 126 MB L2 (this is the reference's own problem size); no flush: the "
-               "real workload is L2 resident too" % ws_mb)
     if rank == 0:
         out = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": a.workload, "description": wl["desc"], **job.blocks,
-                       "iters_per_solve": ITERS_PER_SOLVE,
-                       "parallelism": "%s sharded over %d rank(s), kept blocks (cameras%s) replicated" %
-                                      (job.sharded, world, "" if job.model == "A" else ", markers"),
-                       "l2": l2_note,
-                       "rcs_solver": {1: "dense_cholesky", 2: "pcg"}.get(int(summary.rcs_solver_used), "?"), "rcs_dim": int(summary.rcs_dim)},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic" if wl["kind"] != "hongo" else "reference fixture (tests/golden)",
+            "config": config_of(job, a.workload, world, summary.rcs_solver_used, summary.rcs_dim),
+            "path_used": {0: "generic", 1: "fused_tiles", 2: "fused_strips"}.get(int(summary.path_used), "?"),
+            "parity": parity, "us_per_solve": 1e3 * ms / K * ITERS_PER_SOLVE,
             "jacobian_mobs_per_sec": jac_mobs, "jacobian": jacobian, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "final_cost_last_solve": float(summary.final_cost), "ms_per_step_profiled_pass": ms_prof / K,
             "device_ms": {"jacobian": summary.ms_jacobian, "schur": summary.ms_schur, "rcs_solve": summary.ms_rcs_solve,

@@ -145,7 +145,20 @@ typedef struct ba_cuda_summary {
   double ms_update;            /* K4 back-substitution / model cost / candidate */
   double ms_cost;              /* K5-style cost-only evaluation */
   double ms_collective;        /* NCCL */
+  int32_t path_used;           /* ba_path: which pipeline ran the LM loop */
+  int32_t reserved_;
 } ba_cuda_summary;
+
+/* Which pipeline a solve ran on.  Model B and ba_cuda_eval always use the generic (materialised-Jacobian) pipeline.
+ * Model A uses the fused two-pass pipeline when every point has at most 64 observations: pass 1 on strips of tiles
+ * (register-resident Schur accumulators) when the cameras of a strip fit 64 table slots and no point is seen twice
+ * by one camera, else on single tiles; a problem that fits neither falls back to the generic pipeline (about 3x
+ * slower at BAL scale) -- the reason is printed once on stderr. */
+typedef enum ba_path {
+  BA_PATH_GENERIC = 0,
+  BA_PATH_FUSED_TILES = 1,
+  BA_PATH_FUSED_STRIPS = 2
+} ba_path;
 
 void ba_cuda_options_init(ba_cuda_options* options);
 

@@ -8,6 +8,7 @@ CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
  REASON_MIN_TRUST_REGION_RADIUS, REASON_MAX_ITERATIONS, REASON_TOO_MANY_INVALID_STEPS,
  REASON_INITIAL_EVALUATION_FAILED) = range(8)
 UNIQUE_ID_BYTES = 128
+PATH_GENERIC, PATH_FUSED_TILES, PATH_FUSED_STRIPS = 0, 1, 2
 
 
 class Options(C.Structure):
@@ -92,6 +93,8 @@ class Summary(C.Structure):
         ("ms_update", C.c_double),
         ("ms_cost", C.c_double),
         ("ms_collective", C.c_double),
+        ("path_used", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
     def as_dict(self):

@@ -20,6 +20,7 @@
 #include "ba_structure.cuh"
 #include "ba_rcs.cuh"
 #include "ba_fused_a.cuh"
+#include "ba_strip_a.cuh"
 
 using namespace ba;
 
@@ -117,7 +118,9 @@ struct ba_cuda_problem {
   DVec<double> Sb;           // R.nd * 36 block values | nf * 6 rhs correction (one collective covers both)
   int solver = 0;            // ba_rcs_solver resolved for the current solve
   FusedA FA;                 // Model A: tile structure of the fused two-pass pipeline
-  bool use_fused = false, generic_ws = false;
+  StripA SA;                 // Model A: strip structure of pass 1 (ba_strip_a.cuh); FA then only carries the tiles of pass 2 / k_fa_jac
+  bool use_fused = false, use_strip = false, generic_ws = false;
+  bool smem_attr_set = false;   // the opt-in shared-memory sizes are per device: set once per problem
   DVec<double> fa_part;      // 7 per-tile partial arrays (cost, g2, gmax, mcc, x2, d2, cand)
   int h_pcg_iters = 0;
   double* h_scal = nullptr;  // pinned
@@ -327,7 +330,7 @@ int build_tables(ba_cuda_problem* p, bool candidate) {
 }
 
 FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt);
-int fa_set_smem_attr();
+int fa_set_smem_attr(ba_cuda_problem* p);
 
 // K1 at the current parameters: residuals, scaled Jacobian, sum of squares -> scal[S_COST]
 int run_jacobian(ba_cuda_problem* p) {
@@ -335,7 +338,7 @@ int run_jacobian(ba_cuda_problem* p) {
   BA_TRY(build_tables(p, false));
   int grid;
   if (p->model == 0 && p->use_fused) {  // the tile structure exists: tables staged in shared memory, J leaves as full lines
-    BA_TRY(fa_set_smem_attr());
+    BA_TRY(fa_set_smem_attr(p));
     ba_cuda_options o;
     ba_cuda_options_init(&o);
     const FaParams P = fa_params(p, o);
@@ -535,8 +538,9 @@ FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt) {
   FusedA& F = p->FA;
   const size_t nt = (size_t)F.n_tiles;
   FaParams P;
-  P.tiles = F.tiles.p; P.e_ptr = S.e_ptr.p; P.ob_f = S.ob_f0.p; P.ob_meta = F.ob_meta.p; P.uv = p->uv.p;
-  P.tile_cams = F.cams.group_target.p; P.cap = F.cap;
+  P.tiles = F.tiles.p; P.e_ptr = S.e_ptr.p; P.ob_f = S.ob_f0.p; P.uv = p->uv.p;
+  P.ob_meta = p->use_strip ? p->SA.ob_meta.p : F.ob_meta.p;
+  P.tile_cams = p->use_strip ? p->SA.strip_cams.p : F.cams.group_target.p; P.cap = F.cap;
   P.pts_cap = F.pts_cap; P.tcam = F.tcam; P.tcs = F.tcs; P.pent_cap = F.pent_cap;
   P.pitem_begin = F.pairs.item_begin.p; P.pitem_end = F.pairs.item_end.p; P.pent = F.pairs.ent.p;
   P.citem_begin = F.cams.item_begin.p; P.citem_end = F.cams.item_end.p; P.cent = F.cams.ent.p;
@@ -552,9 +556,8 @@ FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt) {
   return P;
 }
 
-int fa_set_smem_attr() {
-  static bool done = false;
-  if (!done) {
+int fa_set_smem_attr(ba_cuda_problem* p) {
+  if (!p->smem_attr_set) {   // per device (the attribute lives in the context of the device this problem runs on)
     const int kMax = (int)FA_SMEM_MAX;  // dynamic part; the kernels also hold a little static shared memory
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<FA_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<FA_NORMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
@@ -562,7 +565,10 @@ int fa_set_smem_attr() {
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass1<FA_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
     BA_CUDA_TRY(cudaFuncSetAttribute(k_fa_jac, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
-    done = true;
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_sa_pass1<SA_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_sa_pass1<SA_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_sa_pass1<SA_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+    p->smem_attr_set = true;
   }
   return BA_OK;
 }
@@ -594,10 +600,13 @@ int fa_reduce(ba_cuda_problem* p, bool cams, bool pairs) {
 // iteration limit is reached), so only what the row of the progress table needs is computed: cost and gradient.
 // first = true: iteration 0 with Jacobi scaling in one pass (FA_FIRST): the point scaling is applied inside the pass, the
 // camera scaling to the reduced results.
+int sa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool grad_only, bool first);
+
 int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms, bool grad_only = false, bool first = false) {
   const Structure& S = p->S;
   FusedA& F = p->FA;
-  BA_TRY(fa_set_smem_attr());
+  BA_TRY(fa_set_smem_attr(p));
+  if (p->use_strip) return sa_linearize(p, opt, grad_only, first);
   fam_begin(p, F_JAC);
   if (norms || first) {
     BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.nf * 6, 256), 256, 0, p->sf.p, S.nf * 6, 1.0);
@@ -648,6 +657,72 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms, boo
   return BA_OK;
 }
 
+// Strip path (ba_strip_a.cuh): one launch linearises, eliminates and accumulates the Schur products per strip; the
+// partial blocks (one per strip and camera pair / camera) are then summed in a fixed order.
+int sa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool grad_only, bool first) {
+  const Structure& S = p->S;
+  FusedA& F = p->FA;
+  StripA& A = p->SA;
+  fam_begin(p, F_JAC);
+  if (first) {
+    BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.nf * 6, 256), 256, 0, p->sf.p, S.nf * 6, 1.0);
+    BA_LAUNCH(p, KT_MISC, k_fill, grid_for(S.ne * 3, 256), 256, 0, p->se.p, S.ne * 3, 1.0);
+  }
+  BA_TRY(build_tables(p, false));
+  const size_t ns = (size_t)A.n_strips;
+  SaParams P;
+  P.strips = A.strips.p; P.tiles = A.tiles.p; P.strip_cams = A.strip_cams.p; P.slot_out = A.slot_out.p;
+  P.pm = A.pm.p; P.puv = A.puv.p; P.pidx = A.pidx.p; P.ent = A.ent.p; P.seg = A.seg.p;
+  P.segw = A.segw; P.cap_pos = A.cap_pos; P.pts_cap = A.pts_cap; P.tcs = A.tcs; P.ent_cap = A.ent_cap; P.pidx_cap = A.pidx_cap;
+  P.xe = p->xe.p; P.se = p->se.p; P.tab_f = p->tab_f.p; P.radius = p->scal.p + S_RADIUS;
+  P.min_diag = opt.min_lm_diagonal; P.max_diag = opt.max_lm_diagonal;
+  P.partP = A.partP.p; P.partC = A.partC.p; P.n_pout = A.n_pout;
+  P.Lz = F.Lz.p; P.se_out = p->se.p;
+  P.cost_partial = p->fa_part.p; P.g2_partial = p->fa_part.p + ns; P.gmax_partial = p->fa_part.p + 2 * ns;
+  P.status = p->status.p;
+  BA_CUDA_TRY(cudaMemsetAsync(p->status.p, 0, sizeof(int), p->st));
+  if (first) BA_LAUNCH(p, KT_FA_P1, (k_sa_pass1<SA_FIRST>), A.n_strips, SA_NT, A.smem(), P);
+  else if (grad_only) BA_LAUNCH(p, KT_FA_P1L, (k_sa_pass1<SA_GRAD>), A.n_strips, SA_NT, A.smem(), P);
+  else BA_LAUNCH(p, KT_FA_P1, (k_sa_pass1<SA_FULL>), A.n_strips, SA_NT, A.smem(), P);
+  {
+    FoldJob J = {{P.cost_partial, P.g2_partial, P.gmax_partial, nullptr}, {S_COST, S_G2E, S_GMAXE, 0}, {0, 0, 1, 0}};
+    BA_LAUNCH(p, KT_FOLD, k_fold_multi, 3, 1024, 0, J, A.n_strips, p->scal.p);
+  }
+  fam_end(p, F_JAC);
+  fam_begin(p, F_SCHUR);
+  if (A.red_ch_c.n > 0)
+    BA_LAUNCH(p, KT_FA_RED, (k_reduce_items<SA_NVC>), grid_for(A.red_ch_c.n, 4), 128, 0, A.red_ch_c.n, A.red_ch_c.ch, A.red_ch_c.seg.p,
+              A.red_ch_c.begin.p, A.tgt_ptr_c.p, A.red_items_c.p, A.partC.p, A.red1C.p);
+  BA_LAUNCH(p, KT_FA_RED, (k_reduce_final<SA_NVC>), grid_for(S.nf, 4), 128, 0, (int)S.nf, A.red_ch_c.seg_first.p, A.red1C.p, F.camacc.p);
+  if (!grad_only || first) {
+    if (A.red_ch_p.n > 0)
+      BA_LAUNCH(p, KT_FA_RED, (k_reduce_items<36>), grid_for(A.red_ch_p.n, 4), 128, 0, A.red_ch_p.n, A.red_ch_p.ch, A.red_ch_p.seg.p,
+                A.red_ch_p.begin.p, A.tgt_ptr_p.p, A.red_items_p.p, A.partP.p, A.red1P.p);
+    BA_LAUNCH(p, KT_FA_RED, (k_reduce_final<36>), grid_for(S.ndest, 4), 128, 0, S.ndest, A.red_ch_p.seg_first.p, A.red1P.p, p->Pacc.p);
+  }
+  BA_CUDA_TRY(cudaGetLastError());
+  fam_end(p, F_SCHUR);
+  if (p->world > 1) {  // camera sums and the shard-local gradient scalars in one collective
+    fam_begin(p, F_COLL);
+    BA_TRY(allreduce_with_grad_tail(p, F.camacc.p, (size_t)S.nf * SA_NVC));
+    fam_end(p, F_COLL);
+  }
+  if (first) {  // camera scaling from the (global) unscaled column norms, then everything reduced so far into scaled columns
+    BA_LAUNCH(p, KT_MISC, k_sa_jacobi_scale, grid_for(S.nf * 6, 256), 256, 0, S.nf, F.camacc.p, p->sf.p);
+    BA_LAUNCH(p, KT_MISC, k_sa_scale_cams, grid_for(S.nf * SA_NVC, 256), 256, 0, S.nf, p->sf.p, F.camacc.p);
+    BA_LAUNCH(p, KT_MISC, k_fa_scale_pairs, grid_for((int64_t)S.ndest * 36, 256), 256, 0, S.ndest, S.dest_fa.p, S.dest_fb.p, p->sf.p, p->Pacc.p);
+    BA_TRY(build_tables(p, false));   // pass 2 linearises with the scaled camera columns
+  }
+  const int gf = (int)grid_for(S.nf * 6, 256);
+  BA_LAUNCH(p, KT_GRADNORM, (k_gradient_norm<6, SA_NVC, 21>), gf, 256, 0, S.nf, p->f_act_ptr.p, p->xf.p, p->sf.p, F.camacc.p, p->bp0.p, p->bp1.p);
+  {
+    FoldJob J = {{p->bp0.p, p->bp1.p, nullptr, nullptr}, {S_GMAXF, S_G2F, 0, 0}, {1, 0, 0, 0}};
+    BA_LAUNCH(p, KT_FOLD, k_fold_multi, 2, 1024, 0, J, gf, p->scal.p);
+  }
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
 // RCS assembly + solve + (pass 2) back-substitution, model cost change, candidate and its cost
 int fa_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   const Structure& S = p->S;
@@ -673,16 +748,24 @@ int fa_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   }
   fam_begin(p, F_SOLVE);
   if (pcg) {
-    BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_bsr, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->R.diag.p, F.camacc.p, FA_NVC, F.camacc.p + 27, FA_NVC,
-              radius, opt.min_lm_diagonal, opt.max_lm_diagonal, p->Sb.p, p->rhs.p);
+    if (p->use_strip)
+      BA_LAUNCH(p, KT_ASSEMBLE, k_sa_diag_rhs_bsr, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->R.diag.p, F.camacc.p, radius, opt.min_lm_diagonal,
+                opt.max_lm_diagonal, p->Sb.p, p->rhs.p);
+    else
+      BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_bsr, grid_for(S.nf * 6, 128), 128, 0, S.nf, p->R.diag.p, F.camacc.p, FA_NVC, F.camacc.p + 27, FA_NVC,
+                radius, opt.min_lm_diagonal, opt.max_lm_diagonal, p->Sb.p, p->rhs.p);
     {
       LaunchScope scope(p, KT_RCS);
       BA_TRY(launch_pcg(p->pcg, p->R, p->Sb.p, p->rhs.p, p->yf.p, p->status.p, opt, p->st));
     }
     BA_CUDA_TRY(cudaMemcpyAsync(&p->h_pcg_iters, p->pcg.iters.p, sizeof(int), cudaMemcpyDeviceToHost, p->st));
   } else {
-    BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_dense, grid_for(S.nf * 6, 128), 128, 0, S.nf, F.camacc.p, FA_NVC, F.camacc.p + 27, FA_NVC, radius,
-              opt.min_lm_diagonal, opt.max_lm_diagonal, n, p->Sd.p, p->rhs.p);
+    if (p->use_strip)
+      BA_LAUNCH(p, KT_ASSEMBLE, k_sa_diag_rhs_dense, grid_for(S.nf * 6, 128), 128, 0, S.nf, F.camacc.p, radius, opt.min_lm_diagonal,
+                opt.max_lm_diagonal, n, p->Sd.p, p->rhs.p);
+    else
+      BA_LAUNCH(p, KT_ASSEMBLE, k_diag_rhs_dense, grid_for(S.nf * 6, 128), 128, 0, S.nf, F.camacc.p, FA_NVC, F.camacc.p + 27, FA_NVC, radius,
+                opt.min_lm_diagonal, opt.max_lm_diagonal, n, p->Sd.p, p->rhs.p);
     LaunchScope scope(p, KT_RCS);
     BA_TRY(dense_solve(p, n));
   }
@@ -787,13 +870,14 @@ int lm_begin(ba_cuda_problem* p, const ba_cuda_options& opt) {
   for (int f = 0; f < F_COUNT; ++f) { p->fam_ms[f] = 0.0; p->fam_open[f] = false; }
   L.Z.num_residuals = p->nb_global * RD;
   L.Z.rcs_solver_used = p->solver;
+  L.Z.path_used = lm_fused(p) ? (p->use_strip ? BA_PATH_FUSED_STRIPS : BA_PATH_FUSED_TILES) : BA_PATH_GENERIC;
   L.radius = opt.initial_trust_region_radius;
   L.decrease_factor = 2.0;
   L.began = true;
   const double iter_t0 = now_s();
   if (lm_fused(p)) {
     static const bool one_pass = env_int("BA_FA_FIRST", 0, 1, 1) != 0;
-    const bool first = opt.jacobi_scaling && opt.max_num_iterations > 0 && one_pass;
+    const bool first = opt.jacobi_scaling && (p->use_strip || (opt.max_num_iterations > 0 && one_pass));   // the strip path always scales in one pass
     if (!opt.jacobi_scaling) {  // a previous solve of this problem may have left its scaling behind
       BA_LAUNCH(p, KT_MISC, k_fill, grid_for(p->S.nf * 6, 256), 256, 0, p->sf.p, p->S.nf * 6, 1.0);
       BA_LAUNCH(p, KT_MISC, k_fill, grid_for(p->S.ne * 3, 256), 256, 0, p->se.p, p->S.ne * 3, 1.0);
@@ -986,8 +1070,9 @@ int alloc_workspace(ba_cuda_problem* p, int RD, int DE) {
   const int64_t n = p->n_rcs();
   cudaStream_t st = p->st;
   BA_TRY(p->xf.alloc_zero(S.nf * 6, st)); BA_TRY(p->xf_c.alloc_zero(S.nf * 6, st));
-  BA_TRY(p->xe.alloc_zero(S.ne * DE, st)); BA_TRY(p->xe_c.alloc_zero(S.ne * DE, st));
-  BA_TRY(p->sf.alloc(S.nf * 6)); BA_TRY(p->se.alloc(S.ne * DE));
+  // + 2: the strip pass reads a tile's points as a 16-byte aligned slice (one double before / after the tile's own)
+  BA_TRY(p->xe.alloc_zero(S.ne * DE + 2, st)); BA_TRY(p->xe_c.alloc_zero(S.ne * DE + 2, st));
+  BA_TRY(p->sf.alloc(S.nf * 6)); BA_TRY(p->se.alloc(S.ne * DE + 2));
   k_fill<<<grid_for(S.nf * 6, 256), 256, 0, st>>>(p->sf.p, S.nf * 6, 1.0);
   k_fill<<<grid_for(S.ne * DE, 256), 256, 0, st>>>(p->se.p, S.ne * DE, 1.0);
   BA_TRY(p->tab_f.alloc(S.nf * TAB)); BA_TRY(p->tabc_f.alloc(S.nf * TAB));
@@ -1126,7 +1211,9 @@ void reset_problem(ba_cuda_problem* p) {
   new (&p->R) RcsPattern();
   p->FA.~FusedA();
   new (&p->FA) FusedA();
-  p->use_fused = false; p->generic_ws = false;
+  p->SA.~StripA();
+  new (&p->SA) StripA();
+  p->use_fused = false; p->use_strip = false; p->generic_ws = false;
   p->lm.began = false;
   p->S.~Structure();
   new (&p->S) Structure();
@@ -1302,12 +1389,27 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
   p->h_perm.clear();  // fetched on demand by ba_cuda_eval
   BA_TRY(alloc_workspace(p, 2, 3));
   T.lap("alloc_workspace");
-  {  // fused two-pass pipeline when every point has <= FA_KMAX observations, else the generic one
-    const int rc = build_fused_a(p->FA, p->S, p->st);
+  {  // fused two-pass pipeline when every point has <= FA_KMAX observations, else the generic one; pass 1 on strips of
+     // tiles when the cameras of a strip fit (ba_strip_a.cuh), else on single tiles (ba_fused_a.cuh)
+    int rc = build_strip_a(p->SA, p->FA, p->S, p->uv.p, p->st);
     if (rc != BA_OK && rc != BA_ERR_UNSUPPORTED) return rc;
+    p->use_strip = rc == BA_OK;
+    if (!p->use_strip) {
+      p->SA.~StripA();
+      new (&p->SA) StripA();
+      rc = build_fused_a(p->FA, p->S, p->st);
+      if (rc != BA_OK && rc != BA_ERR_UNSUPPORTED) return rc;
+    }
     p->use_fused = rc == BA_OK;
-    if (p->use_fused) BA_TRY(p->fa_part.alloc((size_t)7 * p->FA.n_tiles));
-    else BA_TRY(ensure_generic_workspace(p));
+    if (p->use_fused) {
+      BA_TRY(p->fa_part.alloc((size_t)7 * p->FA.n_tiles));
+    } else {
+      static std::atomic<bool> warned{false};
+      if (n_obs > 0 && !warned.exchange(true))
+        std::fprintf(stderr, "[ba_cuda] Model A problem does not fit the fused pipeline (a point with more than %d observations); "
+                             "using the generic materialised-Jacobian pipeline (ba_cuda_summary.path_used = BA_PATH_GENERIC)\n", FA_KMAX);
+      BA_TRY(ensure_generic_workspace(p));
+    }
   }
   T.lap("build_fused_a");
   const int rc = build_activity(p);

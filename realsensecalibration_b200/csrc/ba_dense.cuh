@@ -73,20 +73,14 @@ k_chol_solve(int n, double* __restrict__ S, const double* __restrict__ rhs, doub
 inline int launch_chol_solve(int n, double* S, const double* rhs, double* y, int* status, cudaStream_t st) {
   if (n <= CHOL_SMEM_MAX_N) {
     const size_t smem = ((size_t)n * n + 2 * (size_t)n) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-      BA_CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
-    }
+    // the opt-in limit belongs to the device the stream runs on; setting it costs microseconds, a process-wide
+    // "done" flag would leave a second GPU without it
+    if (smem > 48 * 1024) BA_CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     k_chol_solve<true><<<1, 1024, smem, st>>>(n, S, rhs, y, status);
   } else {
     const size_t smem = 2 * (size_t)n * sizeof(double);
     if (smem > 200 * 1024) return fail(BA_ERR_UNSUPPORTED, "dense RCS of dimension %d is too large for the single-CTA solver", n);
-    static bool attr_set2 = false;
-    if (!attr_set2) {
-      BA_CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set2 = true;
-    }
+    if (smem > 48 * 1024) BA_CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     k_chol_solve<false><<<1, 1024, smem, st>>>(n, S, rhs, y, status);
   }
   BA_CUDA_TRY(cudaGetLastError());

@@ -441,3 +441,100 @@ def test_error_paths(gpu):
     with pytest.raises(cuda.BAError):
         P2.solve()
     P2.close()
+
+
+# ---- strip pass 1 (ba_strip_a.cuh): register-resident Schur accumulators across a strip of tiles -------------------
+def _solve_a(gpu, pr, opt=None):
+    gpu.set_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr)
+    gpu.set_parameters(pr.params)
+    s, rows = gpu.solve(opt)
+    return s, rows, gpu.get_parameters()
+
+
+class _Env:
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("name", ["balA", "rigA", "chain"])
+def test_strip_path_matches_tile_path_and_oracle(gpu, oracle, name):
+    # the same problem through pass 1 on strips (default) and on single tiles (BA_SA=0, the first-generation kernel):
+    # same rows as the oracle, and as each other
+    pr = {"balA": lambda: S.bal_like(60, 5000, 6, 16, 13, variable_degree=True), "rigA": lambda: S.marker_rig_a(8, 10, 20, 12),
+          "chain": lambda: S.bal_like(300, 20000, 5, 20, 17)}[name]()
+    opt_g, opt_o = cuda.default_options(), oracle.default_options()
+    for o in (opt_g, opt_o):
+        o.max_num_iterations = 6
+        o.rcs_solver = abi.RCS_DENSE_CHOLESKY
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
+    s1, rows1, x1 = _solve_a(gpu, pr, opt_g)
+    assert s1.path_used == abi.PATH_FUSED_STRIPS
+    with _Env(BA_SA=0):
+        s0, rows0, x0 = _solve_a(gpu, pr, opt_g)
+    assert s0.path_used == abi.PATH_FUSED_TILES
+    _check_rows(rows1, rows_o)
+    _check_rows(rows0, rows_o)
+    assert np.abs(x1 - xo).max() < POSE_ATOL and np.abs(x1 - x0).max() < POSE_ATOL
+
+
+@pytest.mark.parametrize("geom", [dict(BA_SA_TOBS=128, BA_SA_L=3), dict(BA_SA_TOBS=256, BA_SA_L=1), dict(BA_SA_TOBS=1024, BA_SA_L=16)])
+def test_strip_geometries(gpu, oracle, geom):
+    # many short tiles per strip (the bulk-copy prefetch runs across tile boundaries), one tile per strip, one strip
+    pr = S.bal_like(60, 5000, 6, 16, 13, variable_degree=True)
+    opt_g, opt_o = cuda.default_options(), oracle.default_options()
+    for o in (opt_g, opt_o):
+        o.max_num_iterations = 5
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
+    with _Env(**geom):
+        s, rows, x = _solve_a(gpu, pr, opt_g)
+    assert s.path_used == abi.PATH_FUSED_STRIPS
+    _check_rows(rows, rows_o)
+    assert np.abs(x - xo).max() < POSE_ATOL
+
+
+def test_strip_flush_warp_and_split_owners(gpu, oracle):
+    # window of 40 cameras: a strip couples up to ~55 x 54 / 2 camera pairs, more than the 512 owner threads, so the
+    # lightest pairs of every strip go through the flush warp (one partial block per tile); the rig has 28 pairs and
+    # 8 cameras for 512 threads, so every pair and camera is split over many owner threads
+    pr = S.bal_like(120, 6000, 8, 40, 41)
+    opt_g, opt_o = cuda.default_options(), oracle.default_options()
+    for o in (opt_g, opt_o):
+        o.max_num_iterations = 5
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
+    s, rows, x = _solve_a(gpu, pr, opt_g)
+    assert s.path_used == abi.PATH_FUSED_STRIPS
+    _check_rows(rows, rows_o)
+    assert np.abs(x - xo).max() < POSE_ATOL
+    pr = S.marker_rig_a(8, 40, 60, 19)
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
+    s, rows, x = _solve_a(gpu, pr, opt_g)
+    assert s.path_used == abi.PATH_FUSED_STRIPS
+    _check_rows(rows, rows_o)
+    assert np.abs(x - xo).max() < POSE_ATOL
+
+
+def test_point_seen_twice_by_one_camera_takes_the_tile_path(gpu, oracle):
+    # a duplicated observation (same point, same camera): the strip plan has no owner for a (camera, camera) pair of
+    # two different observations, so the problem runs on single tiles and still matches the oracle
+    pr = S.bal_like(30, 2000, 5, 12, 5)
+    ci = np.concatenate([pr.cam_idx, pr.cam_idx[:1]]); pi = np.concatenate([pr.pt_idx, pr.pt_idx[:1]])
+    ob = np.concatenate([pr.obs_xy, pr.obs_xy[:1] + 0.25])
+    gpu.set_model_a(pr.n_cam, pr.n_pt, ci, pi, ob, pr.intr)
+    gpu.set_parameters(pr.params)
+    s, rows = gpu.solve()
+    x = gpu.get_parameters()
+    assert s.path_used == abi.PATH_FUSED_TILES
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, ci, pi, ob, pr.intr, pr.params)
+    _check_rows(rows, rows_o)
+    assert np.abs(x - xo).max() < POSE_ATOL
