@@ -39,9 +39,9 @@ for r, (off, src, ins) in zip(data, lines):
     for h in stalls: a[h[6:]] += num(r, h)
 tot = sum(a["samples"] for a in agg.values())
 print("samples", tot, "wavefronts", sum(a["wf"] for a in agg.values()), "ideal", sum(a["ideal"] for a in agg.values()), "inst", sum(a["inst"] for a in agg.values()))
-srcfile = open(os.path.join(os.path.dirname(so), "ba_fused_a.cuh")).read().split("\n")
+srcfiles = {f: open(os.path.join(os.path.dirname(so), f)).read().split("\n") for f in os.listdir(os.path.dirname(so)) if f.endswith((".cuh", ".cu"))}
 for src, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:topn]:
     st = sorted(((a[h[6:]], h[6:]) for h in stalls), reverse=True)[:3]
-    text = srcfile[src[1] - 1].strip()[:90] if src[0] == "ba_fused_a.cuh" and 0 < src[1] <= len(srcfile) else ""
+    text = srcfiles[src[0]][src[1] - 1].strip()[:90] if src[0] in srcfiles and 0 < src[1] <= len(srcfiles[src[0]]) else ""
     print("%5.1f%% wf %9d/%9d inst %8d %-34s %s:%d  %s" % (100 * a["samples"] / tot, a["wf"], a["ideal"], a["inst"],
           " ".join("%s:%d" % (n, v) for v, n in st if v > 0), src[0], src[1], text))

@@ -1,5 +1,5 @@
-"""Tile-geometry sweep of the fused Model A passes on one workload (tuning aid, not a bench):
-   python scratch/sweep.py cfg4 "480,256,128 480,128,128 320,160,128"   (tobs,threads,threads2)"""
+"""Sweep of the tuning switches of the fused Model A passes on one workload (tuning aid, not a bench):
+   python profiles/tools/sweep.py cfg5 "SA_TOBS=768,SA_L=8 SA_TOBS=576,SA_L=12 SA=0,FA_TOBS=1024"   (BA_<name>=<value>)"""
 import os, sys, time, json
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -16,8 +16,8 @@ P = cuda.Problem(0)
 P.set_stream(stream.cuda_stream)
 for combo in combos:
     for k in list(os.environ):
-        if k.startswith("BA_FA_"): del os.environ[k]
-    for k, v in combo.items(): os.environ["BA_FA_" + k] = v
+        if k.startswith("BA_FA_") or k.startswith("BA_SA"): del os.environ[k]
+    for k, v in combo.items(): os.environ["BA_" + k] = v
     t_build = time.perf_counter()
     job.set_model(P)
     P.set_parameters(job.params)

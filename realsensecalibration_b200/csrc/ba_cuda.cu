@@ -680,10 +680,27 @@ int sa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool grad_only,
   P.Lz = F.Lz.p; P.se_out = p->se.p;
   P.cost_partial = p->fa_part.p; P.g2_partial = p->fa_part.p + ns; P.gmax_partial = p->fa_part.p + 2 * ns;
   P.status = p->status.p;
+  P.dbg = env_int("BA_SA_DBG", 0, 7, 0);
+  static DVec<unsigned long long>* clk = nullptr;   // BA_SA_CLOCKS=1: cycles of thread 0 per phase of pass 1, printed per launch (tuning aid)
+  P.clocks = nullptr;
+  if (env_int("BA_SA_CLOCKS", 0, 1, 0)) {
+    if (!clk) { clk = new DVec<unsigned long long>(); BA_TRY(clk->alloc(8)); }
+    BA_CUDA_TRY(cudaMemsetAsync(clk->p, 0, 8 * sizeof(unsigned long long), p->st));
+    P.clocks = clk->p;
+  }
   BA_CUDA_TRY(cudaMemsetAsync(p->status.p, 0, sizeof(int), p->st));
   if (first) BA_LAUNCH(p, KT_FA_P1, (k_sa_pass1<SA_FIRST>), A.n_strips, SA_NT, A.smem(), P);
   else if (grad_only) BA_LAUNCH(p, KT_FA_P1L, (k_sa_pass1<SA_GRAD>), A.n_strips, SA_NT, A.smem(), P);
   else BA_LAUNCH(p, KT_FA_P1, (k_sa_pass1<SA_FULL>), A.n_strips, SA_NT, A.smem(), P);
+  if (P.clocks) {
+    unsigned long long h[8];
+    BA_CUDA_TRY(cudaMemcpyAsync(h, P.clocks, sizeof(h), cudaMemcpyDeviceToHost, p->st));
+    BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+    const double n = (double)A.n_tiles;
+    std::fprintf(stderr, "[ba_cuda clocks] pass 1, cycles per tile as thread 0 sees them: top %.0f | wait inputs %.0f | A1 + barrier %.0f | A2 (own) %.0f | "
+                         "wait entries + barrier %.0f | B (own) %.0f | barrier after B %.0f | sum %.0f\n", h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n,
+                 h[5] / n, h[6] / n, (h[0] + h[1] + h[2] + h[3] + h[4] + h[5] + h[6]) / n);
+  }
   {
     FoldJob J = {{P.cost_partial, P.g2_partial, P.gmax_partial, nullptr}, {S_COST, S_G2E, S_GMAXE, 0}, {0, 0, 1, 0}};
     BA_LAUNCH(p, KT_FOLD, k_fold_multi, 3, 1024, 0, J, A.n_strips, p->scal.p);

@@ -478,7 +478,8 @@ def test_strip_path_matches_tile_path_and_oracle(gpu, oracle, name):
         o.max_num_iterations = 6
         o.rcs_solver = abi.RCS_DENSE_CHOLESKY
     xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
-    s1, rows1, x1 = _solve_a(gpu, pr, opt_g)
+    with _Env(BA_SA=2):   # 2 = strips whenever the problem fits (the default also asks for >= 4 pair products per observation)
+        s1, rows1, x1 = _solve_a(gpu, pr, opt_g)
     assert s1.path_used == abi.PATH_FUSED_STRIPS
     with _Env(BA_SA=0):
         s0, rows0, x0 = _solve_a(gpu, pr, opt_g)
@@ -496,7 +497,7 @@ def test_strip_geometries(gpu, oracle, geom):
     for o in (opt_g, opt_o):
         o.max_num_iterations = 5
     xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
-    with _Env(**geom):
+    with _Env(BA_SA=2, **geom):
         s, rows, x = _solve_a(gpu, pr, opt_g)
     assert s.path_used == abi.PATH_FUSED_STRIPS
     _check_rows(rows, rows_o)
@@ -512,13 +513,14 @@ def test_strip_flush_warp_and_split_owners(gpu, oracle):
     for o in (opt_g, opt_o):
         o.max_num_iterations = 5
     xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
-    s, rows, x = _solve_a(gpu, pr, opt_g)
+    with _Env(BA_SA=2):
+        s, rows, x = _solve_a(gpu, pr, opt_g)
     assert s.path_used == abi.PATH_FUSED_STRIPS
     _check_rows(rows, rows_o)
     assert np.abs(x - xo).max() < POSE_ATOL
     pr = S.marker_rig_a(8, 40, 60, 19)
     xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
-    s, rows, x = _solve_a(gpu, pr, opt_g)
+    s, rows, x = _solve_a(gpu, pr, opt_g)   # 4.5 pair products per observation: strips by default
     assert s.path_used == abi.PATH_FUSED_STRIPS
     _check_rows(rows, rows_o)
     assert np.abs(x - xo).max() < POSE_ATOL
