@@ -1,7 +1,7 @@
 // main_calibration_ba.cpp -- the bundle-adjustment stage of Main_Calibration's main() (main.cpp:35-43) on the
 // files the earlier stages leave behind, driven through the source-compatible host classes:
 //   BAManager(intrinsics, dist) -> StartBA() -> Write() -> ReprojectionCheck::Reproject(...)
-// usage: ba_main_calibration <Common dir> <output dir> [test1]
+// usage: ba_main_calibration <Common dir> <output dir> [test1 | test2]
 // Everything before it in the reference's main() (image capture, ArUco detection, solvePnP) is out of scope; the
 // detected corners Reproject needs are the observations stored in correspondence.txt.
 #include <cstdio>
@@ -40,11 +40,17 @@ int main(int argc, char** argv) {
                 pb.mutable_cameras()[4], pb.mutable_cameras()[5]);
     return 0;
   }
-  const std::vector<std::string> serials(SERIAL_NUMBERS, SERIAL_NUMBERS + CAMERAS);
+  // test2: Test2_BundleAdjustment/main.cpp:53-152 on its fixture -- two cameras, marker 0 free (two-functor dispatch), R<i>
+  // written as the rotation vector, and the check reading that file back (the configuration the committed outputs were made
+  // with: 48 mm markers, cameras 819612072493 / 825312072048)
+  const bool test2 = argc > 3 && std::string(argv[3]) == "test2";
+  const std::vector<std::string> serials = test2 ? std::vector<std::string>{"819612072493", "825312072048"}
+                                                 : std::vector<std::string>(SERIAL_NUMBERS, SERIAL_NUMBERS + CAMERAS);
   std::map<std::string, cv::Mat> camera_intrinsics_map, dist_coeffs_map;
   if (!GetIntrinsics(common, serials, camera_intrinsics_map, dist_coeffs_map)) return 1;
   BAManager::Config cfg;
-  cfg.correspondence_path = common + "/Correspondence/hongo/correspondence.txt";
+  cfg.correspondence_path = common + (test2 ? "/Correspondence/test2/correspondence_test.txt" : "/Correspondence/hongo/correspondence.txt");
+  if (test2) { cfg.serial_numbers = serials; cfg.marker_side = 0.048; cfg.fix_base_marker = false; cfg.rotation_as_rvec = true; }
   cfg.transform_xml_path = out + "/Camera_Transform.xml";
   cfg.extrinsics_dir = out;
   cfg.point3d_path = out + "/point3d.txt";

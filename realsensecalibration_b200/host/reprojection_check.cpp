@@ -50,6 +50,10 @@ ReprojectionCheck::Result ReprojectionCheck::Reproject(const std::string& point3
       }
   std::fclose(fptr);
   if (!ok) { std::cerr << "point3d.txt and the detected image points do not match" << std::endl; return res; }
+  // R<i> is a 3x3 matrix in Main_Calibration's file (bundle_adjustment_manager.cpp:130) and the 3x1 rvec in Test2's
+  // (Test2_BundleAdjustment/main.cpp:128); the rvec form goes to the entry point that runs cv::Rodrigues on the device
+  std::vector<double> rvt(6 * (size_t)num_cameras);
+  int n_mat = 0, n_rvec = 0;
   for (int c = 0; c < num_cameras; c++) {
     const cv::Mat& R = xf["R" + std::to_string(c)];
     const cv::Mat& t = xf["t" + std::to_string(c)];
@@ -57,18 +61,31 @@ ReprojectionCheck::Result ReprojectionCheck::Reproject(const std::string& point3
     if (R.empty() || t.empty() || it == camera_intrinsics_map.end()) { std::cerr << "missing transform / intrinsics of camera " << c << std::endl; return res; }
     if (R.rows * R.cols == 9) {
       for (int k = 0; k < 9; k++) rot[9 * (size_t)c + k] = R.at<double>(k / 3, k % 3);
-    } else {  // Test2 stores the rvec (Test2_BundleAdjustment/main.cpp:128): let the library do Rodrigues
+      ++n_mat;
+    } else if (R.rows * R.cols == 3) {
+      for (int k = 0; k < 3; k++) rvt[6 * (size_t)c + k] = R.rows == 3 ? R.at<double>(k, 0) : R.at<double>(0, k);
+      ++n_rvec;
+    } else {
+      std::cerr << "R" << c << " in " << transform_xml_path << " is neither a 3x3 matrix nor a 3x1 rotation vector" << std::endl;
       return res;
     }
-    for (int k = 0; k < 3; k++) tv[3 * (size_t)c + k] = t.at<double>(k, 0);
+    if (t.rows * t.cols != 3) { std::cerr << "t" << c << " in " << transform_xml_path << " is not a 3-vector" << std::endl; return res; }
+    for (int k = 0; k < 3; k++) {
+      tv[3 * (size_t)c + k] = t.rows == 3 ? t.at<double>(k, 0) : t.at<double>(0, k);
+      rvt[6 * (size_t)c + 3 + k] = tv[3 * (size_t)c + k];
+    }
     const cv::Mat& K = it->second;
     intr[4 * c + 0] = K.at<double>(0, 0); intr[4 * c + 1] = K.at<double>(1, 1); intr[4 * c + 2] = K.at<double>(0, 2); intr[4 * c + 3] = K.at<double>(1, 2);
   }
+  if (n_mat != 0 && n_rvec != 0) { std::cerr << transform_xml_path << " mixes rotation matrices and rotation vectors" << std::endl; return res; }
   ba_cuda_problem* p = nullptr;
   double err = 0.0, rms = 0.0;
   const long long n = (long long)cam.size();
-  ok = ba_cuda_create(&p, device) == BA_OK &&
-       ba_cuda_project_points_error_rt(p, n, xyz.data(), cam.data(), num_cameras, rot.data(), tv.data(), intr.data(), img.data(), &err, nullptr, nullptr) == BA_OK;
+  ok = ba_cuda_create(&p, device) == BA_OK;
+  if (ok && n_rvec == 0)
+    ok = ba_cuda_project_points_error_rt(p, n, xyz.data(), cam.data(), num_cameras, rot.data(), tv.data(), intr.data(), img.data(), &err, nullptr, nullptr) == BA_OK;
+  else if (ok)
+    ok = ba_cuda_project_points_error(p, n, xyz.data(), cam.data(), num_cameras, rvt.data(), intr.data(), img.data(), &err, nullptr, nullptr) == BA_OK;
   if (!ok) std::cerr << "ReprojectionCheck: " << ba_cuda_last_error() << std::endl;
   ba_cuda_destroy(p);
   if (!ok) return res;

@@ -31,3 +31,24 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 
 def test_reference_arm_other_ranks_exit_without_output():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_reference_arm_ignores_omp_num_threads_of_torchrun():
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU arm must still use every core it may run
+    # on (round 1: the 30 M-observation reference run was single threaded under torchrun and timed out at N = 2, 4, 8)
+    lines = _run({"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    want = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == want
+    assert d["cpu_baseline"]["final_cost"] > 0
+
+
+def test_both_arms_print_the_same_config_keys():
+    # the driver compares the two `config` objects: same keys (values are checked on the GPU box where both arms run)
+    import bench
+    ref = json.loads(_run()[0])["config"]
+    job = bench.Job("small", 0, 1)
+    ours = bench.config_of(job, "small", 1, 2, 300)
+    assert sorted(ref) == sorted(ours)
+    assert all(ref[k] == ours[k] for k in ref if k not in ("rcs_solver", "rcs_dim"))

@@ -309,6 +309,30 @@ def test_pcg_matches_oracle_pcg(gpu, oracle, name):
     assert rows[1]["linear_solver_iterations"] == rows_o[1]["linear_solver_iterations"] > 0
 
 
+@pytest.mark.parametrize("name,k", [("balA", 10), ("balA", 40), ("chain", 15)])
+def test_pcg_with_a_fixed_iteration_count_is_the_same_method(gpu, oracle, name, k):
+    # pcg_min_iterations = pcg_max_iterations = k on both sides takes the stopping rule out of the comparison: the k-step
+    # CG iterate is a fixed polynomial of S and the right-hand side, so the LM rows must agree to round-off level
+    pr = S.bal_like(60, 5000, 6, 16, 13, variable_degree=True) if name == "balA" else S.bal_like(300, 20000, 5, 20, 17)
+    opt_g, opt_o = cuda.default_options(), oracle.default_options()
+    for o in (opt_g, opt_o):
+        o.rcs_solver = abi.RCS_PCG
+        o.max_num_iterations = 6
+        o.pcg_min_iterations = k
+        o.pcg_max_iterations = k
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o,
+                                          linear_solver=oracle.SCHUR_PCG, n_threads=4)
+    for env in (dict(BA_SA=2), dict(BA_SA=0)):   # pass 1 on strips and on single tiles
+        with _Env(**env):
+            s, rows, x = _solve_a(gpu, pr, opt_g)
+        assert s.rcs_solver_used == abi.RCS_PCG and len(rows) == len(rows_o)
+        for a, b in zip(rows, rows_o):
+            assert a["linear_solver_iterations"] == b["linear_solver_iterations"] == (k if a["iteration"] > 0 else 0)
+            assert a["step_is_successful"] == b["step_is_successful"]
+            assert H.rel(a["cost"], b["cost"]) <= 1e-9, (env, a, b)
+        assert np.abs(x - xo).max() < POSE_ATOL
+
+
 def test_pcg_converges_to_the_dense_solution(gpu):
     # with a tight CG tolerance the PCG step is the exact step: the LM trace must then equal the dense-Cholesky trace
     pr = S.bal_like(40, 3000, 6, 12, 3)
@@ -538,5 +562,20 @@ def test_point_seen_twice_by_one_camera_takes_the_tile_path(gpu, oracle):
     x = gpu.get_parameters()
     assert s.path_used == abi.PATH_FUSED_TILES
     xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, ci, pi, ob, pr.intr, pr.params)
+    _check_rows(rows, rows_o)
+    assert np.abs(x - xo).max() < POSE_ATOL
+
+
+def test_point_with_more_than_64_observations_takes_the_generic_pipeline(gpu, oracle, capfd):
+    # the fused passes keep the observations of a point in one tile and cap them at 64 (FA_KMAX); a denser point sends the
+    # whole problem through the generic materialised-Jacobian pipeline: said so in summary.path_used (and once on stderr),
+    # and still the oracle's rows
+    pr = S.bal_like(70, 300, 66, 70, 33)
+    opt_g, opt_o = cuda.default_options(), oracle.default_options()
+    for o in (opt_g, opt_o):
+        o.max_num_iterations = 5
+    xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
+    s, rows, x = _solve_a(gpu, pr, opt_g)
+    assert s.path_used == abi.PATH_GENERIC
     _check_rows(rows, rows_o)
     assert np.abs(x - xo).max() < POSE_ATOL

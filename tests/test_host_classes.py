@@ -84,3 +84,23 @@ def test_test1_program_path(tmp_path, oracle):
     xo, so, _ = oracle.solve_model_a(pa.n_cam, pa.n_pt, pa.cam_idx, pa.pt_idx, pa.obs_xy, intr, pa.params)
     cam = np.array([float(v) for v in m.group(4).split()])
     assert np.abs(cam - xo[:6]).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_test2_flow_writes_rvecs_and_reprojects_from_them(tmp_path, oracle):
+    # Test2_BundleAdjustment's flow: two-functor dispatch, Camera_Transform.xml with R<i> as the 3x1 rotation vector
+    # (Test2_BundleAdjustment/main.cpp:128), then ReprojectionCheck::Reproject reading that file back
+    r = subprocess.run([EXE, H.GOLDEN, str(tmp_path), "test2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = F.load_opencv_xml(os.path.join(tmp_path, "Camera_Transform.xml"))
+    gold = F.load_opencv_xml(os.path.join(H.GOLDEN, "Correspondence", "test2", "Camera_Transform.xml"))
+    for c in range(2):
+        assert got["R%d" % c].shape == (3, 1)
+        assert np.abs(got["R%d" % c] - gold["R%d" % c]).max() < 1e-10 and np.abs(got["t%d" % c] - gold["t%d" % c]).max() < 1e-10
+    m = re.search(r"summary: iterations (\d+) initial (\S+) final (\S+) reprojection (\S+) rms (\S+)", r.stdout)
+    assert m and int(m.group(1)) == 4
+    # the check projects the 6-digit points of point3d.txt with float image points: close to the final cost of the solve
+    pb, intr, side, fix0 = H.test2()
+    xo, so, rows_o = oracle.solve_model_b(pb, intr, side, fix0)
+    assert H.rel(float(m.group(3)), so.final_cost) < 1e-10
+    assert abs(float(m.group(4)) - so.final_cost) < 0.02 * so.final_cost
