@@ -21,6 +21,7 @@
 #include "ba_rcs.cuh"
 #include "ba_fused_a.cuh"
 #include "ba_strip_a.cuh"
+#include "ba_exchange.cuh"
 
 using namespace ba;
 
@@ -121,6 +122,7 @@ struct ba_cuda_problem {
   StripA SA;                 // Model A: strip structure of pass 1 (ba_strip_a.cuh); FA then only carries the tiles of pass 2 / k_fa_jac
   bool use_fused = false, use_strip = false, generic_ws = false;
   bool smem_attr_set = false;   // the opt-in shared-memory sizes are per device: set once per problem
+  SparseExchange SX;            // multi-GPU, fused Model A + PCG: all-gather of the ranks' own blocks instead of an all-reduce of all
   DVec<double> fa_part;      // 7 per-tile partial arrays (cost, g2, gmax, mcc, x2, d2, cand)
   int h_pcg_iters = 0;
   double* h_scal = nullptr;  // pinned
@@ -331,6 +333,8 @@ int build_tables(ba_cuda_problem* p, bool candidate) {
 
 FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt);
 int fa_set_smem_attr(ba_cuda_problem* p);
+int sx_exchange(ba_cuda_problem* p, double* camacc, bool with_blocks);
+bool sx_active(const ba_cuda_problem* p);
 
 // K1 at the current parameters: residuals, scaled Jacobian, sum of squares -> scal[S_COST]
 int run_jacobian(ba_cuda_problem* p) {
@@ -636,14 +640,18 @@ int fa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool norms, boo
   fam_begin(p, F_SCHUR);
   BA_TRY(fa_reduce(p, true, !grad_only));
   fam_end(p, F_SCHUR);
-  if (p->world > 1) {  // camera sums and the shard-local gradient scalars in one collective
+  const bool sx = sx_active(p);
+  if (p->world > 1) {  // camera sums and the shard-local gradient scalars in one collective; the partial blocks too when they travel sparse
     fam_begin(p, F_COLL);
-    BA_TRY(allreduce_with_grad_tail(p, F.camacc.p, (size_t)S.nf * FA_NVC));
+    if (sx) BA_TRY(sx_exchange(p, F.camacc.p, !grad_only));
+    else BA_TRY(allreduce_with_grad_tail(p, F.camacc.p, (size_t)S.nf * FA_NVC));
     fam_end(p, F_COLL);
   }
   if (first) {  // camera scaling from the (global) unscaled column norms, then everything reduced so far into scaled columns
     BA_LAUNCH(p, KT_MISC, (k_jacobi_scale<6, FA_NVC>), grid_for(S.nf * 6, 256), 256, 0, S.nf, F.camacc.p, p->sf.p);
     BA_LAUNCH(p, KT_MISC, k_fa_scale_cams, grid_for(S.nf * FA_NVC, 256), 256, 0, S.nf, p->sf.p, F.camacc.p);
+    if (sx) BA_LAUNCH(p, KT_MISC, k_sx_scale_blocks, grid_for((int64_t)p->R.nd * 36, 256), 256, 0, p->R.nd, p->R.fa.p, p->R.fb.p, p->sf.p, p->Sb.p);
+    else
     BA_LAUNCH(p, KT_MISC, k_fa_scale_pairs, grid_for((int64_t)S.ndest * 36, 256), 256, 0, S.ndest, S.dest_fa.p, S.dest_fb.p, p->sf.p, p->Pacc.p);
     BA_TRY(build_tables(p, false));   // pass 2 linearises with the scaled camera columns
   }
@@ -719,14 +727,18 @@ int sa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool grad_only,
   }
   BA_CUDA_TRY(cudaGetLastError());
   fam_end(p, F_SCHUR);
-  if (p->world > 1) {  // camera sums and the shard-local gradient scalars in one collective
+  const bool sx = sx_active(p);
+  if (p->world > 1) {  // camera sums and the shard-local gradient scalars in one collective; the partial blocks too when they travel sparse
     fam_begin(p, F_COLL);
-    BA_TRY(allreduce_with_grad_tail(p, F.camacc.p, (size_t)S.nf * SA_NVC));
+    if (sx) BA_TRY(sx_exchange(p, F.camacc.p, !grad_only || first));
+    else BA_TRY(allreduce_with_grad_tail(p, F.camacc.p, (size_t)S.nf * SA_NVC));
     fam_end(p, F_COLL);
   }
   if (first) {  // camera scaling from the (global) unscaled column norms, then everything reduced so far into scaled columns
     BA_LAUNCH(p, KT_MISC, k_sa_jacobi_scale, grid_for(S.nf * 6, 256), 256, 0, S.nf, F.camacc.p, p->sf.p);
     BA_LAUNCH(p, KT_MISC, k_sa_scale_cams, grid_for(S.nf * SA_NVC, 256), 256, 0, S.nf, p->sf.p, F.camacc.p);
+    if (sx) BA_LAUNCH(p, KT_MISC, k_sx_scale_blocks, grid_for((int64_t)p->R.nd * 36, 256), 256, 0, p->R.nd, p->R.fa.p, p->R.fb.p, p->sf.p, p->Sb.p);
+    else
     BA_LAUNCH(p, KT_MISC, k_fa_scale_pairs, grid_for((int64_t)S.ndest * 36, 256), 256, 0, S.ndest, S.dest_fa.p, S.dest_fb.p, p->sf.p, p->Pacc.p);
     BA_TRY(build_tables(p, false));   // pass 2 linearises with the scaled camera columns
   }
@@ -747,8 +759,10 @@ int fa_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   const int64_t n = p->n_rcs();
   const double* radius = p->scal.p + S_RADIUS;
   const bool pcg = p->solver == BA_RCS_PCG;
+  const bool sx = sx_active(p);   // the block values were exchanged and assembled with the linearisation (sx_exchange)
   fam_begin(p, F_SCHUR);
-  if (pcg) {
+  if (pcg && sx) {
+  } else if (pcg) {
     if (p->world > 1) BA_CUDA_TRY(cudaMemsetAsync(p->Sb.p, 0, p->Sb.bytes(), p->st));
     BA_LAUNCH(p, KT_ASSEMBLE, k_assemble_bsr, grid_for((int64_t)S.ndest * 36, 256), 256, 0, S.ndest, p->R.l2g.p, p->Pacc.p, nullptr, p->Sb.p);
   } else {
@@ -757,7 +771,7 @@ int fa_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
               nullptr, n, p->Sd.p);
   }
   fam_end(p, F_SCHUR);
-  if (p->world > 1) {
+  if (p->world > 1 && !(pcg && sx)) {
     fam_begin(p, F_COLL);
     if (pcg) BA_TRY(allreduce(p, p->Sb.p, (size_t)p->R.nd * 36, kNcclSum));
     else BA_TRY(allreduce(p, p->Sd.p, n * n, kNcclSum));
@@ -808,6 +822,90 @@ int fa_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
 
 bool lm_fused(const ba_cuda_problem* p) { return p->model == 0 && p->use_fused && !p->lm.opt.force_generic_path; }
 
+// Sparse exchange (ba_exchange.cuh): which of my blocks / cameras travel, every rank's lists, the inverse maps.
+int sx_prepare(ba_cuda_problem* p) {
+  const Structure& S = p->S;
+  SparseExchange& X = p->SX;
+  X.on = false; X.world = p->world; X.nvc = p->use_strip ? SA_NVC : FA_NVC;
+  if (!nccl().AllGather || !env_int("BA_SX", 0, 1, 1)) return BA_OK;
+  cudaStream_t st = p->st;
+  const int64_t nf = S.nf, nd = p->R.nd;
+  // my cameras, my sent blocks
+  DVec<int32_t> cflag, cpos, dflag, dpos;
+  BA_TRY(cflag.alloc(nf + 1)); BA_TRY(cpos.alloc(nf + 1)); BA_TRY(dflag.alloc((size_t)S.ndest + 1)); BA_TRY(dpos.alloc((size_t)S.ndest + 1));
+  BA_CUDA_TRY(cudaMemsetAsync(cflag.p, 0, sizeof(int32_t) * (nf + 1), st));
+  BA_CUDA_TRY(cudaMemsetAsync(dflag.p, 0, sizeof(int32_t) * ((size_t)S.ndest + 1), st));
+  k_sx_flags<<<grid_for(nf, 256), 256, 0, st>>>(S.fobs_ptr.p, nf, cflag.p);
+  k_sx_send_flags<<<grid_for(S.ndest, 256), 256, 0, st>>>(S.ndest, S.dest_fa.p, S.dest_fb.p, cflag.p, dflag.p);
+  BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cflag.p, cpos.p, (int)(nf + 1), st); }));
+  BA_TRY(cub_call([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, dflag.p, dpos.p, S.ndest + 1, st); }));
+  int32_t h2[2] = {0, 0};
+  BA_CUDA_TRY(cudaMemcpyAsync(&h2[0], cpos.p + nf, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  BA_CUDA_TRY(cudaMemcpyAsync(&h2[1], dpos.p + S.ndest, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  BA_CUDA_TRY(cudaStreamSynchronize(st));
+  X.nc_local = h2[0]; X.n_send = h2[1];
+  BA_TRY(X.my_cams.alloc((size_t)X.nc_local)); BA_TRY(X.send_d.alloc((size_t)X.n_send));
+  k_sx_compact<<<grid_for(nf, 256), 256, 0, st>>>(cflag.p, cpos.p, nf, X.my_cams.p);
+  k_sx_compact<<<grid_for(S.ndest, 256), 256, 0, st>>>(dflag.p, dpos.p, S.ndest, X.send_d.p);
+  // every rank's counts
+  DVec<int64_t> cnt;
+  BA_TRY(cnt.alloc(2 * (size_t)p->world));
+  const int64_t mine[2] = {X.n_send, X.nc_local};
+  BA_CUDA_TRY(cudaMemcpyAsync(cnt.p + 2 * p->rank, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  int rc = nccl().AllGather(cnt.p + 2 * p->rank, cnt.p, 2, kNcclInt64, p->comm, st);
+  if (rc != 0) return fail(BA_ERR_NCCL, "ncclAllGather failed (%d)", rc);
+  std::vector<int64_t> h(2 * (size_t)p->world);
+  BA_CUDA_TRY(cudaMemcpyAsync(h.data(), cnt.p, sizeof(int64_t) * h.size(), cudaMemcpyDeviceToHost, st));
+  BA_CUDA_TRY(cudaStreamSynchronize(st));
+  int64_t sum_nd = 0, max_nd = 1, max_nc = 1;
+  for (int r = 0; r < p->world; ++r) { sum_nd += h[2 * r]; max_nd = std::max(max_nd, h[2 * r]); max_nc = std::max(max_nc, h[2 * r + 1]); }
+  // worth it only while the shards' lists are (nearly) disjoint: the all-reduce moves ~2 nd blocks per rank, the all-gather sum_nd
+  if ((double)max_nd * p->world > 1.5 * (double)nd) return BA_OK;
+  X.max_nd = (int)max_nd; X.max_nc = (int)max_nc;
+  X.slot = (size_t)max_nd * 36 + (size_t)max_nc * X.nvc + 4;
+  // every rank's lists -> inverse maps
+  DVec<int32_t> lists_d, lists_c;
+  BA_TRY(lists_d.alloc((size_t)max_nd * p->world)); BA_TRY(lists_c.alloc((size_t)max_nc * p->world));
+  BA_CUDA_TRY(cudaMemsetAsync(lists_d.p, 0xff, sizeof(int32_t) * (size_t)max_nd * p->world, st));
+  BA_CUDA_TRY(cudaMemsetAsync(lists_c.p, 0xff, sizeof(int32_t) * (size_t)max_nc * p->world, st));
+  k_sx_gather_l2g<<<grid_for(X.n_send, 256), 256, 0, st>>>(X.n_send, X.send_d.p, p->R.l2g.p, lists_d.p + (size_t)max_nd * p->rank);
+  BA_CUDA_TRY(cudaMemcpyAsync(lists_c.p + (size_t)max_nc * p->rank, X.my_cams.p, sizeof(int32_t) * X.nc_local, cudaMemcpyDeviceToDevice, st));
+  rc = nccl().AllGather(lists_d.p + (size_t)max_nd * p->rank, lists_d.p, (size_t)max_nd, kNcclInt32, p->comm, st);
+  if (rc == 0) rc = nccl().AllGather(lists_c.p + (size_t)max_nc * p->rank, lists_c.p, (size_t)max_nc, kNcclInt32, p->comm, st);
+  if (rc != 0) return fail(BA_ERR_NCCL, "ncclAllGather failed (%d)", rc);
+  BA_TRY(X.inv_d.alloc((size_t)nd * p->world)); BA_TRY(X.inv_c.alloc((size_t)nf * p->world));
+  BA_CUDA_TRY(cudaMemsetAsync(X.inv_d.p, 0xff, sizeof(int32_t) * (size_t)nd * p->world, st));
+  BA_CUDA_TRY(cudaMemsetAsync(X.inv_c.p, 0xff, sizeof(int32_t) * (size_t)nf * p->world, st));
+  k_sx_invert<<<grid_for((int64_t)max_nd * p->world, 256), 256, 0, st>>>(p->world, (int)max_nd, lists_d.p, nd, X.inv_d.p);
+  k_sx_invert<<<grid_for((int64_t)max_nc * p->world, 256), 256, 0, st>>>(p->world, (int)max_nc, lists_c.p, nf, X.inv_c.p);
+  BA_TRY(X.buf.alloc(X.slot * p->world));
+  BA_CUDA_TRY(cudaStreamSynchronize(st));
+  BA_CUDA_TRY(cudaGetLastError());
+  X.on = true;
+  return BA_OK;
+}
+
+// After a linearisation: my blocks, my cameras' sums and my scalars to every rank in one all-gather; the pieces are then
+// added in rank order: the global camera sums, the shard scalars and (with_blocks) the block values of the reduced system.
+int sx_exchange(ba_cuda_problem* p, double* camacc, bool with_blocks) {
+  const Structure& S = p->S;
+  SparseExchange& X = p->SX;
+  double* slot = X.buf.p + X.slot * p->rank;
+  const int64_t n = (int64_t)X.slot;
+  k_sx_pack<<<grid_for(n, 256), 256, 0, p->st>>>(X.n_send, X.send_d.p, p->Pacc.p, X.nc_local, X.my_cams.p, X.nvc, camacc, p->scal.p, S_COST, S_G2E,
+                                              S_GMAXE, X.max_nd, X.max_nc, slot);
+  const int rc = nccl().AllGather(slot, X.buf.p, X.slot, kNcclFloat64, p->comm, p->st);
+  if (rc != 0) return fail(BA_ERR_NCCL, "ncclAllGather failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
+  const size_t cam_off = (size_t)X.max_nd * 36;
+  k_sx_unpack_cams<<<grid_for(S.nf * X.nvc, 256), 256, 0, p->st>>>(p->world, S.nf, X.nvc, X.slot, cam_off, X.buf.p, X.inv_c.p, camacc);
+  k_sx_unpack_scalars<<<1, 32, 0, p->st>>>(p->world, X.slot, cam_off + (size_t)X.max_nc * X.nvc, X.buf.p, p->scal.p, S_COST, S_G2E, S_GMAXE);
+  if (with_blocks)
+    k_sx_unpack_blocks<<<grid_for((int64_t)p->R.nd * 36, 256), 256, 0, p->st>>>(p->world, p->R.nd, X.slot, X.buf.p, X.inv_d.p, p->Sb.p);
+  BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+bool sx_active(const ba_cuda_problem* p) { return p->world > 1 && p->SX.on && p->solver == BA_RCS_PCG; }
+
 // Resolves options.rcs_solver for this problem and makes sure the matching RCS storage exists.
 // BA_RCS_AUTO: dense Cholesky while the system is rig sized (Ceres DENSE_SCHUR, what the reference asks for),
 // block-sparse PCG above.
@@ -832,6 +930,7 @@ int prepare_solver(ba_cuda_problem* p, const ba_cuda_options& opt) {
       BA_CUDA_TRY(cudaGetLastError());
       BA_TRY(p->Sb.alloc((size_t)p->R.nd * 36 + (size_t)S.nf * 6));
       BA_TRY(pcg_prepare(p->pcg, S.nf, p->device));
+      if (p->world > 1 && p->model == 0 && p->use_fused) BA_TRY(sx_prepare(p));
       BA_CUDA_TRY(cudaStreamSynchronize(p->st));
     }
   }
@@ -1034,6 +1133,20 @@ __global__ void k_count_active(const int64_t* __restrict__ ptr, int64_t n, unsig
   if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(count, (unsigned long long)__popc(ballot));
 }
 
+// minimum of a flag over the ranks (no-op on one GPU)
+int agree_min(ba_cuda_problem* p, int* flag) {
+  if (p->world <= 1) return BA_OK;
+  DVec<int32_t> d;
+  const int32_t h = *flag;
+  BA_TRY(d.upload(&h, 1, p->st));
+  BA_TRY(allreduce(p, d.p, 1, 3 /* ncclMin */, kNcclInt32));
+  int32_t out = 0;
+  BA_CUDA_TRY(cudaMemcpyAsync(&out, d.p, sizeof(out), cudaMemcpyDeviceToHost, p->st));
+  BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  *flag = out;
+  return BA_OK;
+}
+
 // number of active blocks (from the CSR pointers)
 int count_active(ba_cuda_problem* p, const DVec<int64_t>& ptr, int64_t nblk, int64_t* out) {
   DVec<unsigned long long> cnt;
@@ -1230,6 +1343,8 @@ void reset_problem(ba_cuda_problem* p) {
   new (&p->FA) FusedA();
   p->SA.~StripA();
   new (&p->SA) StripA();
+  p->SX.~SparseExchange();
+  new (&p->SX) SparseExchange();
   p->use_fused = false; p->use_strip = false; p->generic_ws = false;
   p->lm.began = false;
   p->S.~Structure();
@@ -1408,16 +1523,23 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
   T.lap("alloc_workspace");
   {  // fused two-pass pipeline when every point has <= FA_KMAX observations, else the generic one; pass 1 on strips of
      // tiles when the cameras of a strip fit (ba_strip_a.cuh), else on single tiles (ba_fused_a.cuh)
+    // Multi-GPU: every rank must run the same pipeline (the collectives carry its buffers: a shard on strips and a shard
+    // on tiles would disagree on their layout), so the choice is the minimum over the ranks of what each shard fits.
     int rc = build_strip_a(p->SA, p->FA, p->S, p->uv.p, p->st);
     if (rc != BA_OK && rc != BA_ERR_UNSUPPORTED) return rc;
-    p->use_strip = rc == BA_OK;
+    int ok = rc == BA_OK ? 1 : 0;
+    BA_TRY(agree_min(p, &ok));
+    p->use_strip = ok != 0;
     if (!p->use_strip) {
       p->SA.~StripA();
       new (&p->SA) StripA();
       rc = build_fused_a(p->FA, p->S, p->st);
       if (rc != BA_OK && rc != BA_ERR_UNSUPPORTED) return rc;
+      ok = rc == BA_OK ? 1 : 0;
+      BA_TRY(agree_min(p, &ok));
+      if (!ok) { p->FA.~FusedA(); new (&p->FA) FusedA(); }
     }
-    p->use_fused = rc == BA_OK;
+    p->use_fused = ok != 0;
     if (p->use_fused) {
       BA_TRY(p->fa_part.alloc((size_t)7 * p->FA.n_tiles));
     } else {

@@ -31,9 +31,10 @@ k_chol_solve(int n, double* __restrict__ S, const double* __restrict__ rhs, doub
     for (int i = j + tid; i < n; i += nt) {
       const double v = (i == j) ? l : A[(size_t)i * n + j] * inv;
       col[i] = v;
-      A[(size_t)i * n + j] = v;
+      if (i != j) A[(size_t)i * n + j] = v;   // the diagonal is still being read as d by slower warps (racecheck, round 2)
     }
     __syncthreads();
+    if (tid == 0) A[(size_t)j * n + j] = l;
     for (int i = j + 1 + warp; i < n; i += nw) {
       const double ci = col[i];
       double* row = A + (size_t)i * n;

@@ -234,12 +234,14 @@ struct SaPlanParams {
   int n_strips, L, n_tiles, ncs_cap, nf_cap;
   int cam_budget;               // camera threads per strip (whole warps): the observations of a camera are dealt over its threads
   int by_count;                 // owner slots in order of descending pair count instead of (diagonal, first camera)
+  int balance;                  // deal the warps over the four SM sub-partitions by load
   const int64_t* tile_pt_ptr; const int64_t* e_ptr; const uint8_t* ob_slot; const int64_t* strip_cam_ptr;
   uint32_t* dslot;              // [n_strips][ncs_cap^2]: rank | copies << 12, or 1 << 31 | flush index; ~0 = no such pair
   uint32_t* cslot;              // [n_strips][ncs_cap]: owner threads of the camera; 0 = camera without observations
   uint16_t* cthr;               // [n_strips][ncs_cap][SA_CM_MAX]: the owner threads (layer major: consecutive cameras in consecutive lanes)
   uint32_t* slot_out;           // [n_strips][SA_NT]
   uint16_t* slot_dest;          // [n_strips][SA_NT]: sa << 8 | sb (pair), s (camera)
+  uint16_t* thr_of;             // [n_strips][SA_NT]: logical owner slot -> thread (warps dealt over the four SM sub-partitions by load)
   uint16_t* fl_dest;            // [n_strips][nf_cap]
   int32_t* counts;              // [n_strips][8]: npout, ncout, nflush, flush_t0, npp, -, cbase, ok
 };
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(256) k_sa_strip_plan(SaPlanParams P) {
   __syncthreads();
   __shared__ uint16_t item_ab[SA_NT], sort_ab[SA_NT];
   __shared__ int item_cnt[SA_NT], sort_cnt[SA_NT];
-  __shared__ int sh[8];
+  __shared__ int sh[9];
   __shared__ double shd[1];
   __shared__ uint8_t cm[SA_NCS_MAX];
   if (tid == 0) {
@@ -361,6 +363,13 @@ __global__ void __launch_bounds__(256) k_sa_strip_plan(SaPlanParams P) {
         ++nfl;
       }
     }
+  {
+    int fw_pairs = 0;   // pair products of the flush list per strip
+    for (int a = 0; a < ncs; ++a)
+      for (int b = a + 1; b < ncs; ++b)
+        if (dslot[a * P.ncs_cap + b] != 0xffffffffu && (dslot[a * P.ncs_cap + b] & 0x80000000u)) fw_pairs += cnt[a * SA_NCS_MAX + b];
+    sh[8] = fw_pairs;
+  }
   sh[0] = npp; sh[1] = nfl; sh[2] = ok ? 1 : 0; sh[3] = flush ? 1 : 0; sh[4] = mcap; sh[5] = flush_t0; sh[6] = n_cslots; sh[7] = n_cact;
   shd[0] = target;
   }
@@ -416,36 +425,74 @@ __global__ void __launch_bounds__(256) k_sa_strip_plan(SaPlanParams P) {
       dslot[a * P.ncs_cap + b] = (uint32_t)r | ((uint32_t)m << 12);
       pdest[r] = sort_ab[r];
       pcopies[r] = (uint8_t)m;
+      item_cnt[r] = sort_cnt[r] / m;   // pairs per owner thread of this pair (item_cnt is free now)
     }
   }
   __syncthreads();
   if (tid != 0) return;
+  auto item_w = [&](int r) { return item_cnt[r]; };
   const bool ok = sh[2] != 0, flush = sh[3] != 0;
-  const int nfl = sh[1], flush_t0 = sh[5], n_cslots = sh[6], n_cact = sh[7];
+  const int nfl = sh[1], n_cslots = sh[6], n_cact = sh[7];
+  int flush_t0 = sh[5];
   const int cbase = SA_NT - n_cslots;
   int npout = 0, ncout = 0;
+  uint16_t* thr_of = P.thr_of + (size_t)strip * SA_NT;
   if (ok) {
+    // logical slots: pairs (layer major), the flush warp, the camera threads at the top; lw[] = load of every logical warp
+    // (steps of its fullest lane per strip; a camera observation costs about 1.3 pair products)
+    float lw[SA_NT / 32];
+    for (int w = 0; w < SA_NT / 32; ++w) lw[w] = 0.f;
     int max_m = 0;
     for (int r = 0; r < npp; ++r) max_m = max(max_m, (int)pcopies[r]);
     for (int j = 0; j < max_m; ++j)
       for (int r = 0; r < npp; ++r)
         if (pcopies[r] > j) {
           const int t = j * npp + r;
-          sout[t] = ((uint32_t)SA_TYPE_PAIR << 30) | (uint32_t)npout++;
-          sdest[t] = pdest[r];
+          sort_ab[t] = pdest[r];                                  // logical slot -> destination (sort_ab / sort_cnt are free now)
+          sort_cnt[t] = (SA_TYPE_PAIR << 30) | npout++;
+          lw[t >> 5] = fmaxf(lw[t >> 5], (float)item_w(r));
         }
-    if (flush)
-      for (int u = 0; u < 32; ++u) sout[flush_t0 + u] = ((uint32_t)SA_TYPE_FLUSH << 30) | (uint32_t)u;
-    uint16_t* cthr = P.cthr + (size_t)strip * P.ncs_cap * SA_CM_MAX;
+    if (flush) {
+      for (int u = 0; u < 32; ++u) { sort_ab[flush_t0 + u] = 0; sort_cnt[flush_t0 + u] = (SA_TYPE_FLUSH << 30) | u; }
+      lw[flush_t0 >> 5] = 1.5f * (float)sh[8] / 32.f + 4.f * ((nfl + 31) / 32);
+    }
     int t = cbase;
     for (int j = 0; j < SA_CM_MAX; ++j)
       for (int s = 0; s < ncs; ++s)
         if (cm[s] > j) {
-          cthr[s * SA_CM_MAX + j] = (uint16_t)t;
-          sout[t] = ((uint32_t)SA_TYPE_CAM << 30) | (uint32_t)ncout++;
-          sdest[t] = (uint16_t)s;
+          sort_ab[t] = (uint16_t)s;
+          sort_cnt[t] = (SA_TYPE_CAM << 30) | ncout++;
+          lw[t >> 5] = fmaxf(lw[t >> 5], 1.3f * (float)camobs[s] / (float)cm[s]);
           ++t;
         }
+    // warps -> sub-partitions (warp w runs on sub-partition w % 4): heaviest first into the lightest bin with room
+    int phys[SA_NT / 32], fill[4] = {0, 0, 0, 0};
+    float bin[4] = {0.f, 0.f, 0.f, 0.f};
+    bool done[SA_NT / 32];
+    for (int w = 0; w < SA_NT / 32; ++w) done[w] = false;
+    for (int it = 0; it < SA_NT / 32; ++it) {
+      int best = -1;
+      for (int w = 0; w < SA_NT / 32; ++w)
+        if (!done[w] && (best < 0 || lw[w] > lw[best])) best = w;
+      int b = -1;
+      for (int k = 0; k < 4; ++k)
+        if (fill[k] < SA_NT / 128 && (b < 0 || bin[k] < bin[b])) b = k;
+      done[best] = true;
+      phys[best] = P.balance ? b + 4 * fill[b] : best;
+      ++fill[b]; bin[b] += lw[best];
+    }
+    for (int l = 0; l < SA_NT; ++l) {
+      const int ph = 32 * phys[l >> 5] + (l & 31);
+      thr_of[l] = (uint16_t)ph;
+      sout[ph] = (uint32_t)sort_cnt[l];
+      sdest[ph] = sort_ab[l];
+    }
+    if (flush) flush_t0 = 32 * phys[flush_t0 >> 5];
+    uint16_t* cthr = P.cthr + (size_t)strip * P.ncs_cap * SA_CM_MAX;
+    t = cbase;
+    for (int j = 0; j < SA_CM_MAX; ++j)
+      for (int s = 0; s < ncs; ++s)
+        if (cm[s] > j) { cthr[s * SA_CM_MAX + j] = thr_of[t]; ++t; }
     for (int s = 0; s < ncs; ++s) cslot[s] = cm[s];
   }
   int32_t* out = P.counts + 8 * (size_t)strip;
@@ -478,15 +525,16 @@ struct SaEntParams {
   int L, ncs_cap, segw, stage_cap;
   const SaTile* tiles; const SaStrip* strips;
   const int64_t* e_ptr; const int32_t* ob_e; const uint8_t* ob_slot; const uint16_t* pidx;
-  const uint32_t* dslot; const uint32_t* cslot; const uint16_t* cthr;
+  const uint32_t* dslot; const uint32_t* cslot; const uint16_t* cthr; const uint16_t* thr_of;
   int32_t* ent; uint16_t* seg; int64_t* tile_nfl;
 };
 // owner slot and entry of the pair (l, l2) / of observation l; returns false when there is none
-__device__ __forceinline__ int sa_pair_owner(const SaEntParams& P, const SaStrip& S, const uint32_t* dslot, int sa, int sb, int lp) {
+__device__ __forceinline__ int sa_pair_owner(const SaEntParams& P, const SaStrip& S, const uint32_t* dslot, const uint16_t* thr_of, int sa, int sb,
+                                             int lp) {
   const uint32_t ds = dslot[sa * P.ncs_cap + sb];
   if (ds & 0x80000000u) return SA_NT + (int)(ds & 0xffffu);
   const int m = (int)((ds >> 12) & 0xffu);
-  return (int)(ds & 0xfffu) + (lp % m) * S.npp;
+  return thr_of[(int)(ds & 0xfffu) + (lp % m) * S.npp];
 }
 // One CTA per tile: counting sort of the tile's entries by owner slot (counts and offsets are exact integers; the
 // order inside a segment is then made canonical by sorting the segment), segment table, flush outputs of the tile.
@@ -502,6 +550,7 @@ __global__ void __launch_bounds__(512) k_sa_tile_entries(SaEntParams P) {
   const uint32_t* dslot = P.dslot + (size_t)(t / P.L) * P.ncs_cap * P.ncs_cap;
   const uint32_t* cslot = P.cslot + (size_t)(t / P.L) * P.ncs_cap;
   const uint16_t* cthr = P.cthr + (size_t)(t / P.L) * P.ncs_cap * SA_CM_MAX;
+  const uint16_t* thr_of = P.thr_of + (size_t)(t / P.L) * SA_NT;
   const int nv = SA_NT + S.nflush;
   for (int i = tid; i < P.segw; i += nthr) count[i] = 0;
   if (tid == 0) nfl_s = 0;
@@ -524,7 +573,7 @@ __global__ void __launch_bounds__(512) k_sa_tile_entries(SaEntParams P) {
         const int s2 = P.ob_slot[o2], pos2 = P.pidx[T.pidx0 + (int)(o2 - T.ob0)];
         if (s2 == s) continue;
         const bool fwd = s < s2;
-        const int owner = sa_pair_owner(P, S, dslot, fwd ? s : s2, fwd ? s2 : s, lp);
+        const int owner = sa_pair_owner(P, S, dslot, thr_of, fwd ? s : s2, fwd ? s2 : s, lp);
         if (pass == 0) atomicAdd(&count[owner], 1);
         else dst[start[owner] + atomicAdd(&count[owner], 1)] = fwd ? (pos | (pos2 << 12)) : (pos2 | (pos << 12));
       }
@@ -733,18 +782,20 @@ inline int build_strip_a_geom(StripA& A, FusedA& F, const Structure& S, const do
   // 5. owner slots per strip
   const int nf_cap = std::min(SA_NF_CAP, std::max(8, A.ncs_cap * A.ncs_cap / 2));
   DVec<uint32_t> dslot, cslot;
-  DVec<uint16_t> slot_dest, fl_dest, cthr;
+  DVec<uint16_t> slot_dest, fl_dest, cthr, thr_of;
   DVec<int32_t> counts;
   BA_TRY(dslot.alloc((size_t)ns * A.ncs_cap * A.ncs_cap)); BA_TRY(cslot.alloc((size_t)ns * A.ncs_cap));
   BA_TRY(A.slot_out.alloc((size_t)ns * SA_NT)); BA_TRY(slot_dest.alloc((size_t)ns * SA_NT)); BA_TRY(fl_dest.alloc((size_t)ns * nf_cap));
-  BA_TRY(counts.alloc((size_t)ns * 8)); BA_TRY(cthr.alloc((size_t)ns * A.ncs_cap * SA_CM_MAX));
+  BA_TRY(counts.alloc((size_t)ns * 8)); BA_TRY(cthr.alloc((size_t)ns * A.ncs_cap * SA_CM_MAX)); BA_TRY(thr_of.alloc((size_t)ns * SA_NT));
   {
     SaPlanParams P;
     P.n_strips = ns; P.L = L; P.n_tiles = nt; P.ncs_cap = A.ncs_cap; P.nf_cap = nf_cap;
     P.cam_budget = env_int("BA_SA_NCAM", 32, 256, 64) / 32 * 32;
     P.by_count = env_int("BA_SA_ORDER", 0, 1, 0);
+    P.balance = env_int("BA_SA_BALANCE", 0, 1, 1);
     P.tile_pt_ptr = A.tile_pt_ptr.p; P.e_ptr = S.e_ptr.p; P.ob_slot = ob_slot.p; P.strip_cam_ptr = A.strip_cam_ptr.p;
     P.dslot = dslot.p; P.cslot = cslot.p; P.cthr = cthr.p; P.slot_out = A.slot_out.p; P.slot_dest = slot_dest.p; P.fl_dest = fl_dest.p;
+    P.thr_of = thr_of.p;
     P.counts = counts.p;
     k_sa_strip_plan<<<ns, 256, 0, st>>>(P);
   }
@@ -781,7 +832,7 @@ inline int build_strip_a_geom(StripA& A, FusedA& F, const Structure& S, const do
     SaEntParams P;
     P.L = L; P.ncs_cap = A.ncs_cap; P.segw = A.segw; P.stage_cap = 12288;
     P.tiles = A.tiles.p; P.strips = A.strips.p; P.e_ptr = S.e_ptr.p; P.ob_e = S.ob_e.p; P.ob_slot = ob_slot.p; P.pidx = A.pidx.p;
-    P.dslot = dslot.p; P.cslot = cslot.p; P.cthr = cthr.p; P.ent = A.ent.p; P.seg = A.seg.p; P.tile_nfl = t_nfl.p;
+    P.dslot = dslot.p; P.cslot = cslot.p; P.cthr = cthr.p; P.thr_of = thr_of.p; P.ent = A.ent.p; P.seg = A.seg.p; P.tile_nfl = t_nfl.p;
     const size_t sm = ((size_t)2 * A.segw + 1 + P.stage_cap) * sizeof(int);
     BA_CUDA_TRY(cudaFuncSetAttribute(k_sa_tile_entries, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     k_sa_tile_entries<<<nt, 512, sm, st>>>(P);
