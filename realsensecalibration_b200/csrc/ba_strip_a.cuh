@@ -442,6 +442,7 @@ __global__ void __launch_bounds__(256) k_sa_strip_plan(SaPlanParams P) {
     // (steps of its fullest lane per strip; a camera observation costs about 1.3 pair products)
     float lw[SA_NT / 32];
     for (int w = 0; w < SA_NT / 32; ++w) lw[w] = 0.f;
+    for (int l = 0; l < SA_NT; ++l) { sort_ab[l] = 0; sort_cnt[l] = 0; }   // logical slot tables (idle unless set below)
     int max_m = 0;
     for (int r = 0; r < npp; ++r) max_m = max(max_m, (int)pcopies[r]);
     for (int j = 0; j < max_m; ++j)
