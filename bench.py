@@ -480,8 +480,10 @@ def main():
                "sample": "full workload, one solve of %d LM iterations (problem construction + initial evaluation included), "
                          "oracle/ba_oracle.cpp with OpenMP" % kc}
         if kc == ITERS_PER_SOLVE and K >= ITERS_PER_SOLVE:
+            # relative to the final cost, but never below 1e-12 of the initial cost: a zero-residual problem (cfg1) ends at round-off
+            scale = max(abs(float(osum.final_cost)), 1e-12 * abs(float(osum.initial_cost)), 1e-300)
             parity = {"oracle_final_cost": float(osum.final_cost), "gpu_final_cost": float(summary.final_cost),
-                      "rel": abs(float(summary.final_cost) - float(osum.final_cost)) / abs(float(osum.final_cost)),
+                      "rel": abs(float(summary.final_cost) - float(osum.final_cost)) / scale,
                       "source": "cpu_baseline leg of this run (same options, same start, %d LM iterations)" % kc}
     if parity is None and rank == 0 and K >= ITERS_PER_SOLVE and K % ITERS_PER_SOLVE == 0:
         tr = committed_trace(a.workload)

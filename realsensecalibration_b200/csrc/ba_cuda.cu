@@ -409,8 +409,10 @@ int run_gradient_norms_e(ba_cuda_problem* p) {  // eliminated blocks: shard loca
   constexpr int NU = DE * (DE + 1) / 2;
   const int ge = (int)grid_for(S.ne * DE, 256);
   BA_LAUNCH(p, KT_GRADNORM, (k_gradient_norm<DE, NU + DE, NU>), ge, 256, 0, S.ne, S.e_ptr.p, p->xe.p, p->se.p, p->ME.p, p->bp0.p, p->bp1.p);
-  BA_TRY(fold(p, p->bp0.p, ge, S_GMAXE, true));
-  BA_TRY(fold(p, p->bp1.p, ge, S_G2E));
+  {
+    FoldJob J = {{p->bp0.p, p->bp1.p, nullptr, nullptr}, {S_GMAXE, S_G2E, 0, 0}, {1, 0, 0, 0}};
+    BA_LAUNCH(p, KT_FOLD, k_fold_multi, 2, 1024, 0, J, ge, p->scal.p);
+  }
   BA_CUDA_TRY(cudaGetLastError());
   return BA_OK;
 }
@@ -418,8 +420,10 @@ int run_gradient_norms_f(ba_cuda_problem* p) {  // kept blocks: from the (global
   const Structure& S = p->S;
   const int gf = (int)grid_for(S.nf * 6, 256);
   BA_LAUNCH(p, KT_GRADNORM, (k_gradient_norm<6, NV_F, 21>), gf, 256, 0, S.nf, p->f_act_ptr.p, p->xf.p, p->sf.p, p->HG.p, p->bp0.p, p->bp1.p);
-  BA_TRY(fold(p, p->bp0.p, gf, S_GMAXF, true));
-  BA_TRY(fold(p, p->bp1.p, gf, S_G2F));
+  {
+    FoldJob J = {{p->bp0.p, p->bp1.p, nullptr, nullptr}, {S_GMAXF, S_G2F, 0, 0}, {1, 0, 0, 0}};
+    BA_LAUNCH(p, KT_FOLD, k_fold_multi, 2, 1024, 0, J, gf, p->scal.p);
+  }
   BA_CUDA_TRY(cudaGetLastError());
   return BA_OK;
 }
@@ -523,11 +527,15 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   BA_TRY(fold(p, p->bp0.p, gm, S_MCC));
   const int gce = (int)grid_for(S.ne * DE, 256), gcf = (int)grid_for(S.nf * 6, 256);
   BA_LAUNCH(p, KT_CANDIDATE, (k_candidate<DE>), gce, 256, 0, S.ne, S.e_ptr.p, p->xe.p, p->se.p, p->ye.p, p->xe_c.p, p->bp0.p, p->bp1.p);
-  BA_TRY(fold(p, p->bp0.p, gce, S_XE2));
-  BA_TRY(fold(p, p->bp1.p, gce, S_DE2));
+  {
+    FoldJob J = {{p->bp0.p, p->bp1.p, nullptr, nullptr}, {S_XE2, S_DE2, 0, 0}, {0, 0, 0, 0}};
+    BA_LAUNCH(p, KT_FOLD, k_fold_multi, 2, 1024, 0, J, gce, p->scal.p);
+  }
   BA_LAUNCH(p, KT_CANDIDATE, (k_candidate<6>), gcf, 256, 0, S.nf, p->f_act_ptr.p, p->xf.p, p->sf.p, p->yf.p, p->xf_c.p, p->bp0.p, p->bp1.p);
-  BA_TRY(fold(p, p->bp0.p, gcf, S_XF2));
-  BA_TRY(fold(p, p->bp1.p, gcf, S_DF2));
+  {
+    FoldJob J = {{p->bp0.p, p->bp1.p, nullptr, nullptr}, {S_XF2, S_DF2, 0, 0}, {0, 0, 0, 0}};
+    BA_LAUNCH(p, KT_FOLD, k_fold_multi, 2, 1024, 0, J, gcf, p->scal.p);
+  }
   BA_CUDA_TRY(cudaGetLastError());
   fam_end(p, F_UPDATE);
   fam_begin(p, F_COST);

@@ -1261,10 +1261,11 @@ k_reduce_final(int ntargets, const int32_t* __restrict__ seg_first, const double
 }
 
 // folds up to 4 partial arrays in one launch: blockIdx.x = which; op 0 = sum, 1 = max
-struct FoldJob { const double* partial[4]; int slot[4]; int is_max[4]; };
+struct FoldJob { const double* partial[4]; int slot[4]; int is_max[4]; int n[4] = {0, 0, 0, 0}; };   // n[k] > 0 overrides the common length
 __global__ void k_fold_multi(FoldJob J, int n, double* out) {
   __shared__ double sm[32];
   const double* partial = J.partial[blockIdx.x];
+  if (J.n[blockIdx.x] > 0) n = J.n[blockIdx.x];
   double v = 0.0;
   if (J.is_max[blockIdx.x]) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) v = fmax(v, partial[i]);

@@ -235,6 +235,7 @@ struct SaPlanParams {
   int cam_budget;               // camera threads per strip (whole warps): the observations of a camera are dealt over its threads
   int by_count;                 // owner slots in order of descending pair count instead of (diagonal, first camera)
   int balance;                  // deal the warps over the four SM sub-partitions by load
+  int arrange;                  // class-aware order inside every group of 32 owner slots
   const int64_t* tile_pt_ptr; const int64_t* e_ptr; const uint8_t* ob_slot; const int64_t* strip_cam_ptr;
   uint32_t* dslot;              // [n_strips][ncs_cap^2]: rank | copies << 12, or 1 << 31 | flush index; ~0 = no such pair
   uint32_t* cslot;              // [n_strips][ncs_cap]: owner threads of the camera; 0 = camera without observations
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(256) k_sa_strip_plan(SaPlanParams P) {
   // inside every group of 32 (a warp): quarter warps whose eight pairs have eight different first-camera classes and
   // eight different second-camera classes (mod 8) where the group allows it, so that the records a quarter warp
   // gathers in one step lie in different bank groups
-  if (P.by_count && tid < (npp + 31) / 32) {
+  if (P.arrange && tid < (npp + 31) / 32) {
     const int g0 = 32 * tid, n = min(32, npp - g0);
     uint16_t ab[32]; int cc[32]; bool used[32];
     for (int i = 0; i < n; ++i) { ab[i] = sort_ab[g0 + i]; cc[i] = sort_cnt[g0 + i]; used[i] = false; }
@@ -794,6 +795,7 @@ inline int build_strip_a_geom(StripA& A, FusedA& F, const Structure& S, const do
     P.cam_budget = env_int("BA_SA_NCAM", 32, 256, 64) / 32 * 32;
     P.by_count = env_int("BA_SA_ORDER", 0, 1, 0);
     P.balance = env_int("BA_SA_BALANCE", 0, 1, 1);
+    P.arrange = env_int("BA_SA_ARRANGE", 0, 1, P.by_count);   // measured: no gain in (diagonal, camera) order
     P.tile_pt_ptr = A.tile_pt_ptr.p; P.e_ptr = S.e_ptr.p; P.ob_slot = ob_slot.p; P.strip_cam_ptr = A.strip_cam_ptr.p;
     P.dslot = dslot.p; P.cslot = cslot.p; P.cthr = cthr.p; P.slot_out = A.slot_out.p; P.slot_dest = slot_dest.p; P.fl_dest = fl_dest.p;
     P.thr_of = thr_of.p;
