@@ -104,7 +104,20 @@ typedef struct ba_cuda_options {
   double parameter_tolerance;                /* 1e-8 */
   double pcg_eta;                            /* 1e-1 (q_tolerance) */
   double pcg_r_tolerance;                    /* -1 (disabled, as LevenbergMarquardtStrategy does) */
+  /* Robust loss on every residual block (an observation of Model A: 2 residuals; a marker observation of Model B: 8).
+   * The reference passes NULL to AddResidualBlock (bundle_adjustment_manager.cpp:38,51,68,82; Test1 main.cpp:77): BA_LOSS_NONE,
+   * the default, reproduces it bit for bit.  Huber / Cauchy restate ceres::HuberLoss(a) / ceres::CauchyLoss(a) and Ceres'
+   * Corrector: residuals and Jacobian rows of a block are scaled by sqrt(rho'(s)), s = |r|^2, the cost is sum rho(s) / 2. */
+  int32_t loss_function;                     /* ba_loss, BA_LOSS_NONE */
+  int32_t reserved_;
+  double loss_scale;                         /* a, 1.0 */
 } ba_cuda_options;
+
+typedef enum ba_loss {
+  BA_LOSS_NONE = 0,
+  BA_LOSS_HUBER = 1,
+  BA_LOSS_CAUCHY = 2
+} ba_loss;
 
 /* One row of Ceres' minimizer_progress_to_stdout table (IterationSummary). */
 typedef struct ba_cuda_iteration {

@@ -203,7 +203,24 @@ struct Problem {
   std::vector<int64_t> f_blk_ptr, f_blk;      // CSR f -> sorted residual block ids
   std::vector<int64_t> inc_e;                 // incidence -> e
   int threads = 1;
+  // robust loss on every residual block (ba_cuda_options.loss_function / loss_scale); 0 = none, what the reference passes
+  // (NULL at bundle_adjustment_manager.cpp:38,51,68,82)
+  int loss = 0;
+  double loss_a = 1.0;
 };
+
+// ceres::HuberLoss / ceres::CauchyLoss (loss_function.cc): rho(s), rho'(s); both have rho'' <= 0, so Ceres' Corrector
+// (corrector.cc) scales residuals and Jacobian rows of the block by sqrt(rho') and nothing else.
+inline void loss_eval(int type, double a, double s, double* rho, double* rho1) {
+  *rho = s; *rho1 = 1.0;
+  if (type == 1) {
+    const double b = a * a;
+    if (s > b) { const double r = std::sqrt(s); *rho = 2.0 * a * r - b; *rho1 = std::max(std::numeric_limits<double>::min(), a / r); }
+  } else if (type == 2) {
+    const double b = a * a, sum = 1.0 + s / b, inv = 1.0 / sum;
+    *rho = b * std::log(sum); *rho1 = std::max(std::numeric_limits<double>::min(), inv);
+  }
+}
 
 struct Eval {
   std::vector<double> r, Je, Jf0, Jf1;  // per sorted residual block: rdim, rdim*de, rdim*6, rdim*6
@@ -272,6 +289,21 @@ double evaluate(const Problem& P, const double* x, Eval* ev) {
     double r[8], je[48], j0[48], j1[48];
     if (ev) {
       eval_block(P, x, b, true, r, je, j0, j1);
+      if (P.loss != 0) {   // Corrector::CorrectResiduals / CorrectJacobian with alpha = 0
+        double s = 0.0, rho, rho1;
+        for (int k = 0; k < rd; ++k) s += r[k] * r[k];
+        loss_eval(P.loss, P.loss_a, s, &rho, &rho1);
+        const double w = std::sqrt(rho1);
+        for (int k = 0; k < rd * de; ++k) je[k] *= w;
+        for (int k = 0; k < rd * 6; ++k) { j0[k] *= w; if (P.model == 1) j1[k] *= w; }
+        for (int k = 0; k < rd; ++k) r[k] *= w;
+        cost += rho;
+        std::memcpy(&ev->r[b * rd], r, sizeof(double) * rd);
+        std::memcpy(&ev->Je[b * rd * de], je, sizeof(double) * rd * de);
+        std::memcpy(&ev->Jf0[b * rd * 6], j0, sizeof(double) * rd * 6);
+        if (P.model == 1) std::memcpy(&ev->Jf1[b * rd * 6], j1, sizeof(double) * rd * 6);
+        continue;
+      }
       std::memcpy(&ev->r[b * rd], r, sizeof(double) * rd);
       std::memcpy(&ev->Je[b * rd * de], je, sizeof(double) * rd * de);
       std::memcpy(&ev->Jf0[b * rd * 6], j0, sizeof(double) * rd * 6);
@@ -281,6 +313,7 @@ double evaluate(const Problem& P, const double* x, Eval* ev) {
     }
     double s = 0.0;
     for (int k = 0; k < rd; ++k) s += r[k] * r[k];
+    if (P.loss != 0) { double rho, rho1; loss_eval(P.loss, P.loss_a, s, &rho, &rho1); s = rho; }
     cost += s;
   }
   return 0.5 * cost;
@@ -1008,6 +1041,7 @@ int run(Problem& P, double* params, const ba_cuda_options* options, int linear_s
 #else
   P.threads = 1;
 #endif
+  P.loss = opt.loss_function; P.loss_a = opt.loss_scale;
   LMResult res;
   minimize(P, params, opt, linear_solver, &res);
   if (summary) *summary = res.summary;
@@ -1051,6 +1085,7 @@ void ba_cuda_options_init(ba_cuda_options* o) {
   o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
   o->pcg_eta = 1e-1; o->pcg_r_tolerance = -1.0;
+  o->loss_function = 0; o->loss_scale = 1.0;
 }
 void ba_oracle_options_init(ba_cuda_options* o) { ba_cuda_options_init(o); }
 

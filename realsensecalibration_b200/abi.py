@@ -9,6 +9,7 @@ CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
  REASON_INITIAL_EVALUATION_FAILED) = range(8)
 UNIQUE_ID_BYTES = 128
 PATH_GENERIC, PATH_FUSED_TILES, PATH_FUSED_STRIPS = 0, 1, 2
+LOSS_NONE, LOSS_HUBER, LOSS_CAUCHY = 0, 1, 2
 
 
 class Options(C.Structure):
@@ -34,6 +35,9 @@ class Options(C.Structure):
         ("parameter_tolerance", C.c_double),
         ("pcg_eta", C.c_double),
         ("pcg_r_tolerance", C.c_double),
+        ("loss_function", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("loss_scale", C.c_double),
     ]
 
 

@@ -123,6 +123,7 @@ struct ba_cuda_problem {
   bool use_fused = false, use_strip = false, generic_ws = false;
   bool smem_attr_set = false;   // the opt-in shared-memory sizes are per device: set once per problem
   SparseExchange SX;            // multi-GPU, fused Model A + PCG: all-gather of the ranks' own blocks instead of an all-reduce of all
+  LossSpec loss{0, 1.0};        // robust loss of the current solve (options.loss_function / loss_scale); 0 outside a solve
   DVec<double> fa_part;      // 7 per-tile partial arrays (cost, g2, gmax, mcc, x2, d2, cand)
   int h_pcg_iters = 0;
   double* h_scal = nullptr;  // pinned
@@ -354,11 +355,11 @@ int run_jacobian(ba_cuda_problem* p) {
   if (p->model == 0) {
     grid = (int)grid_for(S.nb, 256);
     BA_LAUNCH(p, KT_JAC, k_jac_a, grid, 256, 0, S.nb, S.ob_e.p, S.ob_f0.p, p->uv.p, p->tab_f.p, p->xe.p, p->se.p, p->RES.p,
-              p->JE.p, p->JF0.p, p->bp0.p);
+              p->JE.p, p->JF0.p, p->bp0.p, p->loss);
   } else {
     grid = (int)grid_for(S.nb * 4, 128);
     BA_LAUNCH(p, KT_JAC, k_jac_b, grid, 128, 0, S.nb, S.ob_e.p, S.ob_f0.p, S.ob_f1.p, p->ob_cam.p, p->obs8.p, p->tab_f.p,
-              p->tab_e.p, p->half_side, p->RES.p, p->JE.p, p->JF0.p, p->JF1.p, p->bp0.p);
+              p->tab_e.p, p->half_side, p->RES.p, p->JE.p, p->JF0.p, p->JF1.p, p->bp0.p, p->loss);
   }
   BA_CUDA_TRY(cudaGetLastError());
   return fold(p, p->bp0.p, grid, S_COST);
@@ -371,11 +372,11 @@ int run_cost_candidate(ba_cuda_problem* p) {
   int grid;
   if (p->model == 0) {
     grid = (int)grid_for(S.nb, 256);
-    BA_LAUNCH(p, KT_COST, k_cost_a, grid, 256, 0, S.nb, S.ob_e.p, S.ob_f0.p, p->uv.p, p->tabc_f.p, p->xe_c.p, p->bp0.p);
+    BA_LAUNCH(p, KT_COST, k_cost_a, grid, 256, 0, S.nb, S.ob_e.p, S.ob_f0.p, p->uv.p, p->tabc_f.p, p->xe_c.p, p->bp0.p, p->loss);
   } else {
     grid = (int)grid_for(S.nb * 4, 128);
     BA_LAUNCH(p, KT_COST, k_cost_b, grid, 128, 0, S.nb, S.ob_e.p, S.ob_f0.p, S.ob_f1.p, p->ob_cam.p, p->obs8.p, p->tabc_f.p,
-              p->tabc_e.p, p->half_side, p->bp0.p);
+              p->tabc_e.p, p->half_side, p->bp0.p, p->loss);
   }
   BA_CUDA_TRY(cudaGetLastError());
   return fold(p, p->bp0.p, grid, S_CAND);
@@ -565,6 +566,7 @@ FaParams fa_params(ba_cuda_problem* p, const ba_cuda_options& opt) {
   P.cand_partial = p->fa_part.p + 6 * nt;
   P.RES = p->RES.p; P.JE = p->JE.p; P.JF = p->JF0.p;
   P.status = p->status.p;
+  P.loss = p->loss;
   return P;
 }
 
@@ -697,6 +699,7 @@ int sa_linearize(ba_cuda_problem* p, const ba_cuda_options& opt, bool grad_only,
   P.cost_partial = p->fa_part.p; P.g2_partial = p->fa_part.p + ns; P.gmax_partial = p->fa_part.p + 2 * ns;
   P.status = p->status.p;
   P.dbg = env_int("BA_SA_DBG", 0, 7, 0);
+  P.loss = p->loss;
   static DVec<unsigned long long>* clk = nullptr;   // BA_SA_CLOCKS=1: cycles of thread 0 per phase of pass 1, printed per launch (tuning aid)
   P.clocks = nullptr;
   if (env_int("BA_SA_CLOCKS", 0, 1, 0)) {
@@ -1376,6 +1379,7 @@ void ba_cuda_options_init(ba_cuda_options* o) {
   o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
   o->pcg_eta = 1e-1; o->pcg_r_tolerance = -1.0;
+  o->loss_function = BA_LOSS_NONE; o->loss_scale = 1.0;
 }
 
 const char* ba_cuda_last_error(void) { return err_buf(); }
@@ -1677,6 +1681,9 @@ int ba_cuda_solve_begin(ba_cuda_problem* p, const ba_cuda_options* options) {
   BA_TRY(use_device(p));
   ba_cuda_options opt;
   if (options) opt = *options; else ba_cuda_options_init(&opt);
+  if (opt.loss_function < BA_LOSS_NONE || opt.loss_function > BA_LOSS_CAUCHY || (opt.loss_function != BA_LOSS_NONE && !(opt.loss_scale > 0.0)))
+    return fail(BA_ERR_INVALID_ARGUMENT, "loss_function %d with scale %g", opt.loss_function, opt.loss_scale);
+  p->loss = LossSpec{opt.loss_function, opt.loss_scale};
   BA_TRY(prepare_solver(p, opt));
   if (p->model == 0 && (opt.force_generic_path || !p->use_fused)) BA_TRY(ensure_generic_workspace(p));
   return p->model == 0 ? lm_begin<2, 3, 1, 1>(p, opt) : lm_begin<8, 6, 32, 2>(p, opt);
@@ -1696,6 +1703,7 @@ int ba_cuda_solve_end(ba_cuda_problem* p, ba_cuda_summary* summary) {
   if (!p->lm.began) return fail(BA_ERR_STATE, "ba_cuda_solve_begin must be called first");
   BA_TRY(use_device(p));
   lm_end(p, summary);
+  p->loss = LossSpec{0, 1.0};   // ba_cuda_eval / ba_cuda_reprojection_error report plain residuals
   if (summary) {
     const int64_t ae = p->n_active_e_global, af = p->n_active_f_global;
     summary->num_free_parameters = ae * (p->model == 0 ? 3 : 6) + af * 6;

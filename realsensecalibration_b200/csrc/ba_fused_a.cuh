@@ -643,7 +643,22 @@ struct FaParams {
   // standalone residual + Jacobian (k_fa_jac)
   double* RES; double* JE; double* JF;
   int* status;
+  LossSpec loss;   // robust loss on every observation (type 0 = none, the reference)
 };
+
+// Ceres' Corrector on one observation: r, J_e, J_f scaled by sqrt(rho'(|r|^2)); returns the cost term rho
+__device__ __forceinline__ double fa_apply_loss(const LossSpec L, double* r, double* je, double* jf) {
+  const double s = r[0] * r[0] + r[1] * r[1];
+  if (L.type == 0) return s;
+  double rho, w;
+  loss_apply(L, s, &rho, &w);
+  r[0] *= w; r[1] *= w;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) je[k] *= w;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) jf[k] *= w;
+  return rho;
+}
 
 __device__ __forceinline__ FaTile fa_load_tile(const FaTile* __restrict__ p) {
   FaTile T;
@@ -798,7 +813,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass1(FaParams P) {
     if (!UNIT) { s[0] = xs[3]; s[1] = xs[4]; s[2] = xs[5]; }
     double r[2], je[6], jf[12];
     fa_linearize(Tt, X, s, ob, r, je, jf);
-    sq += r[0] * r[0] + r[1] * r[1];
+    sq += fa_apply_loss(P.loss, r, je, jf);
     double2* R2 = reinterpret_cast<double2*>(rec + (size_t)l * FA_REC);
 #pragma unroll
     for (int k = 0; k < 3; ++k) R2[k] = make_double2(je[2 * k], je[2 * k + 1]);
@@ -1016,6 +1031,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass2(FaParams P) {
     const double s[3] = {xs[3], xs[4], xs[5]};
     double r[2], je[6], jf[12];
     fa_linearize(Tt, X, s, ob, r, je, jf);
+    fa_apply_loss(P.loss, r, je, jf);
     double q0 = 0.0, q1 = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) { q0 += jf[k] * y[k]; q1 += jf[6 + k] * y[k]; }
@@ -1094,7 +1110,9 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) k_fa_pass2(FaParams P) {
     const double p0 = q[0] + C[9], p1 = q[1] + C[10], p2 = q[2] + C[11];
     const double r0 = C[12] * p0 / p2 + C[14] - ob.x;
     const double r1 = C[13] * p1 / p2 + C[15] - ob.y;
-    sq += r0 * r0 + r1 * r1;
+    double sc = r0 * r0 + r1 * r1;
+    if (P.loss.type != 0) { double w; loss_apply(P.loss, sc, &sc, &w); }
+    sq += sc;
   }
   double v[4] = {mcc, x2, d2, sq};
   const bool mx[4] = {false, false, false, false};
@@ -1160,7 +1178,7 @@ __global__ void __launch_bounds__(FA_JAC_THREADS, 4) k_fa_jac(FaParams P) {
       const double s[3] = {xs[3], xs[4], xs[5]};
       double r[2], je[6], jf[12];
       fa_linearize(Tt, X, s, ob, r, je, jf);
-      sq += r[0] * r[0] + r[1] * r[1];
+      sq += fa_apply_loss(P.loss, r, je, jf);
       RES2[ob0 + l] = make_double2(r[0], r[1]);
       double2* E2 = reinterpret_cast<double2*>(wje) + 3 * lane;
 #pragma unroll

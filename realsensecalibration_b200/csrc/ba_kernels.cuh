@@ -92,6 +92,21 @@ __device__ __forceinline__ void mat3_vec(const double* R, const double* x, doubl
   y[1] = R[3] * x[0] + R[4] * x[1] + R[5] * x[2];
   y[2] = R[6] * x[0] + R[7] * x[1] + R[8] * x[2];
 }
+// Robust loss of one residual block (ceres::HuberLoss / ceres::CauchyLoss, loss_function.cc) and Ceres' Corrector
+// (corrector.cc): for both losses rho'' <= 0, so the corrected residuals and Jacobian rows are the plain ones times
+// sqrt(rho'(s)); the block's cost term is rho(s) / 2.  type 0 (the reference: NULL loss) leaves everything untouched.
+struct LossSpec { int type; double a; };
+__host__ __device__ __forceinline__ void loss_apply(const LossSpec L, double s, double* rho, double* w) {
+  *rho = s; *w = 1.0;
+  if (L.type == 1) {            // Huber: rho = s below a^2, 2 a sqrt(s) - a^2 above
+    const double b = L.a * L.a;
+    if (s > b) { const double r = sqrt(s); *rho = 2.0 * L.a * r - b; *w = sqrt(fmax(DBL_MIN, L.a / r)); }
+  } else if (L.type == 2) {     // Cauchy: rho = a^2 log(1 + s / a^2)
+    const double b = L.a * L.a, sum = 1.0 + s / b, inv = 1.0 / sum;
+    *rho = b * log(sum); *w = sqrt(fmax(DBL_MIN, inv));
+  }
+}
+
 // D[:,k] = A[:,k] x b  (= -[b]x A), the derivative of the rotated point w.r.t. the angle-axis
 __device__ __forceinline__ void rot_deriv(const double* A, const double* b, double* D /*3x3 row-major*/) {
 #pragma unroll
@@ -128,7 +143,7 @@ __device__ __forceinline__ void staged_store(double* stage, const double* vals, 
 __global__ void __launch_bounds__(256)
 k_jac_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const double2* __restrict__ uv,
         const double* __restrict__ tab_f, const double* __restrict__ xe, const double* __restrict__ se,
-        double* __restrict__ RES, double* __restrict__ JE, double* __restrict__ JF0, double* __restrict__ cost_partial) {
+        double* __restrict__ RES, double* __restrict__ JE, double* __restrict__ JF0, double* __restrict__ cost_partial, LossSpec L) {
   __shared__ double sm[32];
   __shared__ __align__(16) double stage[256 * 14];
   const int64_t o0 = blockIdx.x * (int64_t)blockDim.x;
@@ -146,8 +161,8 @@ k_jac_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
     mat3_vec(T, X, q);
     const double p0 = q[0] + T[18], p1 = q[1] + T[19], p2 = q[2] + T[20];
     const double2 ob = uv[o];
-    const double r0 = T[21] * p0 / p2 + T[23] - ob.x;
-    const double r1 = T[22] * p1 / p2 + T[24] - ob.y;
+    double r0 = T[21] * p0 / p2 + T[23] - ob.x;
+    double r1 = T[22] * p1 / p2 + T[24] - ob.y;
     sq = r0 * r0 + r1 * r1;
     const double iz = 1.0 / p2;
     const double a = T[21] * iz, bb = -T[21] * p0 * iz * iz, cc = T[22] * iz, dd = -T[22] * p1 * iz * iz;
@@ -162,6 +177,15 @@ k_jac_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
     jf[9] = 0.0;       jf[10] = cc * T[30]; jf[11] = dd * T[31];
     je[0] = (a * T[0] + bb * T[6]) * s0; je[1] = (a * T[1] + bb * T[7]) * s1; je[2] = (a * T[2] + bb * T[8]) * s2;
     je[3] = (cc * T[3] + dd * T[6]) * s0; je[4] = (cc * T[4] + dd * T[7]) * s1; je[5] = (cc * T[5] + dd * T[8]) * s2;
+    if (L.type != 0) {
+      double w;
+      loss_apply(L, sq, &sq, &w);
+      r0 *= w; r1 *= w;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) jf[k] *= w;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) je[k] *= w;
+    }
     reinterpret_cast<double2*>(RES)[o] = make_double2(r0, r1);
   }
   staged_store<12, 14>(stage, jf, o < nb, JF0 + 12 * o0, n_valid);
@@ -172,7 +196,7 @@ k_jac_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
 
 __global__ void __launch_bounds__(256)
 k_cost_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const double2* __restrict__ uv,
-         const double* __restrict__ tab_f, const double* __restrict__ xe, double* __restrict__ cost_partial) {
+         const double* __restrict__ tab_f, const double* __restrict__ xe, double* __restrict__ cost_partial, LossSpec L) {
   __shared__ double sm[32];
   const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   double sq = 0.0;
@@ -190,6 +214,7 @@ k_cost_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict
     const double r0 = __ldg(T + 21) * p0 / p2 + __ldg(T + 23) - ob.x;
     const double r1 = __ldg(T + 22) * p1 / p2 + __ldg(T + 24) - ob.y;
     sq = r0 * r0 + r1 * r1;
+    if (L.type != 0) { double w; loss_apply(L, sq, &sq, &w); }
   }
   sq = block_sum(sq, sm);
   if (threadIdx.x == 0) cost_partial[blockIdx.x] = sq;
@@ -269,7 +294,7 @@ __global__ void __launch_bounds__(128)
 k_jac_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const int32_t* __restrict__ ob_f1,
         const int32_t* __restrict__ ob_cam, const double* __restrict__ obs8, const double* __restrict__ tab_f,
         const double* __restrict__ tab_e, double half, double* __restrict__ RES, double* __restrict__ JE,
-        double* __restrict__ JF0, double* __restrict__ JF1, double* __restrict__ cost_partial) {
+        double* __restrict__ JF0, double* __restrict__ JF1, double* __restrict__ cost_partial, LossSpec L) {
   __shared__ double sm[32];
   __shared__ __align__(16) double stage[128 * 14];
   const int64_t t0 = blockIdx.x * (int64_t)blockDim.x;   // (marker observation, corner) records are contiguous: 12 doubles each
@@ -277,8 +302,10 @@ k_jac_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
   const int64_t o = t >> 2;
   const int corner = (int)(t & 3);
   const int n_valid = (int)min((int64_t)blockDim.x, 4 * nb - t0);
-  double sq = 0.0;
+  double sq = 0.0, rr0 = 0.0, rr1 = 0.0;
   double je12[12], jc12[12], jm12[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) { je12[k] = 0.0; jc12[k] = 0.0; jm12[k] = 0.0; }
   if (o < nb) {
     const int32_t f0 = ob_f0[o], f1 = ob_f1[o];
     double Tc[TAB], Tt[TAB], Tm[TAB];
@@ -295,8 +322,6 @@ k_jac_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
     sq = r0 * r0 + r1 * r1;
     const double iz = 1.0 / p2;
     const double a = fx * iz, bb = -fx * p0 * iz * iz, cc = fy * iz, dd = -fy * p1 * iz * iz;
-    RES[8 * o + 2 * corner] = r0;
-    RES[8 * o + 2 * corner + 1] = r1;
     double row0[6], row1[6];
     b_rows(P.G, Tt + 9, P.bt, Tt + 26, a, bb, cc, dd, row0, row1);
 #pragma unroll
@@ -307,6 +332,22 @@ k_jac_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
     if (f1 >= 0) b_rows(P.H, Tm + 9, P.bm, Tm + 26, a, bb, cc, dd, row0, row1);
 #pragma unroll
     for (int k = 0; k < 6; ++k) { jm12[k] = f1 >= 0 ? row0[k] : 0.0; jm12[6 + k] = f1 >= 0 ? row1[k] : 0.0; }
+    rr0 = r0; rr1 = r1;
+  }
+  if (L.type != 0) {   // the residual block is the marker observation: |r|^2 over its four corners (four consecutive lanes)
+    double s = sq;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    double rho, w;
+    loss_apply(L, s, &rho, &w);
+    sq = corner == 0 ? rho : 0.0;
+    rr0 *= w; rr1 *= w;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { je12[k] *= w; jc12[k] *= w; jm12[k] *= w; }
+  }
+  if (o < nb) {
+    RES[8 * o + 2 * corner] = rr0;
+    RES[8 * o + 2 * corner + 1] = rr1;
   }
   staged_store<12, 14>(stage, je12, o < nb, JE + 12 * t0, n_valid);
   staged_store<12, 14>(stage, jc12, o < nb, JF0 + 12 * t0, n_valid);
@@ -318,7 +359,7 @@ k_jac_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
 __global__ void __launch_bounds__(128)
 k_cost_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const int32_t* __restrict__ ob_f1,
          const int32_t* __restrict__ ob_cam, const double* __restrict__ obs8, const double* __restrict__ tab_f,
-         const double* __restrict__ tab_e, double half, double* __restrict__ cost_partial) {
+         const double* __restrict__ tab_e, double half, double* __restrict__ cost_partial, LossSpec L) {
   __shared__ double sm[32];
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per (marker observation, corner)
   const int64_t o = t >> 2;
@@ -336,6 +377,14 @@ k_cost_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict
     const double r0 = __ldg(K) * P.p3[0] / P.p3[2] + __ldg(K + 2) - obs8[8 * o + 2 * corner];
     const double r1 = __ldg(K + 1) * P.p3[1] / P.p3[2] + __ldg(K + 3) - obs8[8 * o + 2 * corner + 1];
     sq = r0 * r0 + r1 * r1;
+  }
+  if (L.type != 0) {
+    double s = sq;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    double rho, w;
+    loss_apply(L, s, &rho, &w);
+    sq = corner == 0 ? rho : 0.0;
   }
   sq = block_sum(sq, sm);
   if (threadIdx.x == 0) cost_partial[blockIdx.x] = sq;

@@ -900,6 +900,7 @@ struct SaParams {
   double* Lz; double* se_out; double* cost_partial; double* g2_partial; double* gmax_partial; int* status;
   int dbg;   // BA_SA_DBG (timing experiments only, results are wrong): 1 skips the pair products, 2 the camera sums, 4 the point phases
   unsigned long long* clocks;   // BA_SA_CLOCKS: [8] cycles per phase, summed over the CTAs by thread 0 of each (nullptr: off)
+  LossSpec loss;                // robust loss on every observation (type 0 = none, the reference)
 };
 
 __device__ __forceinline__ uint32_t sa_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1060,7 +1061,7 @@ __global__ void __launch_bounds__(SA_NT, 1) k_sa_pass1(SaParams P) {
         je[0] = (a * tf(0) + bb * tf(6)) * s[0]; je[1] = (a * tf(1) + bb * tf(7)) * s[1]; je[2] = (a * tf(2) + bb * tf(8)) * s[2];
         je[3] = (cc * tf(3) + dd * tf(6)) * s[0]; je[4] = (cc * tf(4) + dd * tf(7)) * s[1]; je[5] = (cc * tf(5) + dd * tf(8)) * s[2];
       }
-      sq += r[0] * r[0] + r[1] * r[1];
+      sq += fa_apply_loss(P.loss, r, je, jf);
 #pragma unroll
       for (int k = 0; k < 3; ++k) R2[k] = make_double2(je[2 * k], je[2 * k + 1]);
 #pragma unroll

@@ -38,6 +38,7 @@ BAManager::BAManager(const std::map<std::string, cv::Mat>& camera_intrinsics_map
   fix_base_marker_ = c.fix_base_marker;
   rotation_as_rvec_ = c.rotation_as_rvec;
   device_ = c.device;
+  loss_function_ = c.loss_function; loss_scale_ = c.loss_scale;
   bal_problem.set_marker_side(c.marker_side);
   Load();
 }
@@ -70,6 +71,7 @@ void BAManager::StartBA() {
   ba_cuda_options_init(&options);
   options.rcs_solver = BA_RCS_DENSE_CHOLESKY;      // options.linear_solver_type = DENSE_SCHUR
   options.minimizer_progress_to_stdout = 1;        // options.minimizer_progress_to_stdout = true
+  options.loss_function = loss_function_; options.loss_scale = loss_scale_;   // NULL loss unless configured otherwise
   check(ba_cuda_solve(p, &options, &summary_), "ba_cuda_solve");
   // Ceres optimises the caller's parameter blocks in place; here the result is copied back into parameters_
   check(ba_cuda_get_parameters(p, bal_problem.mutable_parameters(), bal_problem.num_parameters()), "ba_cuda_get_parameters");

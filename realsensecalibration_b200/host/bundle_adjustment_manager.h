@@ -26,6 +26,8 @@ class BAManager {
   bool rotation_as_rvec_ = false; // Test2 writes R<i> as the 3x1 rvec (Test2_BundleAdjustment/main.cpp:128)
   bool loaded_ = false;
   int device_ = 0;
+  int loss_function_ = BA_LOSS_NONE;
+  double loss_scale_ = 1.0;
   ba_cuda_summary summary_{};
   std::vector<ba_cuda_iteration> iterations_;
   void Load();
@@ -42,6 +44,8 @@ class BAManager {
     double marker_side = MARKER_SIDE;
     bool fix_base_marker = true, rotation_as_rvec = false;
     int device = 0;
+    int loss_function = BA_LOSS_NONE;   // the reference passes NULL to AddResidualBlock (manager.cpp:38,51,68,82)
+    double loss_scale = 1.0;
   };
   BAManager(const std::map<std::string, cv::Mat>& camera_intrinsics_map, const std::map<std::string, cv::Mat>& dist_coeffs_map,
             const Config& config);

@@ -39,7 +39,7 @@ def test_options_defaults_are_ceres_1_14():
 
 def test_pod_sizes_match_header():
     # 10 int32 + 11 double ; 4 int32 + 8 double ; 10 int32 + 2 int64 + 9 double + 2 int32 ; char[32] + int64 + 2 double
-    assert C.sizeof(abi.Options) == 10 * 4 + 11 * 8
+    assert C.sizeof(abi.Options) == 10 * 4 + 11 * 8 + 2 * 4 + 8
     assert C.sizeof(abi.KernelStat) == 32 + 8 + 2 * 8
     assert C.sizeof(abi.Iteration) == 4 * 4 + 8 * 8
     assert C.sizeof(abi.Summary) == 10 * 4 + 2 * 8 + 9 * 8 + 2 * 4
