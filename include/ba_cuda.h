@@ -275,6 +275,17 @@ int ba_cuda_get_iterations(ba_cuda_problem* p, ba_cuda_iteration* rows, int cap)
  *            blocks the functor does not take are zero. */
 int ba_cuda_eval(ba_cuda_problem* p, double* cost, double* residuals, double* jac);
 /* device time (ms, CUDA events) of the last ba_cuda_eval / ba_cuda_reprojection_error kernel */
+/* ---- the numeric part of the correspondence stage that runs just before the path.  ArUco detection and
+ *      solvePnP (EPnP) stay with OpenCV; these are the pose algebra and corner construction around them, in the conventions of
+ *      cv::Rodrigues.
+ *      ba_cuda_marker_corners: Correspondencer::GetCornersInCameraWorld (Main_Calibration/correspondencer.cpp:5-39) for n marker
+ *        poses (rvec | tvec): corners[n][4][3] in the order top left, top right, bottom right, bottom left.
+ *      ba_cuda_compose_poses: out = a o b (marker-from-camera = base o marker-from-base, correspondencer.cpp:141-146) or, with
+ *        invert_b, out = a o b^-1 (base-from-camera from another marker of the object, correspondencer.cpp:118-121).
+ *      The before-BA reprojection error (correspondencer.cpp:284-339) is ba_cuda_project_points_error on those corners. ---- */
+int ba_cuda_marker_corners(ba_cuda_problem* p, int64_t n, const double* rvec_tvec6, double marker_side, double* corners);
+int ba_cuda_compose_poses(ba_cuda_problem* p, int64_t n, const double* a6, const double* b6, int32_t invert_b, double* out6);
+
 double ba_cuda_last_kernel_ms(const ba_cuda_problem* p);
 
 /* Reprojection check, the numeric part of ReprojectionCheck::Reproject

@@ -1298,6 +1298,88 @@ __global__ void k_rodrigues_cv(const double* __restrict__ rt6, int n, double* __
   }
 }
 
+// ---- the numeric part of the correspondence stage (Main_Calibration/correspondencer.cpp) ----------------
+__device__ __forceinline__ void rodrigues_cv_dev(const double* r, double* R) {   // cv::Rodrigues, vector -> matrix
+  const double theta = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  if (theta < DBL_EPSILON) {
+#pragma unroll
+    for (int q = 0; q < 9; ++q) R[q] = (q % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  const double c = cos(theta), s = sin(theta), c1 = 1.0 - c, it = 1.0 / theta;
+  const double k0 = r[0] * it, k1 = r[1] * it, k2 = r[2] * it;
+  R[0] = c + c1 * k0 * k0;      R[1] = c1 * k0 * k1 - s * k2; R[2] = c1 * k0 * k2 + s * k1;
+  R[3] = c1 * k0 * k1 + s * k2; R[4] = c + c1 * k1 * k1;      R[5] = c1 * k1 * k2 - s * k0;
+  R[6] = c1 * k0 * k2 - s * k1; R[7] = c1 * k1 * k2 + s * k0; R[8] = c + c1 * k2 * k2;
+}
+__device__ __forceinline__ void rodrigues_inv_cv_dev(const double* R, double* r) {   // cv::Rodrigues, matrix -> vector
+  double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+  const double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+  const double c = fmin(fmax((R[0] + R[4] + R[8] - 1.0) * 0.5, -1.0), 1.0);
+  double theta = acos(c);
+  if (s < 1e-5) {
+    if (c > 0.0) { r[0] = r[1] = r[2] = 0.0; return; }
+    double t = (R[0] + 1.0) * 0.5;
+    rx = sqrt(fmax(t, 0.0));
+    t = (R[4] + 1.0) * 0.5;
+    ry = sqrt(fmax(t, 0.0)) * (R[1] < 0.0 ? -1.0 : 1.0);
+    t = (R[8] + 1.0) * 0.5;
+    rz = sqrt(fmax(t, 0.0)) * (R[2] < 0.0 ? -1.0 : 1.0);
+    if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && (R[5] > 0.0) != (ry * rz > 0.0)) rz = -rz;
+    theta /= sqrt(rx * rx + ry * ry + rz * rz);
+    r[0] = rx * theta; r[1] = ry * theta; r[2] = rz * theta;
+  } else {
+    const double vth = theta / (2.0 * s);
+    r[0] = rx * vth; r[1] = ry * vth; r[2] = rz * vth;
+  }
+}
+// Correspondencer::GetCornersInCameraWorld (correspondencer.cpp:5-39): t -+ E +- F with E, F = half side x the first two columns of R
+__global__ void k_marker_corners(int64_t n, const double* __restrict__ rt6, double half, double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double R[9];
+  rodrigues_cv_dev(rt6 + 6 * i, R);
+  const double E[3] = {R[0] * half, R[3] * half, R[6] * half}, F[3] = {R[1] * half, R[4] * half, R[7] * half};
+  const double* t = rt6 + 6 * i + 3;
+  double* o = out + 12 * i;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    o[k] = t[k] + (-E[k] + F[k]);       // top left
+    o[3 + k] = t[k] + (E[k] + F[k]);    // top right
+    o[6 + k] = t[k] + (E[k] - F[k]);    // bottom right
+    o[9 + k] = t[k] + (-E[k] - F[k]);   // bottom left
+  }
+}
+// pose composition of correspondencer.cpp:100-149: out = a o b (R = Ra Rb, t = Ra tb + ta; :141-146) or, invert_b,
+// out = a o b^-1 (R = Ra Rb^T, t = Ra Rb^T (-tb) + ta; :118-121)
+__global__ void k_compose_poses(int64_t n, const double* __restrict__ a6, const double* __restrict__ b6, int invert_b, double* __restrict__ out6) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double Ra[9], Rb[9], R[9];
+  rodrigues_cv_dev(a6 + 6 * i, Ra);
+  rodrigues_cv_dev(b6 + 6 * i, Rb);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v += Ra[3 * r + k] * (invert_b ? Rb[3 * c + k] : Rb[3 * k + c]);
+      R[3 * r + c] = v;
+    }
+  const double* ta = a6 + 6 * i + 3;
+  const double* tb = b6 + 6 * i + 3;
+  double* o = out6 + 6 * i;
+  rodrigues_inv_cv_dev(R, o);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double v = 0.0;
+    if (invert_b) { for (int k = 0; k < 3; ++k) v += R[3 * r + k] * (-tb[k]); }
+    else { for (int k = 0; k < 3; ++k) v += Ra[3 * r + k] * tb[k]; }
+    o[3 + r] = v + ta[r];
+  }
+}
+
 // cv::projectPoints with zero distortion, then ((x^ - x)^2 + (y^ - y)^2) / 2 (reprojection_check.cpp:81)
 __global__ void __launch_bounds__(256)
 k_project_error(int64_t n, const double* __restrict__ xyz, const int32_t* __restrict__ cam, const double* __restrict__ R9,
@@ -1943,6 +2025,30 @@ int ba_cuda_model_b_outputs(ba_cuda_problem* p, double* rot9, double* inv12, dou
   if (inv12) BA_CUDA_TRY(cudaMemcpyAsync(inv12, d_inv.p, d_inv.bytes(), cudaMemcpyDeviceToHost, st));
   if (corners && S.nb) BA_CUDA_TRY(cudaMemcpyAsync(corners, d_c.p, d_c.bytes(), cudaMemcpyDeviceToHost, st));
   BA_CUDA_TRY(cudaStreamSynchronize(st));
+  return BA_OK;
+}
+
+int ba_cuda_marker_corners(ba_cuda_problem* p, int64_t n, const double* rvec_tvec6, double marker_side, double* corners) {
+  if (!p || n < 0 || (n > 0 && (!rvec_tvec6 || !corners))) return fail(BA_ERR_INVALID_ARGUMENT, "ba_cuda_marker_corners: bad arguments");
+  BA_TRY(use_device(p));
+  DVec<double> d_in, d_out;
+  BA_TRY(d_in.upload(rvec_tvec6, 6 * (size_t)n, p->st)); BA_TRY(d_out.alloc(12 * (size_t)n));
+  if (n > 0) BA_LAUNCH(p, KT_MISC, k_marker_corners, grid_for(n, 128), 128, 0, n, d_in.p, marker_side / 2, d_out.p);
+  BA_CUDA_TRY(cudaGetLastError());
+  if (n > 0) BA_CUDA_TRY(cudaMemcpyAsync(corners, d_out.p, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, p->st));
+  BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+  return BA_OK;
+}
+
+int ba_cuda_compose_poses(ba_cuda_problem* p, int64_t n, const double* a6, const double* b6, int32_t invert_b, double* out6) {
+  if (!p || n < 0 || (n > 0 && (!a6 || !b6 || !out6))) return fail(BA_ERR_INVALID_ARGUMENT, "ba_cuda_compose_poses: bad arguments");
+  BA_TRY(use_device(p));
+  DVec<double> d_a, d_b, d_out;
+  BA_TRY(d_a.upload(a6, 6 * (size_t)n, p->st)); BA_TRY(d_b.upload(b6, 6 * (size_t)n, p->st)); BA_TRY(d_out.alloc(6 * (size_t)n));
+  if (n > 0) BA_LAUNCH(p, KT_MISC, k_compose_poses, grid_for(n, 128), 128, 0, n, d_a.p, d_b.p, invert_b ? 1 : 0, d_out.p);
+  BA_CUDA_TRY(cudaGetLastError());
+  if (n > 0) BA_CUDA_TRY(cudaMemcpyAsync(out6, d_out.p, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, p->st));
+  BA_CUDA_TRY(cudaStreamSynchronize(p->st));
   return BA_OK;
 }
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "ba_cuda_project_points_error", "ba_cuda_model_b_outputs", "ba_cuda_solve_begin", "ba_cuda_solve_iterate",
     "ba_cuda_solve_end", "ba_cuda_set_stream", "ba_cuda_get_kernel_stats", "ba_cuda_num_launches", "ba_cuda_reset_stats",
     "ba_cuda_save_parameters", "ba_cuda_restore_parameters", "ba_cuda_project_points_error_rt",
-    "ba_cuda_release_cached_memory",
+    "ba_cuda_release_cached_memory", "ba_cuda_marker_corners", "ba_cuda_compose_poses",
 ]
 
 
@@ -226,6 +226,20 @@ class Problem:
                                                   K.ctypes, img.ctypes, C.byref(err), C.byref(rms),
                                                   None if rep is None else rep.ctypes.data_as(C.c_void_p)))
         return err.value, rms.value, rep
+
+    def marker_corners(self, rvec_tvec6, marker_side):
+        """Correspondencer::GetCornersInCameraWorld for n poses -> [n, 4, 3] (top left, top right, bottom right, bottom left)."""
+        rt = np.ascontiguousarray(rvec_tvec6, np.float64).reshape(-1, 6)
+        out = np.zeros((rt.shape[0], 4, 3))
+        _check(lib().ba_cuda_marker_corners(self._h, C.c_int64(rt.shape[0]), rt.ctypes, C.c_double(marker_side), out.ctypes))
+        return out
+
+    def compose_poses(self, a6, b6, invert_b=False):
+        """out = a o b, or a o b^-1 (rvec | tvec rows, cv::Rodrigues conventions)."""
+        a = np.ascontiguousarray(a6, np.float64).reshape(-1, 6); b = np.ascontiguousarray(b6, np.float64).reshape(-1, 6)
+        out = np.zeros_like(a)
+        _check(lib().ba_cuda_compose_poses(self._h, C.c_int64(a.shape[0]), a.ctypes, b.ctypes, C.c_int32(1 if invert_b else 0), out.ctypes))
+        return out
 
     def model_b_outputs(self):
         rot = np.zeros((self.n_cam, 9)); inv = np.zeros((self.n_cam, 12)); corners = np.zeros((self.n_obs * 4, 3))

@@ -579,3 +579,55 @@ def test_point_with_more_than_64_observations_takes_the_generic_pipeline(gpu, or
     assert s.path_used == abi.PATH_GENERIC
     _check_rows(rows, rows_o)
     assert np.abs(x - xo).max() < POSE_ATOL
+
+
+# ---- the numeric part of the correspondence stage --------------------------------------------------------
+def test_correspondence_stage_pose_algebra_vs_opencv(gpu):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(8)
+    n = 500
+    a = np.concatenate([rng.normal(0, 1.2, (n, 3)), rng.normal(0, 0.3, (n, 3))], 1)
+    b = np.concatenate([rng.normal(0, 1.2, (n, 3)), rng.normal(0, 0.3, (n, 3))], 1)
+    a[0, :3] = 0.0; b[1, :3] = 0.0                      # identity rotations
+    a[2, :3] = b[2, :3]                                   # a o b^-1 = identity rotation
+    a[3, :3] = [np.pi - 1e-7, 0.0, 0.0]; b[3, :3] = 0.0   # rotation by (almost) pi: the s < 1e-5 branch of cv::Rodrigues
+    side = 0.0148
+    # Correspondencer::GetCornersInCameraWorld (correspondencer.cpp:5-39)
+    got = gpu.marker_corners(a, side)
+    h = side / 2
+    for i in range(n):
+        R = cv2.Rodrigues(a[i, :3])[0]
+        E, Fv, t = R[:, 0] * h, R[:, 1] * h, a[i, 3:]
+        ref = np.stack([t - E + Fv, t + E + Fv, t + E - Fv, t - E - Fv])
+        assert np.abs(got[i] - ref).max() < 1e-14
+    # pose composition (correspondencer.cpp:118-121 and :141-146), rotation vectors through cv::Rodrigues both ways
+    for inv in (False, True):
+        out = gpu.compose_poses(a, b, inv)
+        for i in range(n):
+            Ra, Rb = cv2.Rodrigues(a[i, :3])[0], cv2.Rodrigues(b[i, :3])[0]
+            R = Ra @ (Rb.T if inv else Rb)
+            t = R @ (-b[i, 3:]) + a[i, 3:] if inv else Ra @ b[i, 3:] + a[i, 3:]
+            assert np.abs(out[i, 3:] - t).max() < 1e-13
+            if i != 3:
+                assert np.abs(cv2.Rodrigues(out[i, :3])[0] - R).max() < 1e-12, (i, inv)
+                assert np.abs(out[i, :3] - cv2.Rodrigues(R)[0].ravel()).max() < 1e-9
+            else:   # within 1e-5 of pi cv::Rodrigues recovers the axis from the diagonal alone: both sides are good to ~1e-7 there
+                assert np.abs(cv2.Rodrigues(out[i, :3])[0] - R).max() < 1e-6
+                assert np.abs(np.abs(out[i, :3]) - np.abs(cv2.Rodrigues(R)[0].ravel())).max() < 1e-6
+
+
+def test_before_ba_reprojection_error_from_the_initial_guess(gpu):
+    # correspondencer.cpp:284-339 on the committed hongo file: marker-from-base-camera poses composed from the frame and marker
+    # blocks, corners by GetCornersInCameraWorld, projected through the initial camera poses: the "Reprojection Error (Before BA)"
+    # is the cost of row 0 of the solve (same corners, same projection, same ((dx)^2 + (dy)^2) / 2)
+    pb, intr, side, fix0 = H.hongo()
+    C, T, M = pb.n_cam, pb.n_time, pb.n_marker
+    cams = pb.params[:6 * C].reshape(C, 6)
+    frames = pb.params[6 * C:6 * (C + T)].reshape(T, 6)
+    markers = pb.params[6 * (C + T):].reshape(M, 6)
+    pose = gpu.compose_poses(frames[pb.time_idx], markers[pb.marker_idx])          # base o marker-from-base
+    corners = gpu.marker_corners(pose, side).reshape(-1, 3)
+    cam_of_point = np.repeat(pb.cam_idx, 4)
+    img = pb.obs8.reshape(-1, 2).astype(np.float32)
+    err, rms, _ = gpu.project_points_error(corners, cam_of_point, cams, intr, img)
+    assert H.rel(err, H.HONGO_COSTS[0]) < 1e-9
