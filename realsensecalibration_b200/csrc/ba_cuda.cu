@@ -393,7 +393,7 @@ int run_normal_parts(ba_cuda_problem* p) {
   BA_LAUNCH(p, KT_SEGFIN, (k_seg_final<NV_F>), grid_for(S.nf, 4), 128, 0, (int)S.nf, S.ch_fobs.seg_first.p, p->part_fobs.p, p->HG.p);
   BA_LAUNCH(p, KT_EM, (k_e_M<RD, DE, GE>), grid_for(S.ne * GE, 128), 128, 0, S.ne, S.e_ptr.p, p->RES.p, p->JE.p, p->ME.p);
   if (p->model == 1) {
-    BA_LAUNCH(p, KT_INCW, (k_inc_W<RD>), grid_for(S.ninc * 8, 128), 128, 0, S.ninc, S.incobs_ptr.p, S.incobs.p, p->JE.p, p->JF0.p,
+    BA_LAUNCH(p, KT_INCW, (k_inc_W<RD>), grid_for(S.ninc * RD, 128), 128, 0, S.ninc, S.incobs_ptr.p, S.incobs.p, p->JE.p, p->JF0.p,
               p->JF1.p, p->Wt.p);
     if (S.ch_dobs.n > 0)
       BA_LAUNCH(p, KT_DOBS, (k_dobs_partial<RD>), grid_for(S.ch_dobs.n, 4), 128, 0, S.ch_dobs.n, S.ch_dobs.ch, S.ch_dobs.seg.p,
@@ -522,7 +522,7 @@ int compute_step(ba_cuda_problem* p, const ba_cuda_options& opt) {
   fam_begin(p, F_UPDATE);
   BA_LAUNCH(p, KT_BACKSUB, (k_e_backsub<DE, GE>), grid_for(S.ne * GE, 128), 128, 0, S.ne, S.einc_ptr, S.inc_f, p->Yt.p, p->Lb.p, p->zb.p,
             p->yf.p, p->ye.p);
-  const int gm = (int)grid_for(S.nb, 256);
+  const int gm = (int)grid_for(S.nb * RD, 256);   // one thread per residual row
   BA_LAUNCH(p, KT_MODELCOST, (k_model_cost<RD, DE, NSLOT>), gm, 256, 0, S.nb, S.ob_e.p, S.ob_f0.p, S.ob_f1.p, p->RES.p, p->JE.p, p->JF0.p,
             p->JF1.p, p->ye.p, p->yf.p, p->bp0.p);
   BA_TRY(fold(p, p->bp0.p, gm, S_MCC));

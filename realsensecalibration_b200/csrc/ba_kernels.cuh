@@ -393,40 +393,43 @@ k_cost_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict
 // ---------------------------------------------------------------------------------------
 // K2: generic over RD (residuals / obs), DE (size of the eliminated block).
 // ---------------------------------------------------------------------------------------
-// F^T F diagonal block (packed 21) and F^T r (6) of one f-block, chunk partials.  One warp per chunk.
+// F^T F diagonal block (packed 21) and F^T r (6) of one f-block, chunk partials.  One warp per chunk; a lane owns one
+// residual row of one observation (32 / RD observations per step), so a warp reads whole 48-byte rows side by side.
+__device__ __forceinline__ void load_row6(const double* __restrict__ p, double* row) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { const double2 v = q[k]; row[2 * k] = v.x; row[2 * k + 1] = v.y; }
+}
 template <int RD>
 __global__ void __launch_bounds__(128)
 k_fobs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_begin,
                const int64_t* __restrict__ fobs_ptr, const int32_t* __restrict__ fobs, const double* __restrict__ RES,
                const double* __restrict__ JF0, const double* __restrict__ JF1, double* __restrict__ partial) {
+  static_assert(32 % RD == 0, "rows of an observation share a warp");
+  constexpr int OPW = 32 / RD;
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= nchunks) return;
+  const int sub = lane / RD, rr = lane % RD;
   const int64_t begin = chunk_begin[c];
   const int64_t end = min(begin + ch, fobs_ptr[chunk_seg[c] + 1]);
   double acc[NV_F];
 #pragma unroll
   for (int k = 0; k < NV_F; ++k) acc[k] = 0.0;
-  for (int64_t idx = begin + lane; idx < end; idx += 32) {
+#pragma unroll 2
+  for (int64_t idx = begin + sub; idx < end; idx += OPW) {
     const int32_t ent = fobs[idx];
     const int64_t o = ent >> 1;
-    const double* J = ((ent & 1) ? JF1 : JF0) + (int64_t)RD * 6 * o;
-    const double* r = RES + (int64_t)RD * o;
+    double row[6];
+    load_row6(((ent & 1) ? JF1 : JF0) + ((int64_t)RD * o + rr) * 6, row);
+    const double rv = RES[(int64_t)RD * o + rr];
+    int q = 0;
 #pragma unroll
-    for (int rr = 0; rr < RD; ++rr) {
-      double row[6];
-      const double2* p = reinterpret_cast<const double2*>(J + 6 * rr);
+    for (int a = 0; a < 6; ++a)
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { const double2 v = p[k]; row[2 * k] = v.x; row[2 * k + 1] = v.y; }
-      const double rv = r[rr];
-      int q = 0;
+      for (int b = a; b < 6; ++b) { acc[q] = fma(row[a], row[b], acc[q]); ++q; }
 #pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int b = a; b < 6; ++b) acc[q++] += row[a] * row[b];
-#pragma unroll
-      for (int a = 0; a < 6; ++a) acc[21 + a] += row[a] * rv;
-    }
+    for (int a = 0; a < 6; ++a) acc[21 + a] = fma(row[a], rv, acc[21 + a]);
   }
 #pragma unroll
   for (int k = 0; k < NV_F; ++k) {
@@ -464,6 +467,25 @@ k_e_M(int64_t ne, const int64_t* __restrict__ e_ptr, const double* __restrict__ 
   double acc[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+  if constexpr (G >= RD && G % RD == 0 && DE == 6) {
+    // a lane owns one residual row; G / RD observations per step, rows read side by side
+    const int sub = g / RD, rr = g % RD;
+    if (live) {
+#pragma unroll 2
+      for (int64_t o = e_ptr[e] + sub; o < e_ptr[e + 1]; o += G / RD) {
+        double row[6];
+        load_row6(JE + ((int64_t)RD * o + rr) * 6, row);
+        const double rv = RES[(int64_t)RD * o + rr];
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int b = a; b < 6; ++b) { acc[q] = fma(row[a], row[b], acc[q]); ++q; }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc[NU + a] = fma(row[a], rv, acc[NU + a]);
+      }
+    }
+  } else
   if (live) {
     for (int64_t o = e_ptr[e] + g; o < e_ptr[e + 1]; o += G) {
       const double* J = JE + (int64_t)RD * DE * o;
@@ -496,12 +518,14 @@ k_e_M(int64_t ne, const int64_t* __restrict__ e_ptr, const double* __restrict__ 
   }
 }
 
-// Model B: W_i^T = sum over the observations of incidence i of JE^T JF  (6 x 6, k-major).  8 lanes per incidence.
+// Model B: W_i^T = sum over the observations of incidence i of JE^T JF  (6 x 6, k-major).  RD lanes per incidence, a lane
+// owns one residual row: the group walks the incidence's observations one at a time and reads both 384-byte records whole.
 template <int RD>
 __global__ void __launch_bounds__(128)
 k_inc_W(int64_t ninc, const int64_t* __restrict__ incobs_ptr, const int32_t* __restrict__ incobs, const double* __restrict__ JE,
         const double* __restrict__ JF0, const double* __restrict__ JF1, double* __restrict__ Wt) {
-  constexpr int G = 8;
+  static_assert(32 % RD == 0, "one lane per residual row, a group inside a warp");   // launched for Model B only (RD = 8)
+  constexpr int G = RD;
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t i = t / G;
   const int g = (int)(t % G);
@@ -510,21 +534,18 @@ k_inc_W(int64_t ninc, const int64_t* __restrict__ incobs_ptr, const int32_t* __r
 #pragma unroll
   for (int k = 0; k < 36; ++k) acc[k] = 0.0;
   if (live) {
-    for (int64_t q = incobs_ptr[i] + g; q < incobs_ptr[i + 1]; q += G) {
+    const int64_t q1 = incobs_ptr[i + 1];
+#pragma unroll 2
+    for (int64_t q = incobs_ptr[i]; q < q1; ++q) {
       const int32_t ent = incobs[q];
-      const int64_t o = ent >> 1;
-      const double* Je = JE + (int64_t)RD * 6 * o;
-      const double* Jf = ((ent & 1) ? JF1 : JF0) + (int64_t)RD * 6 * o;
+      const int64_t row = (int64_t)RD * (ent >> 1) + g;
+      double re[6], rf[6];
+      load_row6(JE + row * 6, re);
+      load_row6(((ent & 1) ? JF1 : JF0) + row * 6, rf);
 #pragma unroll
-      for (int rr = 0; rr < RD; ++rr) {
-        double re[6], rf[6];
+      for (int k = 0; k < 6; ++k)
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { re[k] = Je[rr * 6 + k]; rf[k] = Jf[rr * 6 + k]; }
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-#pragma unroll
-          for (int a = 0; a < 6; ++a) acc[k * 6 + a] += re[k] * rf[a];
-      }
+        for (int a = 0; a < 6; ++a) acc[k * 6 + a] = fma(re[k], rf[a], acc[k * 6 + a]);
     }
   }
 #pragma unroll
@@ -649,71 +670,72 @@ k_finc_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const
 }
 
 // sum over incidence pairs (i,j) of Y_i Y_j^T = Yt_i^T Yt_j for one destination block, chunk partials (36 values).
+// One warp per chunk; a lane owns one row k of the two Yt records of a pair (groups of 8 lanes, or 4 when DE <= 4).
 template <int DE>
 __global__ void __launch_bounds__(128)
 k_pairs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_begin,
                 const int64_t* __restrict__ dpair_ptr, const int2* __restrict__ pairs, const double* __restrict__ Yt,
                 double* __restrict__ partial) {
+  constexpr int G = DE <= 4 ? 4 : 8;
+  static_assert(DE <= G, "one lane per row of Yt");
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= nchunks) return;
+  const int sub = lane / G, k = lane % G;
   const int64_t begin = chunk_begin[c];
   const int64_t end = min(begin + ch, dpair_ptr[chunk_seg[c] + 1]);
   double acc[36];
 #pragma unroll
-  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-  for (int64_t idx = begin + lane; idx < end; idx += 32) {
-    const int2 pr = pairs[idx];
-    if (pr.x < 0) continue;
-    const double2* pi = reinterpret_cast<const double2*>(Yt + (int64_t)DE * 6 * pr.x);
-    const double2* pj = reinterpret_cast<const double2*>(Yt + (int64_t)DE * 6 * pr.y);
-#pragma unroll
-    for (int k = 0; k < DE; ++k) {
+  for (int q = 0; q < 36; ++q) acc[q] = 0.0;
+  if (k < DE) {
+#pragma unroll 2
+    for (int64_t idx = begin + sub; idx < end; idx += 32 / G) {
+      const int2 pr = pairs[idx];
+      if (pr.x < 0) continue;
       double yi[6], yj[6];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const double2 u = pi[3 * k + q], w = pj[3 * k + q];
-        yi[2 * q] = u.x; yi[2 * q + 1] = u.y; yj[2 * q] = w.x; yj[2 * q + 1] = w.y;
-      }
+      load_row6(Yt + ((int64_t)DE * pr.x + k) * 6, yi);
+      load_row6(Yt + ((int64_t)DE * pr.y + k) * 6, yj);
 #pragma unroll
       for (int a = 0; a < 6; ++a)
 #pragma unroll
-        for (int b = 0; b < 6; ++b) acc[a * 6 + b] += yi[a] * yj[b];
+        for (int b = 0; b < 6; ++b) acc[a * 6 + b] = fma(yi[a], yj[b], acc[a * 6 + b]);
     }
   }
 #pragma unroll
-  for (int k = 0; k < 36; ++k) {
-    const double s = warp_sum(acc[k]);
-    if (lane == 0) partial[(int64_t)c * 36 + k] = s;
+  for (int q = 0; q < 36; ++q) {
+    const double s = warp_sum(acc[q]);
+    if (lane == 0) partial[(int64_t)c * 36 + q] = s;
   }
 }
 
-// Model B: sum over observations with (f0,f1) == (fa,fb) of JF0^T JF1, chunk partials (36 values).
+// Model B: sum over observations with (f0,f1) == (fa,fb) of JF0^T JF1, chunk partials (36 values).  One warp per chunk,
+// a lane owns one residual row of one observation.
 template <int RD>
 __global__ void __launch_bounds__(128)
 k_dobs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_begin,
                const int64_t* __restrict__ dobs_ptr, const int32_t* __restrict__ dobs, const double* __restrict__ JF0,
                const double* __restrict__ JF1, double* __restrict__ partial) {
+  static_assert(32 % RD == 0, "rows of an observation share a warp");
+  constexpr int OPW = 32 / RD;
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= nchunks) return;
+  const int sub = lane / RD, rr = lane % RD;
   const int64_t begin = chunk_begin[c];
   const int64_t end = min(begin + ch, dobs_ptr[chunk_seg[c] + 1]);
   double acc[36];
 #pragma unroll
   for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-  for (int64_t idx = begin + lane; idx < end; idx += 32) {
-    const int64_t o = dobs[idx];
+#pragma unroll 2
+  for (int64_t idx = begin + sub; idx < end; idx += OPW) {
+    const int64_t row = (int64_t)RD * dobs[idx] + rr;
+    double ra[6], rb[6];
+    load_row6(JF0 + row * 6, ra);
+    load_row6(JF1 + row * 6, rb);
 #pragma unroll
-    for (int rr = 0; rr < RD; ++rr) {
-      double ra[6], rb[6];
+    for (int a = 0; a < 6; ++a)
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { ra[k] = JF0[(int64_t)RD * 6 * o + rr * 6 + k]; rb[k] = JF1[(int64_t)RD * 6 * o + rr * 6 + k]; }
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int b = 0; b < 6; ++b) acc[a * 6 + b] += ra[a] * rb[b];
-    }
+      for (int b = 0; b < 6; ++b) acc[a * 6 + b] = fma(ra[a], rb[b], acc[a * 6 + b]);
   }
 #pragma unroll
   for (int k = 0; k < 36; ++k) {
@@ -798,7 +820,8 @@ k_e_backsub(int64_t ne, const int64_t* __restrict__ einc_ptr, const int32_t* __r
   }
 }
 
-// model_cost_change partials: with step = -y,  sum_o (J step) . (r + J step / 2)   (the caller negates)
+// model_cost_change partials: with step = -y,  sum_o (J step) . (r + J step / 2)   (the caller negates).
+// One thread per residual row: consecutive lanes read consecutive rows of JE / JF0 / JF1.
 template <int RD, int DE, int NSLOT>
 __global__ void __launch_bounds__(256)
 k_model_cost(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const int32_t* __restrict__ ob_f1,
@@ -806,30 +829,29 @@ k_model_cost(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __rest
              const double* __restrict__ JF1, const double* __restrict__ ye, const double* __restrict__ yf,
              double* __restrict__ partial) {
   __shared__ double sm[32];
-  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t o = row / RD;
   double acc = 0.0;
   if (o < nb) {
-    double se_[DE], s0[6], s1[6];
     const int64_t e = ob_e[o];
-#pragma unroll
-    for (int k = 0; k < DE; ++k) se_[k] = -ye[e * DE + k];
     const int32_t f0 = ob_f0[o];
     const int32_t f1 = NSLOT == 2 ? ob_f1[o] : -1;
+    double m = 0.0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { s0[k] = f0 >= 0 ? -yf[6 * (int64_t)f0 + k] : 0.0; s1[k] = f1 >= 0 ? -yf[6 * (int64_t)f1 + k] : 0.0; }
+    for (int k = 0; k < DE; ++k) m = fma(JE[row * DE + k], -ye[e * DE + k], m);
+    if (f0 >= 0) {
+      double j[6];
+      load_row6(JF0 + row * 6, j);
 #pragma unroll
-    for (int rr = 0; rr < RD; ++rr) {
-      double m = 0.0;
-#pragma unroll
-      for (int k = 0; k < DE; ++k) m += JE[(int64_t)RD * DE * o + rr * DE + k] * se_[k];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) m += JF0[(int64_t)RD * 6 * o + rr * 6 + k] * s0[k];
-      if (NSLOT == 2) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) m += JF1[(int64_t)RD * 6 * o + rr * 6 + k] * s1[k];
-      }
-      acc += m * (RES[(int64_t)RD * o + rr] + m / 2.0);
+      for (int k = 0; k < 6; ++k) m = fma(j[k], -yf[6 * (int64_t)f0 + k], m);
     }
+    if (NSLOT == 2 && f1 >= 0) {
+      double j[6];
+      load_row6(JF1 + row * 6, j);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) m = fma(j[k], -yf[6 * (int64_t)f1 + k], m);
+    }
+    acc = m * (RES[row] + m / 2.0);
   }
   acc = block_sum(acc, sm);
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
