@@ -170,7 +170,8 @@ typedef struct ba_cuda_summary {
 typedef enum ba_path {
   BA_PATH_GENERIC = 0,
   BA_PATH_FUSED_TILES = 1,
-  BA_PATH_FUSED_STRIPS = 2
+  BA_PATH_FUSED_STRIPS = 2,
+  BA_PATH_RIG = 3            /* rig-size problems: the whole trust-region loop in one launch of one CTA (ba_rig.cuh) */
 } ba_path;
 
 void ba_cuda_options_init(ba_cuda_options* options);

@@ -8,7 +8,7 @@ CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
  REASON_MIN_TRUST_REGION_RADIUS, REASON_MAX_ITERATIONS, REASON_TOO_MANY_INVALID_STEPS,
  REASON_INITIAL_EVALUATION_FAILED) = range(8)
 UNIQUE_ID_BYTES = 128
-PATH_GENERIC, PATH_FUSED_TILES, PATH_FUSED_STRIPS = 0, 1, 2
+PATH_GENERIC, PATH_FUSED_TILES, PATH_FUSED_STRIPS, PATH_RIG = 0, 1, 2, 3
 LOSS_NONE, LOSS_HUBER, LOSS_CAUCHY = 0, 1, 2
 
 

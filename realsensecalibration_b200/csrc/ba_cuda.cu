@@ -22,6 +22,7 @@
 #include "ba_fused_a.cuh"
 #include "ba_strip_a.cuh"
 #include "ba_exchange.cuh"
+#include "ba_rig.cuh"
 
 using namespace ba;
 
@@ -71,13 +72,13 @@ enum Family { F_JAC = 0, F_SCHUR, F_SOLVE, F_UPDATE, F_COST, F_COLL, F_COUNT };
 // one entry per kernel (family member) of the solve path; names are what ba_cuda_get_kernel_stats() reports
 enum KT {
   KT_TABLES = 0, KT_JAC, KT_COST, KT_FOBS, KT_EM, KT_INCW, KT_DOBS, KT_ECHOL, KT_INCY, KT_FINC, KT_PAIRS, KT_SEGFIN,
-  KT_ASSEMBLE, KT_RCS, KT_BACKSUB, KT_MODELCOST, KT_CANDIDATE, KT_GRADNORM, KT_FOLD, KT_MISC, KT_FA_P1, KT_FA_RED, KT_FA_P2, KT_FA_P1L, KT_COUNT
+  KT_ASSEMBLE, KT_RCS, KT_BACKSUB, KT_MODELCOST, KT_CANDIDATE, KT_GRADNORM, KT_FOLD, KT_MISC, KT_FA_P1, KT_FA_RED, KT_FA_P2, KT_FA_P1L, KT_RIG, KT_COUNT
 };
 const char* const kKtName[KT_COUNT] = {
   "k1_tables", "k1_residual_jacobian", "k5_cost", "k2_fobs_partial", "k2_e_normal", "k2_inc_w", "k2_dobs_partial",
   "k2_e_cholesky", "k2_inc_y", "k2_finc_partial", "k2_pairs_partial", "k2_seg_final", "k2_assemble", "k3_rcs_solve",
   "k4_backsub", "k4_model_cost", "k4_candidate", "k4_gradient_norm", "fold_partials", "misc",
-  "k1k2_fused_pass1", "k2_reduce_items", "k4k5_fused_pass2", "k1_fused_pass1_light"};
+  "k1k2_fused_pass1", "k2_reduce_items", "k4k5_fused_pass2", "k1_fused_pass1_light", "rig_lm_whole_loop"};
 }  // namespace
 
 struct LmState {  // TrustRegionMinimizer's loop variables, kept between ba_cuda_solve_iterate() calls
@@ -87,6 +88,8 @@ struct LmState {  // TrustRegionMinimizer's loop variables, kept between ba_cuda
   int num_invalid = 0;
   bool began = false, go = false;
   bool need_linearize = false;  // fused Model A path: the Schur system must be re-formed (new radius after a rejection)
+  bool rig = false;             // the whole loop runs in k_rig_lm (ba_rig.cuh)
+  bool rig_begin_pending = false;   // ba_cuda_solve: iteration zero rides in the first (only) launch
 };
 
 struct ba_cuda_problem {
@@ -122,6 +125,10 @@ struct ba_cuda_problem {
   StripA SA;                 // Model A: strip structure of pass 1 (ba_strip_a.cuh); FA then only carries the tiles of pass 2 / k_fa_jac
   bool use_fused = false, use_strip = false, generic_ws = false;
   bool smem_attr_set = false;   // the opt-in shared-memory sizes are per device: set once per problem
+  bool rig_attr_set = false;
+  bool one_shot = false;        // inside ba_cuda_solve: nobody looks at row 0 before the loop runs
+  DVec<unsigned char> rig_buf;  // RigState | rows of one launch
+  unsigned char* h_rig = nullptr;   // pinned mirror
   SparseExchange SX;            // multi-GPU, fused Model A + PCG: all-gather of the ranks' own blocks instead of an all-reduce of all
   LossSpec loss{0, 1.0};        // robust loss of the current solve (options.loss_function / loss_scale); 0 outside a solve
   DVec<double> fa_part;      // 7 per-tile partial arrays (cost, g2, gmax, mcc, x2, d2, cand)
@@ -984,6 +991,86 @@ void lm_read_gradient(ba_cuda_problem* p) {
   L.gnorm = std::sqrt(p->h_scal[S_G2E] + p->h_scal[S_G2F]);
 }
 
+// ---- the rig-size path (ba_rig.cuh): one CTA runs the whole loop ---------------------------------------------
+int ensure_generic_workspace(ba_cuda_problem* p);
+bool rig_eligible(const ba_cuda_problem* p, const ba_cuda_options& opt) {
+  const bool on = env_int("BA_RIG", 0, 1, 1) != 0;   // read per solve: tests run both machines in one process
+  const int64_t rows = p->S.nb * (p->model == 0 ? 2 : 8);
+  return on && p->world == 1 && !opt.force_generic_path && p->solver == BA_RCS_DENSE_CHOLESKY && p->n_rcs() <= RIG_MAX_N &&
+         rows <= RIG_MAX_ROWS;
+}
+
+template <int RD, int DE, int GE, int NSLOT>
+int rig_run(ba_cuda_problem* p, bool begin, int32_t max_new) {
+  LmState& L = p->lm;
+  const Structure& S = p->S;
+  const size_t buf_bytes = sizeof(RigState) + sizeof(ba_cuda_iteration) * RIG_ROWS_CAP;
+  if (p->rig_buf.n != buf_bytes) BA_TRY(p->rig_buf.alloc(buf_bytes));
+  if (!p->h_rig) BA_CUDA_TRY(cudaMallocHost((void**)&p->h_rig, buf_bytes));
+  const int n = (int)p->n_rcs();
+  const size_t smem = rig_smem_bytes(n);
+  if (!p->rig_attr_set) {
+    BA_CUDA_TRY(cudaFuncSetAttribute(k_rig_lm<RD, DE, GE, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rig_smem_bytes(RIG_MAX_N)));
+    p->rig_attr_set = true;
+  }
+  RigParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.nb = S.nb; P.ne = S.ne; P.nf = S.nf; P.ninc = S.ninc; P.ndest = S.ndest; P.n = n; P.ld = n | 1;
+  P.ob_e = S.ob_e.p; P.ob_f0 = S.ob_f0.p; P.ob_f1 = S.ob_f1.p; P.ob_cam = p->ob_cam.p; P.e_ptr = S.e_ptr.p;
+  P.inc_e = S.inc_e; P.inc_f = S.inc_f; P.einc_ptr = S.einc_ptr; P.incobs_ptr = S.incobs_ptr.p; P.incobs = S.incobs.p;
+  P.finc_ptr = S.finc_ptr.p; P.fobs_ptr = S.fobs_ptr.p; P.finc = S.finc.p; P.fobs = S.fobs.p;
+  P.dest_fa = S.dest_fa.p; P.dest_fb = S.dest_fb.p; P.dpair_ptr = S.dpair_ptr.p; P.pairs = S.pairs.p;
+  P.dobs_ptr = S.dobs_ptr.p; P.dobs = S.dobs.p; P.f_act_ptr = p->f_act_ptr.p;
+  P.uv = p->uv.p; P.obs8 = p->obs8.p; P.intr_f = p->intr_f.p; P.half_side = p->half_side;
+  P.xe = p->xe.p; P.xf = p->xf.p; P.xe_c = p->xe_c.p; P.xf_c = p->xf_c.p; P.se = p->se.p; P.sf = p->sf.p;
+  P.tab_f = p->tab_f.p; P.tab_e = p->tab_e.p; P.tabc_f = p->tabc_f.p; P.tabc_e = p->tabc_e.p;
+  P.RES = p->RES.p; P.JE = p->JE.p; P.JF0 = p->JF0.p; P.JF1 = p->JF1.p; P.ME = p->ME.p; P.HG = p->HG.p; P.Wt = p->Wt.p;
+  P.Qacc = p->Qacc.p; P.Lb = p->Lb.p; P.zb = p->zb.p; P.Yt = p->Yt.p; P.vb = p->vb.p; P.Pacc = p->Pacc.p; P.vsum = p->vsum();
+  P.yf = p->yf.p; P.ye = p->ye.p;
+  P.state = reinterpret_cast<RigState*>(p->rig_buf.p);
+  P.rows = reinterpret_cast<ba_cuda_iteration*>(p->rig_buf.p + sizeof(RigState));
+  P.opt = L.opt; P.loss = p->loss;
+  int64_t left = max_new;
+  bool first = begin;
+  while (first || (L.go && left > 0)) {
+    P.begin = first ? 1 : 0;
+    P.max_new = (int32_t)std::min<int64_t>(left, RIG_ROWS_CAP - P.begin);
+    P.rows_base = (int32_t)p->rows.size();
+    if (first) {
+      std::memset(&P.init, 0, sizeof(P.init));
+      P.init.radius = L.radius; P.init.decrease_factor = L.decrease_factor; P.init.go = 1;
+    }
+    BA_LAUNCH(p, KT_RIG, (k_rig_lm<RD, DE, GE, NSLOT>), 1, RIG_THREADS, smem, P);
+    BA_CUDA_TRY(cudaGetLastError());
+    BA_CUDA_TRY(cudaMemcpyAsync(p->h_rig, p->rig_buf.p, buf_bytes, cudaMemcpyDeviceToHost, p->st));
+    BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+    fam_collect(p);
+    const RigState& st = *reinterpret_cast<const RigState*>(p->h_rig);
+    const ba_cuda_iteration* rows = reinterpret_cast<const ba_cuda_iteration*>(p->h_rig + sizeof(RigState));
+    const int fresh = st.n_rows - P.rows_base;
+    for (int r = 0; r < fresh && r < RIG_ROWS_CAP; ++r) {
+      p->rows.push_back(rows[r]);
+      if (L.opt.minimizer_progress_to_stdout) {
+        const ba_cuda_iteration& row = rows[r];
+        if (row.iteration == 0) std::printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius\n");
+        std::printf("%4d % 14.6e % 10.2e % 10.2e % 10.2e % 10.2e % 10.2e\n", row.iteration, row.cost, row.cost_change,
+                    row.gradient_max_norm, row.step_norm, row.relative_decrease, row.trust_region_radius);
+      }
+    }
+    L.radius = st.radius; L.decrease_factor = st.decrease_factor; L.x_cost = st.x_cost; L.gmax = st.gmax; L.gnorm = st.gnorm;
+    L.num_invalid = st.num_invalid; L.go = st.go != 0;
+    ba_cuda_summary& Z = L.Z;
+    Z.num_jacobian_evaluations = st.n_jac; Z.num_linear_solves = st.n_solves; Z.num_cost_evaluations = st.n_solves;
+    Z.num_successful_steps = st.n_success; Z.num_unsuccessful_steps = st.n_unsuccess;
+    if (first) Z.initial_cost = st.n_rows > 0 ? p->rows.front().cost : st.x_cost;
+    Z.final_cost = st.x_cost;
+    if (!L.go) { Z.termination_type = st.term_type; Z.termination_reason = st.term_reason; }
+    left -= P.max_new;
+    first = false;
+  }
+  return BA_OK;
+}
+
 // TrustRegionMinimizer::IterationZero
 template <int RD, int DE, int GE, int NSLOT>
 int lm_begin(ba_cuda_problem* p, const ba_cuda_options& opt) {
@@ -1001,6 +1088,13 @@ int lm_begin(ba_cuda_problem* p, const ba_cuda_options& opt) {
   L.radius = opt.initial_trust_region_radius;
   L.decrease_factor = 2.0;
   L.began = true;
+  if (rig_eligible(p, opt)) {   // the reference's own problem sizes: the whole loop in one CTA
+    BA_TRY(ensure_generic_workspace(p));
+    L.rig = true;
+    L.Z.path_used = BA_PATH_RIG;
+    if (p->one_shot) { L.rig_begin_pending = true; L.go = true; return BA_OK; }
+    return rig_run<RD, DE, GE, NSLOT>(p, true, 0);
+  }
   const double iter_t0 = now_s();
   if (lm_fused(p)) {
     static const bool one_pass = env_int("BA_FA_FIRST", 0, 1, 1) != 0;
@@ -1039,6 +1133,11 @@ int lm_iterate(ba_cuda_problem* p, int32_t max_new) {
   const ba_cuda_options& opt = L.opt;
   ba_cuda_summary& Z = L.Z;
   ba_cuda_iteration row;
+  if (L.rig) {
+    const bool begin = L.rig_begin_pending;
+    L.rig_begin_pending = false;
+    return rig_run<RD, DE, GE, NSLOT>(p, begin, max_new);
+  }
   for (int32_t it = 0; L.go && it < max_new; ++it) {
     const double iter_t0 = now_s();
     std::memset(&row, 0, sizeof(row));
@@ -1513,6 +1612,7 @@ void ba_cuda_destroy(ba_cuda_problem* p) {
   if (p->copy_done) cudaEventDestroy(p->copy_done);
   if (p->h_scal) cudaFreeHost(p->h_scal);
   if (p->h_status) cudaFreeHost(p->h_status);
+  if (p->h_rig) cudaFreeHost(p->h_rig);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   cudaStream_t st = p->own_st, used = p->st;
   DevCache::current_stream() = used;
@@ -1795,7 +1895,10 @@ int ba_cuda_solve_end(ba_cuda_problem* p, ba_cuda_summary* summary) {
 }
 
 int ba_cuda_solve(ba_cuda_problem* p, const ba_cuda_options* options, ba_cuda_summary* summary) {
-  BA_TRY(ba_cuda_solve_begin(p, options));
+  if (p) p->one_shot = true;
+  const int rc_begin = ba_cuda_solve_begin(p, options);
+  if (p) p->one_shot = false;
+  BA_TRY(rc_begin);
   int32_t finished = 0;
   BA_TRY(ba_cuda_solve_iterate(p, INT32_MAX, &finished));
   return ba_cuda_solve_end(p, summary);

@@ -13,6 +13,9 @@
 //   Yt[i][DE][6]  (= L^-1 W_i^T, k-major)  v[i][6]               per incidence i = (e,f)
 //   tab[block][32] = R(9) | A = left Jacobian of SO(3) (9) | t(3) | fx fy ppx ppy (4) | small-angle flag | scale s(6)
 //
+// The item functions (d_*) are shared with the single-CTA rig kernel (ba_rig.cuh), which rewrites tables and Jacobians
+// inside one launch: no explicit __ldg here (the kernels' const __restrict__ parameters still get the read-only path).
+//
 // Every reduction is a fixed-shape tree over a list produced by a stable sort: no floating
 // point atomics anywhere, results are bitwise reproducible run to run.
 #pragma once
@@ -35,10 +38,8 @@ __device__ __forceinline__ int sym_idx6(int a, int b) { return a * 6 - a * (a - 
 // differentiates X + w x X, i.e. the derivative is -[X]x: flag = 1, A = I, and the kernels
 // use X in place of R X.
 // ---------------------------------------------------------------------------------------
-__global__ void k_tables(const double* __restrict__ x6, const double* __restrict__ intr4, const double* __restrict__ s6,
-                         int64_t n, double* __restrict__ tab) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ void d_tables(int64_t i, const double* __restrict__ x6, const double* __restrict__ intr4,
+                                         const double* __restrict__ s6, double* __restrict__ tab) {
   const double w0 = x6[6 * i], w1 = x6[6 * i + 1], w2 = x6[6 * i + 2];
   double R[9], A[9], flag;
   const double theta2 = w0 * w0 + w1 * w1 + w2 * w2;
@@ -81,11 +82,16 @@ __global__ void k_tables(const double* __restrict__ x6, const double* __restrict
 #pragma unroll
   for (int q = 0; q < 6; ++q) T[26 + q] = s6 ? s6[6 * i + q] : 1.0;
 }
+__global__ void k_tables(const double* __restrict__ x6, const double* __restrict__ intr4, const double* __restrict__ s6,
+                         int64_t n, double* __restrict__ tab) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) d_tables(i, x6, intr4, s6, tab);
+}
 
 __device__ __forceinline__ void load_tab(const double* __restrict__ tab, int64_t blk, double* T) {
   const double2* p = reinterpret_cast<const double2*>(tab + TAB * blk);
 #pragma unroll
-  for (int q = 0; q < TAB / 2; ++q) { const double2 v = __ldg(p + q); T[2 * q] = v.x; T[2 * q + 1] = v.y; }
+  for (int q = 0; q < TAB / 2; ++q) { const double2 v = (*(p + q)); T[2 * q] = v.x; T[2 * q + 1] = v.y; }
 }
 __device__ __forceinline__ void mat3_vec(const double* R, const double* x, double* y) {
   y[0] = R[0] * x[0] + R[1] * x[1] + R[2] * x[2];
@@ -140,18 +146,13 @@ __device__ __forceinline__ void staged_store(double* stage, const double* vals, 
 // ---------------------------------------------------------------------------------------
 // Model A.  One thread per observation (sorted by point).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_jac_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const double2* __restrict__ uv,
-        const double* __restrict__ tab_f, const double* __restrict__ xe, const double* __restrict__ se,
-        double* __restrict__ RES, double* __restrict__ JE, double* __restrict__ JF0, double* __restrict__ cost_partial, LossSpec L) {
-  __shared__ double sm[32];
-  __shared__ __align__(16) double stage[256 * 14];
-  const int64_t o0 = blockIdx.x * (int64_t)blockDim.x;
-  const int64_t o = o0 + threadIdx.x;
-  const int n_valid = (int)min((int64_t)blockDim.x, nb - o0);
-  double sq = 0.0;
-  double jf[12], je[6];
-  if (o < nb) {
+// one observation: residual (written), the two Jacobian rows of the camera (jf) and of the point (je), |r|^2 (or rho)
+__device__ __forceinline__ double d_jac_a(int64_t o, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0,
+                                          const double2* __restrict__ uv, const double* __restrict__ tab_f,
+                                          const double* __restrict__ xe, const double* __restrict__ se, double* __restrict__ RES,
+                                          double* jf, double* je, LossSpec L) {
+  double sq;
+  {
     const int32_t e = ob_e[o], c = ob_f0[o];
     double T[TAB];
     load_tab(tab_f, c, T);
@@ -188,34 +189,54 @@ k_jac_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
     }
     reinterpret_cast<double2*>(RES)[o] = make_double2(r0, r1);
   }
+  return sq;
+}
+__global__ void __launch_bounds__(256)
+k_jac_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const double2* __restrict__ uv,
+        const double* __restrict__ tab_f, const double* __restrict__ xe, const double* __restrict__ se,
+        double* __restrict__ RES, double* __restrict__ JE, double* __restrict__ JF0, double* __restrict__ cost_partial, LossSpec L) {
+  __shared__ double sm[32];
+  __shared__ __align__(16) double stage[256 * 14];
+  const int64_t o0 = blockIdx.x * (int64_t)blockDim.x;
+  const int64_t o = o0 + threadIdx.x;
+  const int n_valid = (int)min((int64_t)blockDim.x, nb - o0);
+  double sq = 0.0;
+  double jf[12], je[6];
+  if (o < nb) sq = d_jac_a(o, ob_e, ob_f0, uv, tab_f, xe, se, RES, jf, je, L);
   staged_store<12, 14>(stage, jf, o < nb, JF0 + 12 * o0, n_valid);
   staged_store<6, 6>(stage, je, o < nb, JE + 6 * o0, n_valid);
   sq = block_sum(sq, sm);
   if (threadIdx.x == 0) cost_partial[blockIdx.x] = sq;
 }
 
-__global__ void __launch_bounds__(256)
-k_cost_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const double2* __restrict__ uv,
-         const double* __restrict__ tab_f, const double* __restrict__ xe, double* __restrict__ cost_partial, LossSpec L) {
-  __shared__ double sm[32];
-  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  double sq = 0.0;
-  if (o < nb) {
+__device__ __forceinline__ double d_cost_a(int64_t o, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0,
+                                           const double2* __restrict__ uv, const double* __restrict__ tab_f,
+                                           const double* __restrict__ xe, LossSpec L) {
+  double sq;
+  {
     const int32_t e = ob_e[o], c = ob_f0[o];
     const double* T = tab_f + TAB * (int64_t)c;
     const double X[3] = {xe[3 * (int64_t)e], xe[3 * (int64_t)e + 1], xe[3 * (int64_t)e + 2]};
     double R[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) R[k] = __ldg(T + k);
+    for (int k = 0; k < 9; ++k) R[k] = (*(T + k));
     double q[3];
     mat3_vec(R, X, q);
-    const double p0 = q[0] + __ldg(T + 18), p1 = q[1] + __ldg(T + 19), p2 = q[2] + __ldg(T + 20);
+    const double p0 = q[0] + (*(T + 18)), p1 = q[1] + (*(T + 19)), p2 = q[2] + (*(T + 20));
     const double2 ob = uv[o];
-    const double r0 = __ldg(T + 21) * p0 / p2 + __ldg(T + 23) - ob.x;
-    const double r1 = __ldg(T + 22) * p1 / p2 + __ldg(T + 24) - ob.y;
+    const double r0 = (*(T + 21)) * p0 / p2 + (*(T + 23)) - ob.x;
+    const double r1 = (*(T + 22)) * p1 / p2 + (*(T + 24)) - ob.y;
     sq = r0 * r0 + r1 * r1;
     if (L.type != 0) { double w; loss_apply(L, sq, &sq, &w); }
   }
+  return sq;
+}
+__global__ void __launch_bounds__(256)
+k_cost_a(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const double2* __restrict__ uv,
+         const double* __restrict__ tab_f, const double* __restrict__ xe, double* __restrict__ cost_partial, LossSpec L) {
+  __shared__ double sm[32];
+  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double sq = o < nb ? d_cost_a(o, ob_e, ob_f0, uv, tab_f, xe, L) : 0.0;
   sq = block_sum(sq, sm);
   if (threadIdx.x == 0) cost_partial[blockIdx.x] = sq;
 }
@@ -290,20 +311,16 @@ __device__ __forceinline__ void b_rows(const double* Mleft /*3x3 or nullptr = I*
   }
 }
 
-__global__ void __launch_bounds__(128)
-k_jac_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const int32_t* __restrict__ ob_f1,
-        const int32_t* __restrict__ ob_cam, const double* __restrict__ obs8, const double* __restrict__ tab_f,
-        const double* __restrict__ tab_e, double half, double* __restrict__ RES, double* __restrict__ JE,
-        double* __restrict__ JF0, double* __restrict__ JF1, double* __restrict__ cost_partial, LossSpec L) {
-  __shared__ double sm[32];
-  __shared__ __align__(16) double stage[128 * 14];
-  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x;   // (marker observation, corner) records are contiguous: 12 doubles each
-  const int64_t t = t0 + threadIdx.x;
+// one (marker observation, corner): the two residuals (written) and the two rows of the three Jacobian blocks; returns
+// |r|^2 (robust loss: rho of the marker observation in its corner-0 lane).  Called by whole warps (the loss uses shuffles).
+__device__ __forceinline__ double d_jac_b(int64_t t, int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0,
+                                          const int32_t* __restrict__ ob_f1, const int32_t* __restrict__ ob_cam,
+                                          const double* __restrict__ obs8, const double* __restrict__ tab_f,
+                                          const double* __restrict__ tab_e, double half, double* __restrict__ RES, double* je12,
+                                          double* jc12, double* jm12, LossSpec L) {
   const int64_t o = t >> 2;
   const int corner = (int)(t & 3);
-  const int n_valid = (int)min((int64_t)blockDim.x, 4 * nb - t0);
   double sq = 0.0, rr0 = 0.0, rr1 = 0.0;
-  double je12[12], jc12[12], jm12[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) { je12[k] = 0.0; jc12[k] = 0.0; jm12[k] = 0.0; }
   if (o < nb) {
@@ -313,7 +330,7 @@ k_jac_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
     if (f0 >= 0) load_tab(tab_f, f0, Tc);
     if (f1 >= 0) load_tab(tab_f, f1, Tm);
     const double* K = tab_f + TAB * (int64_t)ob_cam[o] + 21;
-    const double fx = __ldg(K), fy = __ldg(K + 1), ppx = __ldg(K + 2), ppy = __ldg(K + 3);
+    const double fx = (*(K)), fy = (*(K + 1)), ppx = (*(K + 2)), ppy = (*(K + 3));
     BPoint P;
     model_b_chain(f0 >= 0 ? Tc : nullptr, Tt, f1 >= 0 ? Tm : nullptr, half, corner, true, P);
     const double p0 = P.p3[0], p1 = P.p3[1], p2 = P.p3[2];
@@ -349,6 +366,21 @@ k_jac_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
     RES[8 * o + 2 * corner] = rr0;
     RES[8 * o + 2 * corner + 1] = rr1;
   }
+  return sq;
+}
+__global__ void __launch_bounds__(128)
+k_jac_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const int32_t* __restrict__ ob_f1,
+        const int32_t* __restrict__ ob_cam, const double* __restrict__ obs8, const double* __restrict__ tab_f,
+        const double* __restrict__ tab_e, double half, double* __restrict__ RES, double* __restrict__ JE,
+        double* __restrict__ JF0, double* __restrict__ JF1, double* __restrict__ cost_partial, LossSpec L) {
+  __shared__ double sm[32];
+  __shared__ __align__(16) double stage[128 * 14];
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x;   // (marker observation, corner) records are contiguous: 12 doubles each
+  const int64_t t = t0 + threadIdx.x;
+  const int64_t o = t >> 2;
+  const int n_valid = (int)min((int64_t)blockDim.x, 4 * nb - t0);
+  double je12[12], jc12[12], jm12[12];
+  double sq = d_jac_b(t, nb, ob_e, ob_f0, ob_f1, ob_cam, obs8, tab_f, tab_e, half, RES, je12, jc12, jm12, L);
   staged_store<12, 14>(stage, je12, o < nb, JE + 12 * t0, n_valid);
   staged_store<12, 14>(stage, jc12, o < nb, JF0 + 12 * t0, n_valid);
   staged_store<12, 14>(stage, jm12, o < nb, JF1 + 12 * t0, n_valid);
@@ -356,12 +388,10 @@ k_jac_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict_
   if (threadIdx.x == 0) cost_partial[blockIdx.x] = sq;
 }
 
-__global__ void __launch_bounds__(128)
-k_cost_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const int32_t* __restrict__ ob_f1,
-         const int32_t* __restrict__ ob_cam, const double* __restrict__ obs8, const double* __restrict__ tab_f,
-         const double* __restrict__ tab_e, double half, double* __restrict__ cost_partial, LossSpec L) {
-  __shared__ double sm[32];
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per (marker observation, corner)
+__device__ __forceinline__ double d_cost_b(int64_t t, int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0,
+                                           const int32_t* __restrict__ ob_f1, const int32_t* __restrict__ ob_cam,
+                                           const double* __restrict__ obs8, const double* __restrict__ tab_f,
+                                           const double* __restrict__ tab_e, double half, LossSpec L) {
   const int64_t o = t >> 2;
   const int corner = (int)(t & 3);
   double sq = 0.0;
@@ -374,8 +404,8 @@ k_cost_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict
     const double* K = tab_f + TAB * (int64_t)ob_cam[o] + 21;
     BPoint P;
     model_b_chain(f0 >= 0 ? Tc : nullptr, Tt, f1 >= 0 ? Tm : nullptr, half, corner, false, P);
-    const double r0 = __ldg(K) * P.p3[0] / P.p3[2] + __ldg(K + 2) - obs8[8 * o + 2 * corner];
-    const double r1 = __ldg(K + 1) * P.p3[1] / P.p3[2] + __ldg(K + 3) - obs8[8 * o + 2 * corner + 1];
+    const double r0 = (*(K)) * P.p3[0] / P.p3[2] + (*(K + 2)) - obs8[8 * o + 2 * corner];
+    const double r1 = (*(K + 1)) * P.p3[1] / P.p3[2] + (*(K + 3)) - obs8[8 * o + 2 * corner + 1];
     sq = r0 * r0 + r1 * r1;
   }
   if (L.type != 0) {
@@ -386,6 +416,15 @@ k_cost_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict
     loss_apply(L, s, &rho, &w);
     sq = corner == 0 ? rho : 0.0;
   }
+  return sq;
+}
+__global__ void __launch_bounds__(128)
+k_cost_b(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const int32_t* __restrict__ ob_f1,
+         const int32_t* __restrict__ ob_cam, const double* __restrict__ obs8, const double* __restrict__ tab_f,
+         const double* __restrict__ tab_e, double half, double* __restrict__ cost_partial, LossSpec L) {
+  __shared__ double sm[32];
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per (marker observation, corner)
+  double sq = d_cost_b(t, nb, ob_e, ob_f0, ob_f1, ob_cam, obs8, tab_f, tab_e, half, L);
   sq = block_sum(sq, sm);
   if (threadIdx.x == 0) cost_partial[blockIdx.x] = sq;
 }
@@ -400,20 +439,14 @@ __device__ __forceinline__ void load_row6(const double* __restrict__ p, double* 
 #pragma unroll
   for (int k = 0; k < 3; ++k) { const double2 v = q[k]; row[2 * k] = v.x; row[2 * k + 1] = v.y; }
 }
+// this lane's share of list entries [begin, end) (sum the 27 values over the warp afterwards)
 template <int RD>
-__global__ void __launch_bounds__(128)
-k_fobs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_begin,
-               const int64_t* __restrict__ fobs_ptr, const int32_t* __restrict__ fobs, const double* __restrict__ RES,
-               const double* __restrict__ JF0, const double* __restrict__ JF1, double* __restrict__ partial) {
+__device__ __forceinline__ void d_fobs_seg(int lane, int64_t begin, int64_t end, const int32_t* __restrict__ fobs,
+                                           const double* __restrict__ RES, const double* __restrict__ JF0,
+                                           const double* __restrict__ JF1, double* acc) {
   static_assert(32 % RD == 0, "rows of an observation share a warp");
   constexpr int OPW = 32 / RD;
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= nchunks) return;
   const int sub = lane / RD, rr = lane % RD;
-  const int64_t begin = chunk_begin[c];
-  const int64_t end = min(begin + ch, fobs_ptr[chunk_seg[c] + 1]);
-  double acc[NV_F];
 #pragma unroll
   for (int k = 0; k < NV_F; ++k) acc[k] = 0.0;
 #pragma unroll 2
@@ -431,6 +464,19 @@ k_fobs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const
 #pragma unroll
     for (int a = 0; a < 6; ++a) acc[21 + a] = fma(row[a], rv, acc[21 + a]);
   }
+}
+template <int RD>
+__global__ void __launch_bounds__(128)
+k_fobs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_begin,
+               const int64_t* __restrict__ fobs_ptr, const int32_t* __restrict__ fobs, const double* __restrict__ RES,
+               const double* __restrict__ JF0, const double* __restrict__ JF1, double* __restrict__ partial) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= nchunks) return;
+  const int64_t begin = chunk_begin[c];
+  const int64_t end = min(begin + ch, fobs_ptr[chunk_seg[c] + 1]);
+  double acc[NV_F];
+  d_fobs_seg<RD>(lane, begin, end, fobs, RES, JF0, JF1, acc);
 #pragma unroll
   for (int k = 0; k < NV_F; ++k) {
     const double s = warp_sum(acc[k]);
@@ -456,11 +502,9 @@ k_seg_final(int nseg, const int32_t* __restrict__ seg_first, const double* __res
 
 // E^T E (packed upper) and E^T r per eliminated block; G lanes cooperate on one block.
 template <int RD, int DE, int G>
-__global__ void __launch_bounds__(128)
-k_e_M(int64_t ne, const int64_t* __restrict__ e_ptr, const double* __restrict__ RES, const double* __restrict__ JE,
-      double* __restrict__ ME) {
+__device__ __forceinline__ void d_e_M(int64_t t, int64_t ne, const int64_t* __restrict__ e_ptr, const double* __restrict__ RES,
+                                      const double* __restrict__ JE, double* __restrict__ ME) {   // whole warps call this
   constexpr int NU = DE * (DE + 1) / 2, NV = NU + DE;
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t e = t / G;
   const int g = (int)(t % G);
   const bool live = e < ne;
@@ -517,16 +561,21 @@ k_e_M(int64_t ne, const int64_t* __restrict__ e_ptr, const double* __restrict__ 
     for (int k = 0; k < NV; ++k) ME[e * NV + k] = acc[k];
   }
 }
+template <int RD, int DE, int G>
+__global__ void __launch_bounds__(128)
+k_e_M(int64_t ne, const int64_t* __restrict__ e_ptr, const double* __restrict__ RES, const double* __restrict__ JE,
+      double* __restrict__ ME) {
+  d_e_M<RD, DE, G>(blockIdx.x * (int64_t)blockDim.x + threadIdx.x, ne, e_ptr, RES, JE, ME);
+}
 
 // Model B: W_i^T = sum over the observations of incidence i of JE^T JF  (6 x 6, k-major).  RD lanes per incidence, a lane
 // owns one residual row: the group walks the incidence's observations one at a time and reads both 384-byte records whole.
 template <int RD>
-__global__ void __launch_bounds__(128)
-k_inc_W(int64_t ninc, const int64_t* __restrict__ incobs_ptr, const int32_t* __restrict__ incobs, const double* __restrict__ JE,
-        const double* __restrict__ JF0, const double* __restrict__ JF1, double* __restrict__ Wt) {
-  static_assert(32 % RD == 0, "one lane per residual row, a group inside a warp");   // launched for Model B only (RD = 8)
+__device__ __forceinline__ void d_inc_W(int64_t t, int64_t ninc, const int64_t* __restrict__ incobs_ptr, const int32_t* __restrict__ incobs,
+                                        const double* __restrict__ JE, const double* __restrict__ JF0,
+                                        const double* __restrict__ JF1, double* __restrict__ Wt) {   // whole warps call this
+  static_assert(32 % RD == 0, "one lane per residual row, a group inside a warp");   // used for Model B only (RD = 8)
   constexpr int G = RD;
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t i = t / G;
   const int g = (int)(t % G);
   const bool live = i < ninc;
@@ -557,17 +606,19 @@ k_inc_W(int64_t ninc, const int64_t* __restrict__ incobs_ptr, const int32_t* __r
     for (int k = 0; k < 36; ++k) Wt[i * 36 + k] = acc[k];
   }
 }
+template <int RD>
+__global__ void __launch_bounds__(128)
+k_inc_W(int64_t ninc, const int64_t* __restrict__ incobs_ptr, const int32_t* __restrict__ incobs, const double* __restrict__ JE,
+        const double* __restrict__ JF0, const double* __restrict__ JF1, double* __restrict__ Wt) {
+  d_inc_W<RD>(blockIdx.x * (int64_t)blockDim.x + threadIdx.x, ninc, incobs_ptr, incobs, JE, JF0, JF1, Wt);
+}
 
 // (E^T E + D_e^2) = L L^T and z = L^-1 E^T r per eliminated block.  D_e = sqrt(clamp(diag)/radius)
 // (LevenbergMarquardtStrategy::ComputeStep).  status bit 0 is raised when a block is not PD.
 template <int DE>
-__global__ void __launch_bounds__(256)
-k_e_chol(int64_t ne, const double* __restrict__ ME, const double* __restrict__ radius_p, double min_diag, double max_diag,
-         double* __restrict__ Lb, double* __restrict__ zb, int* status) {
+__device__ __forceinline__ void d_e_chol(int64_t e, const double* __restrict__ ME, double radius, double min_diag, double max_diag,
+                                         double* __restrict__ Lb, double* __restrict__ zb, int* status) {
   constexpr int NU = DE * (DE + 1) / 2, NV = NU + DE;
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= ne) return;
-  const double radius = *radius_p;
   double M[DE * DE], g[DE];
   int q = 0;
 #pragma unroll
@@ -591,16 +642,20 @@ k_e_chol(int64_t ne, const double* __restrict__ ME, const double* __restrict__ r
 #pragma unroll
   for (int k = 0; k < DE; ++k) zb[e * DE + k] = g[k];
 }
+template <int DE>
+__global__ void __launch_bounds__(256)
+k_e_chol(int64_t ne, const double* __restrict__ ME, const double* __restrict__ radius_p, double min_diag, double max_diag,
+         double* __restrict__ Lb, double* __restrict__ zb, int* status) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < ne) d_e_chol<DE>(e, ME, *radius_p, min_diag, max_diag, Lb, zb, status);
+}
 
 // Yt_i = L^-1 W_i^T (DE x 6, k-major) and v_i = Yt_i^T z per incidence.  FROM_J: the incidence is a single
 // observation (Model A) and W_i^T = JE^T JF0 is formed on the fly.
 template <int RD, int DE, bool FROM_J>
-__global__ void __launch_bounds__(128)
-k_inc_Y(int64_t ninc, const int32_t* __restrict__ inc_e, const double* __restrict__ JE, const double* __restrict__ JF0,
-        const double* __restrict__ Wt, const double* __restrict__ Lb, const double* __restrict__ zb, double* __restrict__ Yt,
-        double* __restrict__ vb) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= ninc) return;
+__device__ __forceinline__ void d_inc_Y(int64_t i, const int32_t* __restrict__ inc_e, const double* __restrict__ JE,
+                                        const double* __restrict__ JF0, const double* __restrict__ Wt, const double* __restrict__ Lb,
+                                        const double* __restrict__ zb, double* __restrict__ Yt, double* __restrict__ vb) {
   const int64_t e = inc_e[i];
   double W[DE * 6];
   if (FROM_J) {
@@ -645,8 +700,26 @@ k_inc_Y(int64_t ninc, const int32_t* __restrict__ inc_e, const double* __restric
 #pragma unroll
   for (int k = 0; k < 3; ++k) pv[k] = make_double2(v[2 * k], v[2 * k + 1]);
 }
+template <int RD, int DE, bool FROM_J>
+__global__ void __launch_bounds__(128)
+k_inc_Y(int64_t ninc, const int32_t* __restrict__ inc_e, const double* __restrict__ JE, const double* __restrict__ JF0,
+        const double* __restrict__ Wt, const double* __restrict__ Lb, const double* __restrict__ zb, double* __restrict__ Yt,
+        double* __restrict__ vb) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < ninc) d_inc_Y<RD, DE, FROM_J>(i, inc_e, JE, JF0, Wt, Lb, zb, Yt, vb);
+}
 
 // sum of v_i over the incidences of one f-block, chunk partials (6 values).
+__device__ __forceinline__ void d_finc_seg(int lane, int64_t begin, int64_t end, const int32_t* __restrict__ finc,
+                                           const double* __restrict__ vb, double* acc) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) acc[k] = 0.0;
+  for (int64_t idx = begin + lane; idx < end; idx += 32) {
+    const double2* p = reinterpret_cast<const double2*>(vb + 6 * (int64_t)finc[idx]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const double2 v = p[k]; acc[2 * k] += v.x; acc[2 * k + 1] += v.y; }
+  }
+}
 __global__ void __launch_bounds__(128)
 k_finc_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_begin,
                const int64_t* __restrict__ finc_ptr, const int32_t* __restrict__ finc, const double* __restrict__ vb,
@@ -656,12 +729,8 @@ k_finc_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const
   if (c >= nchunks) return;
   const int64_t begin = chunk_begin[c];
   const int64_t end = min(begin + ch, finc_ptr[chunk_seg[c] + 1]);
-  double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int64_t idx = begin + lane; idx < end; idx += 32) {
-    const double2* p = reinterpret_cast<const double2*>(vb + 6 * (int64_t)finc[idx]);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { const double2 v = p[k]; acc[2 * k] += v.x; acc[2 * k + 1] += v.y; }
-  }
+  double acc[6];
+  d_finc_seg(lane, begin, end, finc, vb, acc);
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     const double s = warp_sum(acc[k]);
@@ -672,19 +741,11 @@ k_finc_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const
 // sum over incidence pairs (i,j) of Y_i Y_j^T = Yt_i^T Yt_j for one destination block, chunk partials (36 values).
 // One warp per chunk; a lane owns one row k of the two Yt records of a pair (groups of 8 lanes, or 4 when DE <= 4).
 template <int DE>
-__global__ void __launch_bounds__(128)
-k_pairs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_begin,
-                const int64_t* __restrict__ dpair_ptr, const int2* __restrict__ pairs, const double* __restrict__ Yt,
-                double* __restrict__ partial) {
+__device__ __forceinline__ void d_pairs_seg(int lane, int64_t begin, int64_t end, const int2* __restrict__ pairs,
+                                            const double* __restrict__ Yt, double* acc) {
   constexpr int G = DE <= 4 ? 4 : 8;
   static_assert(DE <= G, "one lane per row of Yt");
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= nchunks) return;
   const int sub = lane / G, k = lane % G;
-  const int64_t begin = chunk_begin[c];
-  const int64_t end = min(begin + ch, dpair_ptr[chunk_seg[c] + 1]);
-  double acc[36];
 #pragma unroll
   for (int q = 0; q < 36; ++q) acc[q] = 0.0;
   if (k < DE) {
@@ -701,6 +762,19 @@ k_pairs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, cons
         for (int b = 0; b < 6; ++b) acc[a * 6 + b] = fma(yi[a], yj[b], acc[a * 6 + b]);
     }
   }
+}
+template <int DE>
+__global__ void __launch_bounds__(128)
+k_pairs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_begin,
+                const int64_t* __restrict__ dpair_ptr, const int2* __restrict__ pairs, const double* __restrict__ Yt,
+                double* __restrict__ partial) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= nchunks) return;
+  const int64_t begin = chunk_begin[c];
+  const int64_t end = min(begin + ch, dpair_ptr[chunk_seg[c] + 1]);
+  double acc[36];
+  d_pairs_seg<DE>(lane, begin, end, pairs, Yt, acc);
 #pragma unroll
   for (int q = 0; q < 36; ++q) {
     const double s = warp_sum(acc[q]);
@@ -711,19 +785,11 @@ k_pairs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, cons
 // Model B: sum over observations with (f0,f1) == (fa,fb) of JF0^T JF1, chunk partials (36 values).  One warp per chunk,
 // a lane owns one residual row of one observation.
 template <int RD>
-__global__ void __launch_bounds__(128)
-k_dobs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_begin,
-               const int64_t* __restrict__ dobs_ptr, const int32_t* __restrict__ dobs, const double* __restrict__ JF0,
-               const double* __restrict__ JF1, double* __restrict__ partial) {
+__device__ __forceinline__ void d_dobs_seg(int lane, int64_t begin, int64_t end, const int32_t* __restrict__ dobs,
+                                           const double* __restrict__ JF0, const double* __restrict__ JF1, double* acc) {
   static_assert(32 % RD == 0, "rows of an observation share a warp");
   constexpr int OPW = 32 / RD;
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= nchunks) return;
   const int sub = lane / RD, rr = lane % RD;
-  const int64_t begin = chunk_begin[c];
-  const int64_t end = min(begin + ch, dobs_ptr[chunk_seg[c] + 1]);
-  double acc[36];
 #pragma unroll
   for (int k = 0; k < 36; ++k) acc[k] = 0.0;
 #pragma unroll 2
@@ -737,6 +803,19 @@ k_dobs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const
 #pragma unroll
       for (int b = 0; b < 6; ++b) acc[a * 6 + b] = fma(ra[a], rb[b], acc[a * 6 + b]);
   }
+}
+template <int RD>
+__global__ void __launch_bounds__(128)
+k_dobs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_begin,
+               const int64_t* __restrict__ dobs_ptr, const int32_t* __restrict__ dobs, const double* __restrict__ JF0,
+               const double* __restrict__ JF1, double* __restrict__ partial) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= nchunks) return;
+  const int64_t begin = chunk_begin[c];
+  const int64_t end = min(begin + ch, dobs_ptr[chunk_seg[c] + 1]);
+  double acc[36];
+  d_dobs_seg<RD>(lane, begin, end, dobs, JF0, JF1, acc);
 #pragma unroll
   for (int k = 0; k < 36; ++k) {
     const double s = warp_sum(acc[k]);
@@ -745,23 +824,25 @@ k_dobs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const
 }
 
 // Dense RCS: S[fa,fb] = Q - P (and its transpose).  One thread per (dest, entry).
-__global__ void k_assemble_dense(int ndest, const int32_t* __restrict__ dest_fa, const int32_t* __restrict__ dest_fb,
-                                 const double* __restrict__ P, const double* __restrict__ Q, int64_t n, double* __restrict__ S) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t >= (int64_t)ndest * 36) return;
+__device__ __forceinline__ void d_assemble_dense(int64_t t, const int32_t* __restrict__ dest_fa, const int32_t* __restrict__ dest_fb,
+                                                 const double* __restrict__ P, const double* __restrict__ Q, int64_t n /* row stride */,
+                                                 double* __restrict__ S) {
   const int d = (int)(t / 36), q = (int)(t % 36), a = q / 6, b = q % 6;
   const int64_t fa = dest_fa[d], fb = dest_fb[d];
   const double v = (Q ? Q[t] : 0.0) - P[t];
   S[(6 * fa + a) * n + 6 * fb + b] = v;
   if (fa != fb) S[(6 * fb + b) * n + 6 * fa + a] = v;
 }
+__global__ void k_assemble_dense(int ndest, const int32_t* __restrict__ dest_fa, const int32_t* __restrict__ dest_fb,
+                                 const double* __restrict__ P, const double* __restrict__ Q, int64_t n, double* __restrict__ S) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < (int64_t)ndest * 36) d_assemble_dense(t, dest_fa, dest_fb, P, Q, n, S);
+}
 
 // After the (optional) cross-GPU sum: add F^T F diagonal blocks and the LM diagonal D_f^2, form the rhs.
-__global__ void k_diag_rhs_dense(int64_t nf, const double* __restrict__ HG, int hg_stride, const double* __restrict__ vsum,
-                                 int v_stride, const double* __restrict__ radius_p, double min_diag, double max_diag, int64_t n,
-                                 double* __restrict__ S, double* __restrict__ rhs) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t >= nf * 6) return;
+__device__ __forceinline__ void d_diag_rhs_dense(int64_t t, const double* __restrict__ HG, int hg_stride, const double* __restrict__ vsum,
+                                                 int v_stride, const double* __restrict__ radius_p, double min_diag, double max_diag,
+                                                 int64_t n /* row stride */, double* __restrict__ S, double* __restrict__ rhs) {
   const int64_t f = t / 6;
   const int a = (int)(t % 6);
   const double* H = HG + f * hg_stride;
@@ -773,16 +854,21 @@ __global__ void k_diag_rhs_dense(int64_t nf, const double* __restrict__ HG, int 
   }
   rhs[t] = H[21 + a] - vsum[f * v_stride + a];
 }
+__global__ void k_diag_rhs_dense(int64_t nf, const double* __restrict__ HG, int hg_stride, const double* __restrict__ vsum,
+                                 int v_stride, const double* __restrict__ radius_p, double min_diag, double max_diag, int64_t n,
+                                 double* __restrict__ S, double* __restrict__ rhs) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < nf * 6) d_diag_rhs_dense(t, HG, hg_stride, vsum, v_stride, radius_p, min_diag, max_diag, n, S, rhs);
+}
 
 // ---------------------------------------------------------------------------------------
 // K4
 // ---------------------------------------------------------------------------------------
 // y_e = L^-T (z - sum_i Yt_i y_f(i)); G lanes per eliminated block.
 template <int DE, int G>
-__global__ void __launch_bounds__(128)
-k_e_backsub(int64_t ne, const int64_t* __restrict__ einc_ptr, const int32_t* __restrict__ inc_f, const double* __restrict__ Yt,
-            const double* __restrict__ Lb, const double* __restrict__ zb, const double* __restrict__ yf, double* __restrict__ ye) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__device__ __forceinline__ void d_e_backsub(int64_t t, int64_t ne, const int64_t* __restrict__ einc_ptr, const int32_t* __restrict__ inc_f,
+                                            const double* __restrict__ Yt, const double* __restrict__ Lb, const double* __restrict__ zb,
+                                            const double* __restrict__ yf, double* __restrict__ ye) {   // whole warps call this
   const int64_t e = t / G;
   const int g = (int)(t % G);
   const bool live = e < ne;
@@ -819,20 +905,23 @@ k_e_backsub(int64_t ne, const int64_t* __restrict__ einc_ptr, const int32_t* __r
     for (int k = 0; k < DE; ++k) ye[e * DE + k] = x[k];
   }
 }
+template <int DE, int G>
+__global__ void __launch_bounds__(128)
+k_e_backsub(int64_t ne, const int64_t* __restrict__ einc_ptr, const int32_t* __restrict__ inc_f, const double* __restrict__ Yt,
+            const double* __restrict__ Lb, const double* __restrict__ zb, const double* __restrict__ yf, double* __restrict__ ye) {
+  d_e_backsub<DE, G>(blockIdx.x * (int64_t)blockDim.x + threadIdx.x, ne, einc_ptr, inc_f, Yt, Lb, zb, yf, ye);
+}
 
 // model_cost_change partials: with step = -y,  sum_o (J step) . (r + J step / 2)   (the caller negates).
 // One thread per residual row: consecutive lanes read consecutive rows of JE / JF0 / JF1.
 template <int RD, int DE, int NSLOT>
-__global__ void __launch_bounds__(256)
-k_model_cost(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const int32_t* __restrict__ ob_f1,
-             const double* __restrict__ RES, const double* __restrict__ JE, const double* __restrict__ JF0,
-             const double* __restrict__ JF1, const double* __restrict__ ye, const double* __restrict__ yf,
-             double* __restrict__ partial) {
-  __shared__ double sm[32];
-  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__device__ __forceinline__ double d_model_cost_row(int64_t row, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0,
+                                                   const int32_t* __restrict__ ob_f1, const double* __restrict__ RES,
+                                                   const double* __restrict__ JE, const double* __restrict__ JF0,
+                                                   const double* __restrict__ JF1, const double* __restrict__ ye,
+                                                   const double* __restrict__ yf) {
   const int64_t o = row / RD;
-  double acc = 0.0;
-  if (o < nb) {
+  {
     const int64_t e = ob_e[o];
     const int32_t f0 = ob_f0[o];
     const int32_t f1 = NSLOT == 2 ? ob_f1[o] : -1;
@@ -851,13 +940,33 @@ k_model_cost(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __rest
 #pragma unroll
       for (int k = 0; k < 6; ++k) m = fma(j[k], -yf[6 * (int64_t)f1 + k], m);
     }
-    acc = m * (RES[row] + m / 2.0);
+    return m * (RES[row] + m / 2.0);
   }
+}
+template <int RD, int DE, int NSLOT>
+__global__ void __launch_bounds__(256)
+k_model_cost(int64_t nb, const int32_t* __restrict__ ob_e, const int32_t* __restrict__ ob_f0, const int32_t* __restrict__ ob_f1,
+             const double* __restrict__ RES, const double* __restrict__ JE, const double* __restrict__ JF0,
+             const double* __restrict__ JF1, const double* __restrict__ ye, const double* __restrict__ yf,
+             double* __restrict__ partial) {
+  __shared__ double sm[32];
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double acc = row / RD < nb ? d_model_cost_row<RD, DE, NSLOT>(row, ob_e, ob_f0, ob_f1, RES, JE, JF0, JF1, ye, yf) : 0.0;
   acc = block_sum(acc, sm);
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
 // candidate = x - s .* y over blocks of width W; partial sums of x^2 and (x - candidate)^2 over active blocks.
+template <int W>
+__device__ __forceinline__ void d_candidate(int64_t t, const int64_t* __restrict__ ptr, const double* __restrict__ x,
+                                            const double* __restrict__ s, const double* __restrict__ y, double* __restrict__ xc,
+                                            double& x2, double& d2) {
+  const int64_t b = t / W;
+  const double xv = x[t];
+  const double c = xv + (-(y[t]) * s[t]);
+  xc[t] = c;
+  if (ptr[b + 1] > ptr[b]) { x2 = xv * xv; const double d = xv - c; d2 = d * d; }
+}
 template <int W>
 __global__ void __launch_bounds__(256)
 k_candidate(int64_t nblk, const int64_t* __restrict__ ptr /*block is active iff ptr[b+1] > ptr[b]*/, const double* __restrict__ x,
@@ -866,13 +975,7 @@ k_candidate(int64_t nblk, const int64_t* __restrict__ ptr /*block is active iff 
   __shared__ double sm[32];
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   double x2 = 0.0, d2 = 0.0;
-  if (t < nblk * W) {
-    const int64_t b = t / W;
-    const double xv = x[t];
-    const double c = xv + (-(y[t]) * s[t]);
-    xc[t] = c;
-    if (ptr[b + 1] > ptr[b]) { x2 = xv * xv; const double d = xv - c; d2 = d * d; }
-  }
+  if (t < nblk * W) d_candidate<W>(t, ptr, x, s, y, xc, x2, d2);
   x2 = block_sum(x2, sm);
   d2 = block_sum(d2, sm);
   if (threadIdx.x == 0) { p_x2[blockIdx.x] = x2; p_d2[blockIdx.x] = d2; }
@@ -881,22 +984,25 @@ k_candidate(int64_t nblk, const int64_t* __restrict__ ptr /*block is active iff 
 // |x - Plus(x, -g)| max and squared-sum partials (TrustRegionMinimizer::EvaluateGradientAndJacobian);
 // g (unscaled) = g_scaled / s.  src holds per block NVB values with the gradient at offset GOFF.
 template <int W, int NVB, int GOFF>
+__device__ __forceinline__ void d_gradient_norm(int64_t t, const int64_t* __restrict__ ptr, const double* __restrict__ x,
+                                                const double* __restrict__ s, const double* __restrict__ src, double& mx, double& sq) {
+  const int64_t b = t / W;
+  const int k = (int)(t % W);
+  if (ptr[b + 1] > ptr[b]) {
+    const double g = src[b * NVB + GOFF + k] / s[t];
+    const double xv = x[t];
+    const double d = xv - (xv + (-g));
+    mx = fabs(d); sq = d * d;
+  }
+}
+template <int W, int NVB, int GOFF>
 __global__ void __launch_bounds__(256)
 k_gradient_norm(int64_t nblk, const int64_t* __restrict__ ptr, const double* __restrict__ x, const double* __restrict__ s,
                 const double* __restrict__ src, double* __restrict__ p_max, double* __restrict__ p_sq) {
   __shared__ double sm[32];
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   double mx = 0.0, sq = 0.0;
-  if (t < nblk * W) {
-    const int64_t b = t / W;
-    const int k = (int)(t % W);
-    if (ptr[b + 1] > ptr[b]) {
-      const double g = src[b * NVB + GOFF + k] / s[t];
-      const double xv = x[t];
-      const double d = xv - (xv + (-g));
-      mx = fabs(d); sq = d * d;
-    }
-  }
+  if (t < nblk * W) d_gradient_norm<W, NVB, GOFF>(t, ptr, x, s, src, mx, sq);
   mx = block_max(mx, sm);
   sq = block_sum(sq, sm);
   if (threadIdx.x == 0) { p_max[blockIdx.x] = mx; p_sq[blockIdx.x] = sq; }
@@ -904,13 +1010,16 @@ k_gradient_norm(int64_t nblk, const int64_t* __restrict__ ptr, const double* __r
 
 // Jacobi scaling s = 1 / (1 + sqrt(|column|^2)) from the packed normal-equation diagonals (iteration 0 only).
 template <int W, int NVB>
-__global__ void k_jacobi_scale(int64_t nblk, const double* __restrict__ src, double* __restrict__ s) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t >= nblk * W) return;
+__device__ __forceinline__ void d_jacobi_scale(int64_t t, const double* __restrict__ src, double* __restrict__ s) {
   const int64_t b = t / W;
   const int k = (int)(t % W);
   const int di = k * W - k * (k - 1) / 2;  // packed index of (k,k)
   s[t] = 1.0 / (1.0 + sqrt(src[b * NVB + di]));
+}
+template <int W, int NVB>
+__global__ void k_jacobi_scale(int64_t nblk, const double* __restrict__ src, double* __restrict__ s) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < nblk * W) d_jacobi_scale<W, NVB>(t, src, s);
 }
 
 __global__ void k_fill(double* a, int64_t n, double v) {

@@ -1,0 +1,475 @@
+// ba_rig.cuh -- the rig-size latency path: the whole trust-region loop of ceres::Solve in ONE launch of ONE CTA.
+//
+// The reference's own problems (Common/Correspondence/hongo: 68 marker observations; Test1/Test2_BundleAdjustment: 16..200
+// observations; Main_Calibration/bundle_adjustment_manager.cpp:16-96) are three orders of magnitude below what fills a
+// B200: on the multi-kernel pipeline one LM iteration is ~40 launches and two host round trips, all latency.  Here one
+// CTA of 1024 threads walks the same phases (the item functions d_* of ba_kernels.cuh, so the arithmetic per observation,
+// per block and per incidence is the generic pipeline's) separated by __syncthreads instead of launches; the reduced camera
+// system lives in shared memory and is factorised there (LDL^T, one barrier per column; the two triangular solves run in
+// one warp's registers); TrustRegionMinimizer's loop variables and its decisions (lm_begin / lm_iterate of ba_cuda.cu,
+// statement for statement) are taken by thread 0 between barriers, and the iteration rows are written to HBM for the host
+// to read after the launch.  Every sum is a fixed tree: results are bitwise reproducible.
+#pragma once
+#include "ba_kernels.cuh"
+
+namespace ba {
+
+constexpr int RIG_THREADS = 512;        // 128 registers per thread: the item functions keep whole tables and 36 accumulators
+constexpr int RIG_ROWS_CAP = 256;       // iteration rows one launch can record
+constexpr int RIG_MAX_N = 160;       // reduced camera system dimension that fits shared memory (n * (n | 1) doubles)
+constexpr int64_t RIG_MAX_ROWS = 16384;   // residual rows (nb * RD): beyond this the multi-kernel pipeline is the better machine
+
+struct RigState {   // LmState of ba_cuda.cu, on the device
+  double radius, decrease_factor, x_cost, gmax, gnorm;
+  int32_t num_invalid, go, n_rows, term_type, term_reason;
+  int32_t n_jac, n_solves, n_success, n_unsuccess, last_iteration, pad_;
+  double last_gmax, last_gnorm;      // gradient norms of the previous row (an invalid step repeats them)
+};
+
+struct RigParams {
+  int64_t nb, ne, nf, ninc;
+  int ndest, n, ld;
+  // structure (ba_structure.cuh)
+  const int32_t *ob_e, *ob_f0, *ob_f1, *ob_cam;
+  const int64_t* e_ptr;
+  const int32_t *inc_e, *inc_f;
+  const int64_t* einc_ptr;
+  const int64_t* incobs_ptr; const int32_t* incobs;
+  const int64_t *finc_ptr, *fobs_ptr; const int32_t *finc, *fobs;
+  const int32_t *dest_fa, *dest_fb;
+  const int64_t* dpair_ptr; const int2* pairs;
+  const int64_t* dobs_ptr; const int32_t* dobs;
+  const int64_t* f_act_ptr;
+  // model data
+  const double2* uv; const double* obs8; const double* intr_f; double half_side;
+  // parameters, scaling, tables
+  double *xe, *xf, *xe_c, *xf_c, *se, *sf, *tab_f, *tab_e, *tabc_f, *tabc_e;
+  // workspace of the generic pipeline
+  double *RES, *JE, *JF0, *JF1, *ME, *HG, *Wt, *Qacc, *Lb, *zb, *Yt, *vb, *Pacc, *vsum, *yf, *ye;
+  RigState* state;
+  ba_cuda_iteration* rows;
+  int32_t rows_base;  // rows recorded by earlier launches of this solve
+  int32_t begin;      // 1: start from `init` and run iteration zero first (TrustRegionMinimizer::IterationZero)
+  int32_t max_new;    // at most this many loop iterations in this launch (begin + max_new <= RIG_ROWS_CAP)
+  RigState init;
+  ba_cuda_options opt;
+  LossSpec loss;
+};
+
+// ---- CTA-wide helpers --------------------------------------------------------------------------------------
+__device__ __forceinline__ double rig_sum(double v, double* red) {   // every thread gets the sum
+  v = block_sum(v, red);
+  __syncthreads();
+  if (threadIdx.x == 0) red[32] = v;
+  __syncthreads();
+  return red[32];
+}
+__device__ __forceinline__ double rig_max(double v, double* red) {
+  v = block_max(v, red);
+  __syncthreads();
+  if (threadIdx.x == 0) red[32] = v;
+  __syncthreads();
+  return red[32];
+}
+__device__ __forceinline__ double rig_now_s() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return 1e-9 * (double)t;
+}
+
+// tables at x (candidate = false) or at the candidate point
+template <int MODEL>
+__device__ __forceinline__ void rig_tables(const RigParams& P, bool candidate) {
+  const double* xf = candidate ? P.xf_c : P.xf;
+  double* tf = candidate ? P.tabc_f : P.tab_f;
+  for (int64_t i = threadIdx.x; i < P.nf; i += RIG_THREADS) d_tables(i, xf, P.intr_f, P.sf, tf);
+  if (MODEL == 1) {
+    const double* xe = candidate ? P.xe_c : P.xe;
+    double* te = candidate ? P.tabc_e : P.tab_e;
+    for (int64_t i = threadIdx.x; i < P.ne; i += RIG_THREADS) d_tables(i, xe, nullptr, P.se, te);
+  }
+  __syncthreads();
+}
+
+// K1: residuals and scaled Jacobian at x; returns sum r^2 (or sum rho)
+template <int MODEL>
+__device__ __forceinline__ double rig_jacobian(const RigParams& P, double* red) {
+  rig_tables<MODEL>(P, false);
+  double sq = 0.0;
+  if (MODEL == 0) {
+    for (int64_t base = 0; base < P.nb; base += RIG_THREADS) {
+      const int64_t o = base + threadIdx.x;
+      if (o < P.nb) {
+        double jf[12], je[6];
+        sq += d_jac_a(o, P.ob_e, P.ob_f0, P.uv, P.tab_f, P.xe, P.se, P.RES, jf, je, P.loss);
+        double2* pf = reinterpret_cast<double2*>(P.JF0 + 12 * o);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) pf[k] = make_double2(jf[2 * k], jf[2 * k + 1]);
+        double2* pe = reinterpret_cast<double2*>(P.JE + 6 * o);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pe[k] = make_double2(je[2 * k], je[2 * k + 1]);
+      }
+    }
+  } else {
+    for (int64_t base = 0; base < 4 * P.nb; base += RIG_THREADS) {   // whole warps: the robust loss sums over a marker's 4 lanes
+      const int64_t t = base + threadIdx.x;
+      double je12[12], jc12[12], jm12[12];
+      sq += d_jac_b(t, P.nb, P.ob_e, P.ob_f0, P.ob_f1, P.ob_cam, P.obs8, P.tab_f, P.tab_e, P.half_side, P.RES, je12, jc12, jm12, P.loss);
+      if ((t >> 2) < P.nb) {
+        double2* a = reinterpret_cast<double2*>(P.JE + 12 * t);
+        double2* b = reinterpret_cast<double2*>(P.JF0 + 12 * t);
+        double2* c = reinterpret_cast<double2*>(P.JF1 + 12 * t);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          a[k] = make_double2(je12[2 * k], je12[2 * k + 1]);
+          b[k] = make_double2(jc12[2 * k], jc12[2 * k + 1]);
+          c[k] = make_double2(jm12[2 * k], jm12[2 * k + 1]);
+        }
+      }
+    }
+  }
+  return rig_sum(sq, red);   // its barriers also publish RES / J
+}
+
+// K5: cost only, at the candidate
+template <int MODEL>
+__device__ __forceinline__ double rig_cost_candidate(const RigParams& P, double* red) {
+  rig_tables<MODEL>(P, true);
+  double sq = 0.0;
+  if (MODEL == 0) {
+    for (int64_t o = threadIdx.x; o < P.nb; o += RIG_THREADS) sq += d_cost_a(o, P.ob_e, P.ob_f0, P.uv, P.tabc_f, P.xe_c, P.loss);
+  } else {
+    for (int64_t base = 0; base < 4 * P.nb; base += RIG_THREADS)
+      sq += d_cost_b(base + threadIdx.x, P.nb, P.ob_e, P.ob_f0, P.ob_f1, P.ob_cam, P.obs8, P.tabc_f, P.tabc_e, P.half_side, P.loss);
+  }
+  return rig_sum(sq, red);
+}
+
+// K2, the part that depends on J only (run_normal_parts)
+template <int RD, int DE, int GE>
+__device__ __forceinline__ void rig_normal_parts(const RigParams& P) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = RIG_THREADS / 32;
+  for (int64_t f = warp; f < P.nf; f += NW) {
+    double acc[NV_F];
+    d_fobs_seg<RD>(lane, P.fobs_ptr[f], P.fobs_ptr[f + 1], P.fobs, P.RES, P.JF0, P.JF1, acc);
+#pragma unroll
+    for (int k = 0; k < NV_F; ++k) {
+      const double s = warp_sum(acc[k]);
+      if (lane == 0) P.HG[f * NV_F + k] = s;
+    }
+  }
+  for (int64_t base = 0; base < P.ne * GE; base += RIG_THREADS) d_e_M<RD, DE, GE>(base + threadIdx.x, P.ne, P.e_ptr, P.RES, P.JE, P.ME);
+  if (RD == 8) {   // Model B
+    for (int64_t base = 0; base < P.ninc * RD; base += RIG_THREADS)
+      d_inc_W<RD>(base + threadIdx.x, P.ninc, P.incobs_ptr, P.incobs, P.JE, P.JF0, P.JF1, P.Wt);
+    for (int d = warp; d < P.ndest; d += NW) {
+      double acc[36];
+      d_dobs_seg<RD>(lane, P.dobs_ptr[d], P.dobs_ptr[d + 1], P.dobs, P.JF0, P.JF1, acc);
+#pragma unroll
+      for (int k = 0; k < 36; ++k) {
+        const double s = warp_sum(acc[k]);
+        if (lane == 0) P.Qacc[(int64_t)d * 36 + k] = s;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// gradient norms at x (EvaluateGradientAndJacobian): max and 2-norm over the active blocks
+template <int DE>
+__device__ __forceinline__ void rig_gradient(const RigParams& P, double* red, double& gmax, double& gnorm) {
+  constexpr int NU = DE * (DE + 1) / 2;
+  double mx = 0.0, sq = 0.0;
+  for (int64_t t = threadIdx.x; t < P.ne * DE; t += RIG_THREADS) {
+    double m = 0.0, s = 0.0;
+    d_gradient_norm<DE, NU + DE, NU>(t, P.e_ptr, P.xe, P.se, P.ME, m, s);
+    mx = fmax(mx, m); sq += s;
+  }
+  const double g2e = rig_sum(sq, red);
+  sq = 0.0;
+  for (int64_t t = threadIdx.x; t < P.nf * 6; t += RIG_THREADS) {
+    double m = 0.0, s = 0.0;
+    d_gradient_norm<6, NV_F, 21>(t, P.f_act_ptr, P.xf, P.sf, P.HG, m, s);
+    mx = fmax(mx, m); sq += s;
+  }
+  const double g2f = rig_sum(sq, red);
+  gmax = rig_max(mx, red);
+  gnorm = sqrt(g2e + g2f);
+}
+
+// S = L D L^T in place in shared memory (lower triangle; the diagonal keeps d_k, invd[k] = 1 / d_k), then
+// S y = rhs by one warp.  Returns false (uniformly) when a pivot is not positive.
+__device__ __forceinline__ bool rig_ldlt_solve(double* S, int n, int ld, double* rhs, double* invd, double* __restrict__ y_out, int* flag) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = RIG_THREADS / 32;
+  for (int k = 0; k < n; ++k) {
+    const double d = S[k * ld + k];
+    if (!(d > 0.0) || !isfinite(d)) return false;   // every thread reads the same value after the barrier: uniform
+    const double inv = 1.0 / d;
+    if (threadIdx.x == 0) invd[k] = inv;
+    for (int i = k + 1 + warp; i < n; i += NW) {
+      const double lik = S[i * ld + k] * inv;
+      for (int j = k + 1 + lane; j <= i; j += 32) S[i * ld + j] = fma(-lik, S[j * ld + k], S[i * ld + j]);
+    }
+    __syncthreads();
+  }
+  if (warp == 0) {
+    // forward: w_k = (b_k - sum_{j<k} S'[k][j] w_j) / d_k, column oriented; lane owns rows lane, lane + 32, ...
+    constexpr int MR = (RIG_MAX_N + 31) / 32;
+    double b[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) { const int i = lane + 32 * m; b[m] = i < n ? rhs[i] : 0.0; }
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+      for (int kk = 0; kk < 32; ++kk) {
+        const int k = 32 * m + kk;
+        if (k >= n) break;
+        const double wk = __shfl_sync(0xffffffffu, b[m], kk) * invd[k];
+        if (lane == kk) b[m] = wk;
+#pragma unroll
+        for (int mm = 0; mm < MR; ++mm) {
+          const int i = lane + 32 * mm;
+          if (mm >= m && i > k && i < n) b[mm] = fma(-S[i * ld + k], wk, b[mm]);
+        }
+      }
+    }
+    // backward: x_k = w_k - (sum_{i>k} S'[i][k] x_i) / d_k, row oriented (row k of the lower triangle is contiguous)
+    double acc[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) acc[m] = 0.0;
+#pragma unroll
+    for (int m = MR - 1; m >= 0; --m) {
+      for (int kk = 31; kk >= 0; --kk) {
+        const int k = 32 * m + kk;
+        if (k >= n) continue;
+        const double mine = fma(-acc[m], invd[k], b[m]);   // meaningful in lane kk
+        const double xk = __shfl_sync(0xffffffffu, mine, kk);
+        if (lane == kk) b[m] = xk;
+#pragma unroll
+        for (int mm = 0; mm < MR; ++mm) {
+          const int i = lane + 32 * mm;
+          if (mm <= m && i < k) acc[mm] = fma(S[k * ld + i], xk, acc[mm]);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < MR; ++m) { const int i = lane + 32 * m; if (i < n) y_out[i] = b[m]; }
+  }
+  (void)flag;
+  __syncthreads();
+  return true;
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------------
+template <int RD, int DE, int GE, int NSLOT>
+__global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
+  constexpr int MODEL = RD == 8 ? 1 : 0;
+  constexpr int NU = DE * (DE + 1) / 2;
+  extern __shared__ __align__(16) double dsm[];
+  double* S = dsm;                          // n x ld
+  double* rhs = S + (size_t)P.n * P.ld;     // n
+  double* invd = rhs + P.n;                 // n
+  __shared__ double red[34];
+  __shared__ RigState st;
+  __shared__ int status;
+  __shared__ double sh_radius;
+  __shared__ int sh_flow;                   // thread 0's decision: 0 continue the loop body, 1 next iteration, 2 leave
+  const ba_cuda_options& opt = P.opt;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = RIG_THREADS / 32;
+  if (tid == 0) st = P.begin ? P.init : *P.state;
+  __syncthreads();
+
+  // FinalizeIterationAndCheckIfMinimizerCanContinue (lm_finalize), by thread 0
+  auto finalize = [&](ba_cuda_iteration& row, double t0) -> bool {
+    if (row.step_is_successful) st.n_success++; else st.n_unsuccess++;
+    row.trust_region_radius = st.radius;
+    row.iteration_time_s = rig_now_s() - t0;
+    if (st.n_rows - P.rows_base < RIG_ROWS_CAP) P.rows[st.n_rows - P.rows_base] = row;
+    st.n_rows++;
+    st.last_iteration = row.iteration;
+    st.last_gmax = row.gradient_max_norm; st.last_gnorm = row.gradient_norm;
+    if (row.iteration >= opt.max_num_iterations) { st.term_type = BA_NO_CONVERGENCE; st.term_reason = BA_REASON_MAX_ITERATIONS; return false; }
+    if (row.step_is_successful && row.gradient_max_norm <= opt.gradient_tolerance) { st.term_type = BA_CONVERGENCE; st.term_reason = BA_REASON_GRADIENT_TOLERANCE; return false; }
+    if (row.trust_region_radius <= opt.min_trust_region_radius) { st.term_type = BA_CONVERGENCE; st.term_reason = BA_REASON_MIN_TRUST_REGION_RADIUS; return false; }
+    return true;
+  };
+  auto zero_row = [](ba_cuda_iteration& row) {
+    row.iteration = 0; row.step_is_valid = 0; row.step_is_successful = 0; row.linear_solver_iterations = 0;
+    row.cost = 0.0; row.cost_change = 0.0; row.gradient_max_norm = 0.0; row.gradient_norm = 0.0; row.step_norm = 0.0;
+    row.relative_decrease = 0.0; row.trust_region_radius = 0.0; row.iteration_time_s = 0.0;
+  };
+  // EvaluateGradientAndJacobian at x: cost, gradient norms into st (all threads see them after the barrier inside)
+  auto evaluate = [&](bool first) {
+    if (first) {
+      for (int64_t t = tid; t < P.ne * DE; t += RIG_THREADS) P.se[t] = 1.0;
+      for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS) P.sf[t] = 1.0;
+      __syncthreads();
+    }
+    double cost = rig_jacobian<MODEL>(P, red);
+    rig_normal_parts<RD, DE, GE>(P);
+    if (first && opt.jacobi_scaling) {
+      for (int64_t t = tid; t < P.ne * DE; t += RIG_THREADS) d_jacobi_scale<DE, NU + DE>(t, P.ME, P.se);
+      for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS) d_jacobi_scale<6, NV_F>(t, P.HG, P.sf);
+      __syncthreads();
+      cost = rig_jacobian<MODEL>(P, red);   // same residuals, Jacobian now column scaled
+      rig_normal_parts<RD, DE, GE>(P);
+    }
+    double gmax, gnorm;
+    rig_gradient<DE>(P, red, gmax, gnorm);
+    if (tid == 0) { st.x_cost = 0.5 * cost; st.gmax = gmax; st.gnorm = gnorm; st.n_jac++; }
+    __syncthreads();
+  };
+
+  if (P.begin) {   // TrustRegionMinimizer::IterationZero (lm_begin)
+    const double t0 = rig_now_s();
+    evaluate(true);
+    if (tid == 0) {
+      ba_cuda_iteration row;
+      zero_row(row);
+      if (!isfinite(st.x_cost)) {
+        st.term_type = BA_FAILURE; st.term_reason = BA_REASON_INITIAL_EVALUATION_FAILED; st.go = 0;
+      } else {
+        row.iteration = 0; row.step_is_valid = 1; row.step_is_successful = 1; row.cost = st.x_cost;
+        row.gradient_max_norm = st.gmax; row.gradient_norm = st.gnorm;
+        st.go = finalize(row, t0) ? 1 : 0;
+      }
+    }
+    __syncthreads();
+  }
+
+  for (int32_t it = 0; st.go && it < P.max_new; ++it) {   // lm_iterate; st.go is read after a barrier: uniform
+    const double t0 = rig_now_s();
+    // ---- compute_step -------------------------------------------------------------------------
+    if (tid == 0) { status = 0; sh_radius = st.radius; }
+    __syncthreads();
+    const double radius = sh_radius;
+    for (int64_t e = tid; e < P.ne; e += RIG_THREADS) d_e_chol<DE>(e, P.ME, radius, opt.min_lm_diagonal, opt.max_lm_diagonal, P.Lb, P.zb, &status);
+    __syncthreads();
+    for (int64_t i = tid; i < P.ninc; i += RIG_THREADS) {
+      if (MODEL == 0) d_inc_Y<RD, DE, true>(i, P.inc_e, P.JE, P.JF0, nullptr, P.Lb, P.zb, P.Yt, P.vb);
+      else d_inc_Y<RD, DE, false>(i, P.inc_e, nullptr, nullptr, P.Wt, P.Lb, P.zb, P.Yt, P.vb);
+    }
+    for (int idx = tid; idx < P.n * P.ld; idx += RIG_THREADS) S[idx] = 0.0;
+    __syncthreads();
+    for (int64_t f = warp; f < P.nf; f += NW) {
+      double acc[6];
+      d_finc_seg(lane, P.finc_ptr[f], P.finc_ptr[f + 1], P.finc, P.vb, acc);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double s = warp_sum(acc[k]);
+        if (lane == 0) P.vsum[f * 6 + k] = s;
+      }
+    }
+    for (int d = warp; d < P.ndest; d += NW) {
+      double acc[36];
+      d_pairs_seg<DE>(lane, P.dpair_ptr[d], P.dpair_ptr[d + 1], P.pairs, P.Yt, acc);
+#pragma unroll
+      for (int q = 0; q < 36; ++q) {
+        const double s = warp_sum(acc[q]);
+        if (lane == 0) P.Pacc[(int64_t)d * 36 + q] = s;
+      }
+    }
+    __syncthreads();
+    for (int64_t t = tid; t < (int64_t)P.ndest * 36; t += RIG_THREADS)
+      d_assemble_dense(t, P.dest_fa, P.dest_fb, P.Pacc, MODEL == 1 ? P.Qacc : nullptr, P.ld, S);
+    __syncthreads();
+    for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS)
+      d_diag_rhs_dense(t, P.HG, NV_F, P.vsum, 6, &sh_radius, opt.min_lm_diagonal, opt.max_lm_diagonal, P.ld, S, rhs);
+    __syncthreads();
+    const bool pd = rig_ldlt_solve(S, P.n, P.ld, rhs, invd, P.yf, &status);
+    if (!pd) {
+      for (int t = tid; t < P.n; t += RIG_THREADS) P.yf[t] = 0.0;
+      if (tid == 0) status |= 2;
+      __syncthreads();
+    }
+    for (int64_t base = 0; base < P.ne * GE; base += RIG_THREADS)
+      d_e_backsub<DE, GE>(base + tid, P.ne, P.einc_ptr, P.inc_f, P.Yt, P.Lb, P.zb, P.yf, P.ye);
+    __syncthreads();
+    double acc = 0.0;
+    for (int64_t row = tid; row < P.nb * RD; row += RIG_THREADS)
+      acc += d_model_cost_row<RD, DE, NSLOT>(row, P.ob_e, P.ob_f0, P.ob_f1, P.RES, P.JE, P.JF0, P.JF1, P.ye, P.yf);
+    const double mcc = rig_sum(acc, red);
+    double x2 = 0.0, d2 = 0.0;
+    for (int64_t t = tid; t < P.ne * DE; t += RIG_THREADS) { double a = 0.0, b = 0.0; d_candidate<DE>(t, P.e_ptr, P.xe, P.se, P.ye, P.xe_c, a, b); x2 += a; d2 += b; }
+    const double xe2 = rig_sum(x2, red), de2 = rig_sum(d2, red);
+    x2 = 0.0; d2 = 0.0;
+    for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS) { double a = 0.0, b = 0.0; d_candidate<6>(t, P.f_act_ptr, P.xf, P.sf, P.yf, P.xf_c, a, b); x2 += a; d2 += b; }
+    const double xf2 = rig_sum(x2, red), df2 = rig_sum(d2, red);
+    const double cand = rig_cost_candidate<MODEL>(P, red);
+
+    // ---- the decisions of lm_iterate, by thread 0 ---------------------------------------------
+    ba_cuda_iteration row;
+    if (tid == 0) {
+      zero_row(row);
+      sh_flow = 0;
+      st.n_solves++;
+      row.iteration = st.last_iteration + 1;
+      const double model_cost_change = -mcc;
+      const bool solve_ok = status == 0 && isfinite(model_cost_change);
+      row.step_is_valid = solve_ok && model_cost_change > 0.0;
+      if (!row.step_is_valid) {   // HandleInvalidStep
+        if (++st.num_invalid >= opt.max_num_consecutive_invalid_steps) {
+          st.term_type = BA_FAILURE; st.term_reason = BA_REASON_TOO_MANY_INVALID_STEPS; st.go = 0;
+          sh_flow = 2;
+        } else {
+          st.radius = st.radius / st.decrease_factor; st.decrease_factor *= 2.0;
+          row.cost = st.x_cost; row.cost_change = 0.0;
+          row.gradient_max_norm = st.last_gmax; row.gradient_norm = st.last_gnorm;
+          st.go = finalize(row, t0) ? 1 : 0;
+          sh_flow = 1;
+        }
+      } else {
+        st.num_invalid = 0;
+        const double cand_cost = 0.5 * cand;
+        const double x_norm = sqrt(xe2 + xf2);
+        row.step_norm = sqrt(de2 + df2);
+        row.cost_change = st.x_cost - cand_cost;
+        if (row.step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {   // ParameterToleranceReached
+          st.term_type = BA_CONVERGENCE; st.term_reason = BA_REASON_PARAMETER_TOLERANCE; st.go = 0;
+          sh_flow = 2;
+        } else if (fabs(row.cost_change) <= opt.function_tolerance * st.x_cost) {              // FunctionToleranceReached
+          st.term_type = BA_CONVERGENCE; st.term_reason = BA_REASON_FUNCTION_TOLERANCE; st.go = 0;
+          sh_flow = 2;
+        } else {
+          row.relative_decrease = row.cost_change / model_cost_change;
+          if (row.relative_decrease > opt.min_relative_decrease) {   // HandleSuccessfulStep
+            const double q = 2.0 * row.relative_decrease - 1.0;
+            st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+            st.radius = fmin(opt.max_trust_region_radius, st.radius);
+            st.decrease_factor = 2.0;
+            sh_flow = 3;   // accept: x <- candidate, evaluate there
+          } else {       // HandleUnsuccessfulStep
+            st.radius = st.radius / st.decrease_factor; st.decrease_factor *= 2.0;
+            row.cost = cand_cost;
+            st.go = finalize(row, t0) ? 1 : 0;
+            sh_flow = 1;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int flow = sh_flow;
+    if (flow == 2) break;
+    if (flow == 3) {
+      for (int64_t t = tid; t < P.ne * DE; t += RIG_THREADS) P.xe[t] = P.xe_c[t];
+      for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS) P.xf[t] = P.xf_c[t];
+      __syncthreads();
+      evaluate(false);
+      if (tid == 0) {
+        row.step_is_successful = 1;
+        row.cost = st.x_cost; row.gradient_max_norm = st.gmax; row.gradient_norm = st.gnorm;
+        st.go = finalize(row, t0) ? 1 : 0;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (tid == 0) *P.state = st;
+}
+
+inline size_t rig_smem_bytes(int n) { return sizeof(double) * ((size_t)n * (n | 1) + 2 * (size_t)n + 2); }
+
+}  // namespace ba

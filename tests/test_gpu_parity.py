@@ -631,3 +631,80 @@ def test_before_ba_reprojection_error_from_the_initial_guess(gpu):
     img = pb.obs8.reshape(-1, 2).astype(np.float32)
     err, rms, _ = gpu.project_points_error(corners, cam_of_point, cams, intr, img)
     assert H.rel(err, H.HONGO_COSTS[0]) < 1e-9
+
+
+# ---- the rig-size path: the whole trust-region loop in one launch of one CTA (csrc/ba_rig.cuh) ------------------
+def _rig_cases():
+    pb, intr, side, fix0 = H.hongo()
+    yield "hongo", "B", (pb, intr, side, fix0)
+    pb, intr, side, fix0 = H.test2()
+    yield "test2", "B", (pb, intr, side, fix0)
+    pr = S.marker_rig_b(4, 8, 15, 24, perturb=(0.25, 0.07))   # rejected steps: radius halving / quartering, then recovery
+    pb = F.ModelBFile(pr.n_time, pr.n_cam, pr.n_marker, pr.counts, pr.time_idx, pr.cam_idx, pr.marker_idx, pr.obs8, pr.params)
+    yield "rejected", "B", (pb, pr.intr, pr.marker_side, 1)
+    pa, intr = H.two_cam()
+    yield "two_cam", "A", (pa, intr)
+
+
+@pytest.mark.parametrize("case", list(_rig_cases()), ids=lambda c: c[0])
+def test_rig_path_is_the_same_method_as_the_multi_kernel_pipeline(gpu, oracle, case):
+    name, model, args = case
+
+    def load():
+        if model == "B":
+            _set_b(gpu, *args)
+        else:
+            pa, intr = args
+            gpu.set_model_a(pa.n_cam, pa.n_pt, pa.cam_idx, pa.pt_idx, pa.obs_xy, intr)
+            gpu.set_parameters(pa.params)
+
+    load()
+    s1, rows1 = gpu.solve()
+    x1 = gpu.get_parameters()
+    assert s1.path_used == abi.PATH_RIG
+    with _Env(BA_RIG=0):
+        load()
+        s0, rows0 = gpu.solve()
+        x0 = gpu.get_parameters()
+    assert s0.path_used != abi.PATH_RIG
+    assert (s1.termination_type, s1.termination_reason, s1.num_iterations) == (s0.termination_type, s0.termination_reason, s0.num_iterations)
+    assert (s1.num_successful_steps, s1.num_unsuccessful_steps) == (s0.num_successful_steps, s0.num_unsuccessful_steps)
+    assert (s1.num_jacobian_evaluations, s1.num_linear_solves) == (s0.num_jacobian_evaluations, s0.num_linear_solves)
+    assert H.rel(s1.final_cost, s0.final_cost) <= (COST_RTOL if name != "two_cam" else 1.0) or abs(s1.final_cost) < 1e-10
+    for a, b in zip(rows1, rows0):
+        assert (a["iteration"], a["step_is_valid"], a["step_is_successful"]) == (b["iteration"], b["step_is_valid"], b["step_is_successful"])
+        if name != "two_cam" or b["cost"] > 1e-3:   # two_cam ends in an exact fit: costs ~1e-12 are round-off
+            assert H.rel(a["cost"], b["cost"]) <= 1e-9, (a, b)
+    assert np.abs(x1 - x0).max() < (POSE_ATOL if name != "two_cam" else 1e-6)
+    # the same solve one iteration per call (ba_cuda_solve_begin / _iterate / _end): same rows, bit for bit
+    load()
+    gpu.solve_begin()
+    n_calls = 0
+    while not gpu.solve_iterate(1):
+        n_calls += 1
+        assert n_calls < 100
+    s2, rows2 = gpu.solve_end()
+    assert s2.path_used == abi.PATH_RIG and s2.num_iterations == s1.num_iterations
+    for a, b in zip(rows2, rows1):
+        assert a["cost"] == b["cost"] and a["trust_region_radius"] == b["trust_region_radius"]
+    assert np.array_equal(gpu.get_parameters(), x1)
+
+
+def test_rig_path_with_a_robust_loss_and_without_jacobi_scaling(gpu, oracle):
+    pb, intr, side, fix0 = H.hongo()
+    for kw in (dict(loss_function=abi.LOSS_HUBER, loss_scale=1.5), dict(jacobi_scaling=0)):
+        opt = cuda.default_options()
+        for k, v in kw.items():
+            setattr(opt, k, v)
+        _set_b(gpu, pb, intr, side, fix0)
+        s1, rows1 = gpu.solve(opt)
+        x1 = gpu.get_parameters()
+        assert s1.path_used == abi.PATH_RIG
+        with _Env(BA_RIG=0):
+            _set_b(gpu, pb, intr, side, fix0)
+            s0, rows0 = gpu.solve(opt)
+            x0 = gpu.get_parameters()
+        assert s0.path_used == abi.PATH_GENERIC and s1.num_iterations == s0.num_iterations
+        for a, b in zip(rows1, rows0):
+            assert H.rel(a["cost"], b["cost"]) <= 1e-9 and a["step_is_successful"] == b["step_is_successful"]
+        assert np.abs(x1 - x0).max() < POSE_ATOL
