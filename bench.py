@@ -233,10 +233,14 @@ def run_steps(P, opts, k):
     while done < k:
         n = min(ITERS_PER_SOLVE, k - done)
         P.restore_parameters()
-        P.solve_begin(opts)
-        P.solve_iterate(n)
+        if n == opts.max_num_iterations:   # the one-call API (what BAManager::Solve uses): ba_cuda_solve
+            out = P.solve(opts)
+        else:
+            P.solve_begin(opts)
+            P.solve_iterate(n)
+            out = P.solve_end()
         done += n
-    return P.solve_end()
+    return out
 
 
 def oracle_steps(job, k, threads):
@@ -498,7 +502,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic" if wl["kind"] != "hongo" else "reference fixture (tests/golden)",
             "config": config_of(job, a.workload, world, summary.rcs_solver_used, summary.rcs_dim),
-            "path_used": {0: "generic", 1: "fused_tiles", 2: "fused_strips"}.get(int(summary.path_used), "?"),
+            "path_used": {0: "generic", 1: "fused_tiles", 2: "fused_strips", 3: "rig_one_cta"}.get(int(summary.path_used), "?"),
             "parity": parity, "us_per_solve": 1e3 * ms / K * ITERS_PER_SOLVE,
             "jacobian_mobs_per_sec": jac_mobs, "jacobian": jacobian, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "final_cost_last_solve": float(summary.final_cost), "ms_per_step_profiled_pass": ms_prof / K,

@@ -1030,6 +1030,10 @@ int rig_run(ba_cuda_problem* p, bool begin, int32_t max_new) {
   P.state = reinterpret_cast<RigState*>(p->rig_buf.p);
   P.rows = reinterpret_cast<ba_cuda_iteration*>(p->rig_buf.p + sizeof(RigState));
   P.opt = L.opt; P.loss = p->loss;
+  static const bool clocks = env_int("BA_RIG_CLOCKS", 0, 1, 0) != 0;
+  P.dbg = env_int("BA_RIG_DBG", 0, 255, 0);
+  DVec<long long> clk;
+  if (clocks) { BA_TRY(clk.alloc_zero(16, p->st)); P.clk = clk.p; }
   int64_t left = max_new;
   bool first = begin;
   while (first || (L.go && left > 0)) {
@@ -1067,6 +1071,15 @@ int rig_run(ba_cuda_problem* p, bool begin, int32_t max_new) {
     if (!L.go) { Z.termination_type = st.term_type; Z.termination_reason = st.term_reason; }
     left -= P.max_new;
     first = false;
+    if (clocks) {
+      long long h[16];
+      BA_CUDA_TRY(cudaMemcpy(h, clk.p, sizeof(h), cudaMemcpyDeviceToHost));
+      static const char* const nm[13] = {"jacobian", "normal_parts", "gradient", "e_chol+inc_Y", "vsum+pairs", "assemble+diag", "ldlt+solve",
+                                         "backsub+model_cost", "candidate", "cost_candidate", "decision", "other", "of_which_triangular_solves"};
+      std::fprintf(stderr, "[ba_cuda rig clocks] rows=%d", st.n_rows);
+      for (int k = 0; k < 13; ++k) std::fprintf(stderr, " %s=%lld", nm[k], h[k]);
+      std::fprintf(stderr, "\n");
+    }
   }
   return BA_OK;
 }

@@ -52,6 +52,8 @@ struct RigParams {
   int32_t begin;      // 1: start from `init` and run iteration zero first (TrustRegionMinimizer::IterationZero)
   int32_t max_new;    // at most this many loop iterations in this launch (begin + max_new <= RIG_ROWS_CAP)
   RigState init;
+  int dbg;            // BA_RIG_DBG: timing experiments only (results are wrong)
+  long long* clk;     // BA_RIG_CLOCKS=1: SM cycles per phase (16 slots), thread 0's view
   ba_cuda_options opt;
   LossSpec loss;
 };
@@ -77,16 +79,50 @@ __device__ __forceinline__ double rig_now_s() {
   return 1e-9 * (double)t;
 }
 
+// Sum of 36 values over a group of 8 lanes by halving: after three exchanges every lane holds 5 (or 4) of the 36 sums and
+// stores them (32 shuffles instead of the 108 of a butterfly per value).  Whole warps call this; fixed order.
+__device__ __forceinline__ void group8_sum36_store(const double* acc, int lane, double* __restrict__ dst, bool live) {
+  const bool b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+  double v1[18], v2[9], v3[5];
+#pragma unroll
+  for (int q = 0; q < 18; ++q) {
+    const double send = b2 ? acc[q] : acc[18 + q], keep = b2 ? acc[18 + q] : acc[q];
+    v1[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    const double send = b1 ? v1[q] : v1[9 + q], keep = b1 ? v1[9 + q] : v1[q];
+    v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {   // bit 0 clear keeps [0, 5), set keeps [5, 9)
+    const double hi = q < 4 ? v2[5 + q] : 0.0;
+    const double send = b0 ? v2[q] : hi, keep = b0 ? hi : v2[q];
+    v3[q] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  if (live) {
+    const int base = (b2 ? 18 : 0) + (b1 ? 9 : 0) + (b0 ? 5 : 0), cnt = b0 ? 4 : 5;
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+      if (q < cnt) dst[base + q] = v3[q];
+  }
+}
+
 // tables at x (candidate = false) or at the candidate point
 template <int MODEL>
 __device__ __forceinline__ void rig_tables(const RigParams& P, bool candidate) {
   const double* xf = candidate ? P.xf_c : P.xf;
   double* tf = candidate ? P.tabc_f : P.tab_f;
-  for (int64_t i = threadIdx.x; i < P.nf; i += RIG_THREADS) d_tables(i, xf, P.intr_f, P.sf, tf);
-  if (MODEL == 1) {
+  if (MODEL == 1) {   // one pass over both kinds of block (sin / cos make this the longest per-thread chain of the evaluation)
     const double* xe = candidate ? P.xe_c : P.xe;
     double* te = candidate ? P.tabc_e : P.tab_e;
-    for (int64_t i = threadIdx.x; i < P.ne; i += RIG_THREADS) d_tables(i, xe, nullptr, P.se, te);
+    for (int64_t i = threadIdx.x; i < P.nf + P.ne; i += RIG_THREADS) {
+      const bool isf = i < P.nf;
+      const int64_t j = isf ? i : i - P.nf;
+      d_tables(j, isf ? xf : xe, isf ? P.intr_f : nullptr, isf ? P.sf : P.se, isf ? tf : te);
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < P.nf; i += RIG_THREADS) d_tables(i, xf, P.intr_f, P.sf, tf);
   }
   __syncthreads();
 }
@@ -163,14 +199,28 @@ __device__ __forceinline__ void rig_normal_parts(const RigParams& P) {
   if (RD == 8) {   // Model B
     for (int64_t base = 0; base < P.ninc * RD; base += RIG_THREADS)
       d_inc_W<RD>(base + threadIdx.x, P.ninc, P.incobs_ptr, P.incobs, P.JE, P.JF0, P.JF1, P.Wt);
-    for (int d = warp; d < P.ndest; d += NW) {
+    // a destination of a rig holds a handful of observations (the frames that saw the pair): 8 lanes (= rows) per destination
+    for (int base = 0; base < P.ndest; base += RIG_THREADS / 8) {
+      const int d = base + (threadIdx.x >> 3), r = threadIdx.x & 7;
+      const bool live = d < P.ndest;
       double acc[36];
-      d_dobs_seg<RD>(lane, P.dobs_ptr[d], P.dobs_ptr[d + 1], P.dobs, P.JF0, P.JF1, acc);
 #pragma unroll
-      for (int k = 0; k < 36; ++k) {
-        const double s = warp_sum(acc[k]);
-        if (lane == 0) P.Qacc[(int64_t)d * 36 + k] = s;
+      for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+      if (live) {
+        const int64_t end = P.dobs_ptr[d + 1];
+#pragma unroll 2
+        for (int64_t idx = P.dobs_ptr[d]; idx < end; ++idx) {
+          const int64_t row = (int64_t)RD * P.dobs[idx] + r;
+          double ra[6], rb[6];
+          load_row6(P.JF0 + row * 6, ra);
+          load_row6(P.JF1 + row * 6, rb);
+#pragma unroll
+          for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = 0; b < 6; ++b) acc[a * 6 + b] = fma(ra[a], rb[b], acc[a * 6 + b]);
+        }
       }
+      group8_sum36_store(acc, lane, P.Qacc + (int64_t)(live ? d : 0) * 36, live);
     }
   }
   __syncthreads();
@@ -198,65 +248,152 @@ __device__ __forceinline__ void rig_gradient(const RigParams& P, double* red, do
   gnorm = sqrt(g2e + g2f);
 }
 
-// S = L D L^T in place in shared memory (lower triangle; the diagonal keeps d_k, invd[k] = 1 / d_k), then
-// S y = rhs by one warp.  Returns false (uniformly) when a pivot is not positive.
-__device__ __forceinline__ bool rig_ldlt_solve(double* S, int n, int ld, double* rhs, double* invd, double* __restrict__ y_out, int* flag) {
+// S = L' D^-1 L'^T in place in shared memory (lower triangle; L' keeps the pivots d_k on its diagonal, invd[k] = 1 / d_k),
+// blocked by panels of 8 columns: (a) warp 0 factorises the 8 x 8 diagonal block in registers (lane = row, shuffles for the
+// pivot rows); (b) one thread per row below solves its 8 panel entries against that block; (c) rank-8 update of the
+// trailing triangle, a warp per row, a lane per column.  Three barriers per 8 columns.  Then S y = rhs by one warp.
+// Returns false (uniformly) when a pivot is not positive.
+__device__ __forceinline__ bool rig_ldlt_solve(double* S, int n, int ld, double* rhs, double* invd, double* tacc, double* blk /* 64 + 1 */,
+                                               double* __restrict__ y_out, long long* sclk, int dbg = 0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = RIG_THREADS / 32;
-  for (int k = 0; k < n; ++k) {
-    const double d = S[k * ld + k];
-    if (!(d > 0.0) || !isfinite(d)) return false;   // every thread reads the same value after the barrier: uniform
-    const double inv = 1.0 / d;
-    if (threadIdx.x == 0) invd[k] = inv;
-    for (int i = k + 1 + warp; i < n; i += NW) {
-      const double lik = S[i * ld + k] * inv;
-      for (int j = k + 1 + lane; j <= i; j += 32) S[i * ld + j] = fma(-lik, S[j * ld + k], S[i * ld + j]);
+  constexpr int NB = 8;
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int w = min(NB, n - k0);
+    if (threadIdx.x == 0) {   // (a): a lone warp runs ~6 cycles per instruction, so the fewest instructions win: one thread, the
+                              // whole 8 x 8 block in registers, no shuffles, no predicates
+      double a[NB][NB];
+#pragma unroll
+      for (int r = 0; r < NB; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = r < w ? S[(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
+      bool ok = true;
+#pragma unroll
+      for (int kk = 0; kk < NB; ++kk) {
+        const double d = a[kk][kk];
+        const double inv = (d > 0.0 && isfinite(d)) ? __drcp_rn(d) : 0.0;   // = 1.0 / d, correctly rounded
+        ok = ok && inv != 0.0;
+        if (kk < w) invd[k0 + kk] = inv;
+#pragma unroll
+        for (int r = kk + 1; r < NB; ++r) {
+          const double lrk = a[r][kk] * inv;   // L'[r][kk] / d_kk
+          blk[r * NB + kk] = lrk;              // the block scaled by D^-1, for (b)
+#pragma unroll
+          for (int c = kk + 1; c <= r; ++c) a[r][c] = fma(-lrk, a[c][kk], a[r][c]);
+        }
+      }
+#pragma unroll
+      for (int r = 1; r < NB; ++r)
+#pragma unroll
+        for (int c = 1; c <= r; ++c)
+          if (r < w) S[(k0 + r) * ld + k0 + c] = a[r][c];
+      blk[NB * NB] = ok ? 1.0 : 0.0;
     }
     __syncthreads();
-  }
-  if (warp == 0) {
-    // forward: w_k = (b_k - sum_{j<k} S'[k][j] w_j) / d_k, column oriented; lane owns rows lane, lane + 32, ...
-    constexpr int MR = (RIG_MAX_N + 31) / 32;
-    double b[MR];
+    if (blk[NB * NB] == 0.0) return false;
+    const int m = n - k0 - w;   // rows below the panel (w == NB whenever m > 0)
+    if (m > 0) {
+      for (int r = threadIdx.x; r < m; r += RIG_THREADS) {   // (b)
+        double* row = S + (k0 + NB + r) * ld + k0;
+        double x[NB];
 #pragma unroll
-    for (int m = 0; m < MR; ++m) { const int i = lane + 32 * m; b[m] = i < n ? rhs[i] : 0.0; }
+        for (int c = 0; c < NB; ++c) x[c] = row[c];
 #pragma unroll
-    for (int m = 0; m < MR; ++m) {
-      for (int kk = 0; kk < 32; ++kk) {
-        const int k = 32 * m + kk;
-        if (k >= n) break;
-        const double wk = __shfl_sync(0xffffffffu, b[m], kk) * invd[k];
-        if (lane == kk) b[m] = wk;
+        for (int kk = 1; kk < NB; ++kk) {
 #pragma unroll
-        for (int mm = 0; mm < MR; ++mm) {
-          const int i = lane + 32 * mm;
-          if (mm >= m && i > k && i < n) b[mm] = fma(-S[i * ld + k], wk, b[mm]);
+          for (int q = 0; q < kk; ++q) x[kk] = fma(-x[q], blk[kk * NB + q], x[kk]);
+        }
+#pragma unroll
+        for (int c = 1; c < NB; ++c) row[c] = x[c];
+      }
+      __syncthreads();
+      double iv[NB];
+#pragma unroll
+      for (int kk = 0; kk < NB; ++kk) iv[kk] = invd[k0 + kk];
+#pragma unroll 1
+      for (int r = warp; r < m; r += NW) {   // (c)
+        double* row = S + (k0 + NB + r) * ld + k0;
+        double li[NB];
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) li[kk] = row[kk] * iv[kk];
+#pragma unroll 1
+        for (int c = lane; c <= r; c += 32) {
+          const double* rj = S + (k0 + NB + c) * ld + k0;
+          double acc = row[NB + c];
+#pragma unroll
+          for (int kk = 0; kk < NB; ++kk) acc = fma(-li[kk], rj[kk], acc);
+          row[NB + c] = acc;
         }
       }
+      __syncthreads();
     }
-    // backward: x_k = w_k - (sum_{i>k} S'[i][k] x_i) / d_k, row oriented (row k of the lower triangle is contiguous)
-    double acc[MR];
-#pragma unroll
-    for (int m = 0; m < MR; ++m) acc[m] = 0.0;
-#pragma unroll
-    for (int m = MR - 1; m >= 0; --m) {
-      for (int kk = 31; kk >= 0; --kk) {
-        const int k = 32 * m + kk;
-        if (k >= n) continue;
-        const double mine = fma(-acc[m], invd[k], b[m]);   // meaningful in lane kk
-        const double xk = __shfl_sync(0xffffffffu, mine, kk);
-        if (lane == kk) b[m] = xk;
-#pragma unroll
-        for (int mm = 0; mm < MR; ++mm) {
-          const int i = lane + 32 * mm;
-          if (mm <= m && i < k) acc[mm] = fma(S[k * ld + i], xk, acc[mm]);
-        }
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < MR; ++m) { const int i = lane + 32 * m; if (i < n) y_out[i] = b[m]; }
   }
-  (void)flag;
+  long long t_f = 0;
+  if (sclk && threadIdx.x == 0) t_f = clock64();
+  if (!(dbg & 4)) {
+    // forward, L' u = rhs  (u_k = (b_k - sum_{j<k} L'[k][j] u_j) / d_k), by panels of 8: warp 0 finishes the panel's 8
+    // unknowns (lane = row, one broadcast per unknown), then one thread per row below subtracts the panel's contribution
+    for (int k0 = 0; k0 < n; k0 += NB) {
+      const int w = min(NB, n - k0);
+      if (warp == 0) {   // everything the 8 dependent steps need is loaded first: a step is a broadcast, a product, an fma
+        const int rl = lane < w ? lane : 0;
+        const double* lrow = S + (k0 + rl) * ld + k0;
+        double bv = lane < w ? rhs[k0 + lane] : 0.0;
+        double lv[NB], iv[NB];
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) { lv[kk] = (kk < lane && lane < w) ? lrow[kk] : 0.0; iv[kk] = kk < w ? invd[k0 + kk] : 0.0; }
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) {
+          const double uk = __shfl_sync(0xffffffffu, bv, kk) * iv[kk];
+          bv = lane == kk ? uk : fma(-lv[kk], uk, bv);   // lv is zero for the rows already finished
+        }
+        if (lane < w) rhs[k0 + lane] = bv;
+      }
+      __syncthreads();
+      for (int i = k0 + NB + threadIdx.x; i < n; i += RIG_THREADS) {
+        const double* row = S + i * ld + k0;
+        double bv = rhs[i];
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) bv = fma(-row[kk], rhs[k0 + kk], bv);
+        rhs[i] = bv;
+      }
+      __syncthreads();
+    }
+    // backward, L'^T x = D u  (x_k = u_k - (sum_{i>k} L'[i][k] x_i) / d_k), panels from the last: tacc[k] collects the sum over
+    // the rows already solved; warp 0 finishes the panel, then one thread per row above adds the panel's contribution
+    for (int i = threadIdx.x; i < n; i += RIG_THREADS) tacc[i] = 0.0;
+    __syncthreads();
+    for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
+      const int w = min(NB, n - k0);
+      if (warp == 0) {
+        double av = lane < w ? tacc[k0 + lane] : 0.0;
+        const double uv = lane < w ? rhs[k0 + lane] : 0.0;
+        const double iv = lane < w ? invd[k0 + lane] : 0.0;
+        double lv[NB];   // column `lane` of the block: L'[k0 + kk][k0 + lane], kk > lane
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) lv[kk] = (lane < kk && kk < w) ? S[(k0 + kk) * ld + k0 + lane] : 0.0;
+        double xv = 0.0;
+#pragma unroll
+        for (int kk = NB - 1; kk >= 0; --kk) {
+          const double mine = fma(-av, iv, uv);   // meaningful in lane kk once the rows below it are in av
+          const double xk = __shfl_sync(0xffffffffu, mine, kk);
+          if (lane == kk) xv = xk;
+          av = fma(lv[kk], xk, av);
+        }
+        if (lane < w) { rhs[k0 + lane] = xv; y_out[k0 + lane] = xv; }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < k0; i += RIG_THREADS) {
+        double av = tacc[i];
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk)
+          if (kk < w) av = fma(S[(k0 + kk) * ld + i], rhs[k0 + kk], av);
+        tacc[i] = av;
+      }
+      __syncthreads();
+    }
+  }
+  if (sclk && threadIdx.x == 0) sclk[12] += clock64() - t_f;
   __syncthreads();
   return true;
 }
@@ -270,13 +407,19 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
   double* S = dsm;                          // n x ld
   double* rhs = S + (size_t)P.n * P.ld;     // n
   double* invd = rhs + P.n;                 // n
+  double* tacc = invd + P.n;                // n: the backward solve's running sums
+  double* blk = tacc + P.n;                 // 65: the scaled diagonal block of the current panel, and its verdict
   __shared__ double red[34];
   __shared__ RigState st;
   __shared__ int status;
   __shared__ double sh_radius;
   __shared__ int sh_flow;                   // thread 0's decision: 0 continue the loop body, 1 next iteration, 2 leave
+  __shared__ long long sclk[16];
+  long long clk_last = 0;
   const ba_cuda_options& opt = P.opt;
   const int tid = threadIdx.x;
+  if (P.clk && tid == 0) { for (int k = 0; k < 16; ++k) sclk[k] = 0; clk_last = clock64(); }
+  auto lap = [&](int slot) { if (P.clk && tid == 0) { const long long now = clock64(); sclk[slot] += now - clk_last; clk_last = now; } };
   const int lane = tid & 31, warp = tid >> 5;
   constexpr int NW = RIG_THREADS / 32;
   if (tid == 0) st = P.begin ? P.init : *P.state;
@@ -301,47 +444,60 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
     row.cost = 0.0; row.cost_change = 0.0; row.gradient_max_norm = 0.0; row.gradient_norm = 0.0; row.step_norm = 0.0;
     row.relative_decrease = 0.0; row.trust_region_radius = 0.0; row.iteration_time_s = 0.0;
   };
-  // EvaluateGradientAndJacobian at x: cost, gradient norms into st (all threads see them after the barrier inside)
-  auto evaluate = [&](bool first) {
-    if (first) {
-      for (int64_t t = tid; t < P.ne * DE; t += RIG_THREADS) P.se[t] = 1.0;
-      for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS) P.sf[t] = 1.0;
-      __syncthreads();
-    }
-    double cost = rig_jacobian<MODEL>(P, red);
-    rig_normal_parts<RD, DE, GE>(P);
-    if (first && opt.jacobi_scaling) {
-      for (int64_t t = tid; t < P.ne * DE; t += RIG_THREADS) d_jacobi_scale<DE, NU + DE>(t, P.ME, P.se);
-      for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS) d_jacobi_scale<6, NV_F>(t, P.HG, P.sf);
-      __syncthreads();
-      cost = rig_jacobian<MODEL>(P, red);   // same residuals, Jacobian now column scaled
-      rig_normal_parts<RD, DE, GE>(P);
-    }
-    double gmax, gnorm;
-    rig_gradient<DE>(P, red, gmax, gnorm);
-    if (tid == 0) { st.x_cost = 0.5 * cost; st.gmax = gmax; st.gnorm = gnorm; st.n_jac++; }
-    __syncthreads();
-  };
-
-  if (P.begin) {   // TrustRegionMinimizer::IterationZero (lm_begin)
-    const double t0 = rig_now_s();
-    evaluate(true);
-    if (tid == 0) {
-      ba_cuda_iteration row;
-      zero_row(row);
-      if (!isfinite(st.x_cost)) {
-        st.term_type = BA_FAILURE; st.term_reason = BA_REASON_INITIAL_EVALUATION_FAILED; st.go = 0;
-      } else {
-        row.iteration = 0; row.step_is_valid = 1; row.step_is_successful = 1; row.cost = st.x_cost;
-        row.gradient_max_norm = st.gmax; row.gradient_norm = st.gnorm;
-        st.go = finalize(row, t0) ? 1 : 0;
+  // One loop, one copy of every phase: at its top EvaluateGradientAndJacobian when a row is waiting for it (row 0 of
+  // IterationZero / lm_begin, or the row of an accepted step), then the body of lm_iterate.
+  bool need_eval = P.begin != 0, first = P.begin != 0;
+  ba_cuda_iteration row;
+  double t0 = rig_now_s();
+  int32_t it = 0;
+  for (;;) {
+    if (need_eval) {
+      if (first) {
+        for (int64_t t = tid; t < P.ne * DE; t += RIG_THREADS) P.se[t] = 1.0;
+        for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS) P.sf[t] = 1.0;
+        __syncthreads();
       }
+      const int passes = (first && opt.jacobi_scaling) ? 2 : 1;   // iteration 0: the second pass has the Jacobian column scaled
+      double cost = 0.0;
+      lap(11);
+#pragma unroll 1
+      for (int pass = 0; pass < passes; ++pass) {
+        if (pass == 1) {
+          for (int64_t t = tid; t < P.ne * DE; t += RIG_THREADS) d_jacobi_scale<DE, NU + DE>(t, P.ME, P.se);
+          for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS) d_jacobi_scale<6, NV_F>(t, P.HG, P.sf);
+          __syncthreads();
+        }
+        cost = rig_jacobian<MODEL>(P, red);
+        lap(0);
+        rig_normal_parts<RD, DE, GE>(P);
+        lap(1);
+      }
+      double gmax, gnorm;
+      rig_gradient<DE>(P, red, gmax, gnorm);
+      lap(2);
+      if (tid == 0) {
+        st.x_cost = 0.5 * cost; st.gmax = gmax; st.gnorm = gnorm; st.n_jac++;
+        if (first) {
+          zero_row(row);
+          if (!isfinite(st.x_cost)) {
+            st.term_type = BA_FAILURE; st.term_reason = BA_REASON_INITIAL_EVALUATION_FAILED; st.go = 0;
+          } else {
+            row.iteration = 0; row.step_is_valid = 1; row.step_is_successful = 1; row.cost = st.x_cost;
+            row.gradient_max_norm = st.gmax; row.gradient_norm = st.gnorm;
+            st.go = finalize(row, t0) ? 1 : 0;
+          }
+        } else {
+          row.step_is_successful = 1;
+          row.cost = st.x_cost; row.gradient_max_norm = st.gmax; row.gradient_norm = st.gnorm;
+          st.go = finalize(row, t0) ? 1 : 0;
+        }
+      }
+      __syncthreads();
+      need_eval = false; first = false;
     }
-    __syncthreads();
-  }
-
-  for (int32_t it = 0; st.go && it < P.max_new; ++it) {   // lm_iterate; st.go is read after a barrier: uniform
-    const double t0 = rig_now_s();
+    if (!st.go || it >= P.max_new) break;   // st.go is read after a barrier: uniform
+    ++it;
+    t0 = rig_now_s();
     // ---- compute_step -------------------------------------------------------------------------
     if (tid == 0) { status = 0; sh_radius = st.radius; }
     __syncthreads();
@@ -354,6 +510,7 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
     }
     for (int idx = tid; idx < P.n * P.ld; idx += RIG_THREADS) S[idx] = 0.0;
     __syncthreads();
+    lap(3);
     for (int64_t f = warp; f < P.nf; f += NW) {
       double acc[6];
       d_finc_seg(lane, P.finc_ptr[f], P.finc_ptr[f + 1], P.finc, P.vb, acc);
@@ -363,23 +520,52 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
         if (lane == 0) P.vsum[f * 6 + k] = s;
       }
     }
-    for (int d = warp; d < P.ndest; d += NW) {
-      double acc[36];
-      d_pairs_seg<DE>(lane, P.dpair_ptr[d], P.dpair_ptr[d + 1], P.pairs, P.Yt, acc);
+    if (P.ndest >= 2 * NW) {   // many destinations with short pair lists (a rig): 8 lanes (= rows of Yt) per destination
+      for (int base = 0; base < P.ndest; base += RIG_THREADS / 8) {
+        const int d = base + (tid >> 3), r = tid & 7;
+        const bool live = d < P.ndest;
+        double acc[36];
 #pragma unroll
-      for (int q = 0; q < 36; ++q) {
-        const double s = warp_sum(acc[q]);
-        if (lane == 0) P.Pacc[(int64_t)d * 36 + q] = s;
+        for (int q = 0; q < 36; ++q) acc[q] = 0.0;
+        if (live && r < DE) {
+          const int64_t end = P.dpair_ptr[d + 1];
+#pragma unroll 2
+          for (int64_t idx = P.dpair_ptr[d]; idx < end; ++idx) {
+            const int2 pr = P.pairs[idx];
+            if (pr.x < 0) continue;
+            double yi[6], yj[6];
+            load_row6(P.Yt + ((int64_t)DE * pr.x + r) * 6, yi);
+            load_row6(P.Yt + ((int64_t)DE * pr.y + r) * 6, yj);
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+              for (int b = 0; b < 6; ++b) acc[a * 6 + b] = fma(yi[a], yj[b], acc[a * 6 + b]);
+          }
+        }
+        group8_sum36_store(acc, lane, P.Pacc + (int64_t)(live ? d : 0) * 36, live);
+      }
+    } else {
+      for (int d = warp; d < P.ndest; d += NW) {
+        double acc[36];
+        d_pairs_seg<DE>(lane, P.dpair_ptr[d], P.dpair_ptr[d + 1], P.pairs, P.Yt, acc);
+#pragma unroll
+        for (int q = 0; q < 36; ++q) {
+          const double s = warp_sum(acc[q]);
+          if (lane == 0) P.Pacc[(int64_t)d * 36 + q] = s;
+        }
       }
     }
     __syncthreads();
+    lap(4);
     for (int64_t t = tid; t < (int64_t)P.ndest * 36; t += RIG_THREADS)
       d_assemble_dense(t, P.dest_fa, P.dest_fb, P.Pacc, MODEL == 1 ? P.Qacc : nullptr, P.ld, S);
     __syncthreads();
     for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS)
       d_diag_rhs_dense(t, P.HG, NV_F, P.vsum, 6, &sh_radius, opt.min_lm_diagonal, opt.max_lm_diagonal, P.ld, S, rhs);
     __syncthreads();
-    const bool pd = rig_ldlt_solve(S, P.n, P.ld, rhs, invd, P.yf, &status);
+    lap(5);
+    const bool pd = rig_ldlt_solve(S, P.n, P.ld, rhs, invd, tacc, blk, P.yf, P.clk ? sclk : nullptr, P.dbg);
+    lap(6);
     if (!pd) {
       for (int t = tid; t < P.n; t += RIG_THREADS) P.yf[t] = 0.0;
       if (tid == 0) status |= 2;
@@ -389,8 +575,9 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
       d_e_backsub<DE, GE>(base + tid, P.ne, P.einc_ptr, P.inc_f, P.Yt, P.Lb, P.zb, P.yf, P.ye);
     __syncthreads();
     double acc = 0.0;
-    for (int64_t row = tid; row < P.nb * RD; row += RIG_THREADS)
-      acc += d_model_cost_row<RD, DE, NSLOT>(row, P.ob_e, P.ob_f0, P.ob_f1, P.RES, P.JE, P.JF0, P.JF1, P.ye, P.yf);
+    for (int64_t rr = tid; rr < P.nb * RD; rr += RIG_THREADS)
+      acc += d_model_cost_row<RD, DE, NSLOT>(rr, P.ob_e, P.ob_f0, P.ob_f1, P.RES, P.JE, P.JF0, P.JF1, P.ye, P.yf);
+    lap(7);
     const double mcc = rig_sum(acc, red);
     double x2 = 0.0, d2 = 0.0;
     for (int64_t t = tid; t < P.ne * DE; t += RIG_THREADS) { double a = 0.0, b = 0.0; d_candidate<DE>(t, P.e_ptr, P.xe, P.se, P.ye, P.xe_c, a, b); x2 += a; d2 += b; }
@@ -398,10 +585,11 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
     x2 = 0.0; d2 = 0.0;
     for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS) { double a = 0.0, b = 0.0; d_candidate<6>(t, P.f_act_ptr, P.xf, P.sf, P.yf, P.xf_c, a, b); x2 += a; d2 += b; }
     const double xf2 = rig_sum(x2, red), df2 = rig_sum(d2, red);
+    lap(8);
     const double cand = rig_cost_candidate<MODEL>(P, red);
+    lap(9);
 
     // ---- the decisions of lm_iterate, by thread 0 ---------------------------------------------
-    ba_cuda_iteration row;
     if (tid == 0) {
       zero_row(row);
       sh_flow = 0;
@@ -451,25 +639,21 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
       }
     }
     __syncthreads();
+    lap(10);
     const int flow = sh_flow;
     if (flow == 2) break;
     if (flow == 3) {
       for (int64_t t = tid; t < P.ne * DE; t += RIG_THREADS) P.xe[t] = P.xe_c[t];
       for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS) P.xf[t] = P.xf_c[t];
       __syncthreads();
-      evaluate(false);
-      if (tid == 0) {
-        row.step_is_successful = 1;
-        row.cost = st.x_cost; row.gradient_max_norm = st.gmax; row.gradient_norm = st.gnorm;
-        st.go = finalize(row, t0) ? 1 : 0;
-      }
-      __syncthreads();
+      need_eval = true;
     }
   }
   __syncthreads();
   if (tid == 0) *P.state = st;
+  if (P.clk && tid == 0) for (int k = 0; k < 16; ++k) P.clk[k] = sclk[k];
 }
 
-inline size_t rig_smem_bytes(int n) { return sizeof(double) * ((size_t)n * (n | 1) + 2 * (size_t)n + 2); }
+inline size_t rig_smem_bytes(int n) { return sizeof(double) * ((size_t)n * (n | 1) + 3 * (size_t)n + 66); }
 
 }  // namespace ba

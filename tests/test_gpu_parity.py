@@ -502,10 +502,10 @@ def test_strip_path_matches_tile_path_and_oracle(gpu, oracle, name):
         o.max_num_iterations = 6
         o.rcs_solver = abi.RCS_DENSE_CHOLESKY
     xo, so, rows_o = oracle.solve_model_a(pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params, options=opt_o, n_threads=4)
-    with _Env(BA_SA=2):   # 2 = strips whenever the problem fits (the default also asks for >= 4 pair products per observation)
+    with _Env(BA_SA=2, BA_RIG=0):   # 2 = strips whenever the problem fits (the default also asks for >= 4 pair products per observation)
         s1, rows1, x1 = _solve_a(gpu, pr, opt_g)
     assert s1.path_used == abi.PATH_FUSED_STRIPS
-    with _Env(BA_SA=0):
+    with _Env(BA_SA=0, BA_RIG=0):   # BA_RIG=0: the rig is small enough for the one-CTA path (tested further down)
         s0, rows0, x0 = _solve_a(gpu, pr, opt_g)
     assert s0.path_used == abi.PATH_FUSED_TILES
     _check_rows(rows1, rows_o)
