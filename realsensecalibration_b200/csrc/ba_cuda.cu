@@ -996,8 +996,9 @@ int ensure_generic_workspace(ba_cuda_problem* p);
 bool rig_eligible(const ba_cuda_problem* p, const ba_cuda_options& opt) {
   const bool on = env_int("BA_RIG", 0, 1, 1) != 0;   // read per solve: tests run both machines in one process
   const int64_t rows = p->S.nb * (p->model == 0 ? 2 : 8);
+  const int64_t max_rows = env_int("BA_RIG_MAX_ROWS", 0, 1 << 30, (int)RIG_MAX_ROWS);   // tuning aid (profiles/tools/rig_crossover.py)
   return on && p->world == 1 && !opt.force_generic_path && p->solver == BA_RCS_DENSE_CHOLESKY && p->n_rcs() <= RIG_MAX_N &&
-         rows <= RIG_MAX_ROWS;
+         rows <= max_rows;
 }
 
 template <int RD, int DE, int GE, int NSLOT>

@@ -17,7 +17,7 @@ namespace ba {
 constexpr int RIG_THREADS = 512;        // 128 registers per thread: the item functions keep whole tables and 36 accumulators
 constexpr int RIG_ROWS_CAP = 256;       // iteration rows one launch can record
 constexpr int RIG_MAX_N = 160;       // reduced camera system dimension that fits shared memory (n * (n | 1) doubles)
-constexpr int64_t RIG_MAX_ROWS = 16384;   // residual rows (nb * RD): beyond this the multi-kernel pipeline is the better machine
+constexpr int64_t RIG_MAX_ROWS = 8192;    // residual rows (nb * RD); measured crossover with the multi-kernel pipeline ~9k rows (profiles/r02_rig_crossover.txt)
 
 struct RigState {   // LmState of ba_cuda.cu, on the device
   double radius, decrease_factor, x_cost, gmax, gnorm;
