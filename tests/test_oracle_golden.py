@@ -132,3 +132,98 @@ def test_jet_jacobian_vs_complex_step(oracle):
                 args[bi][k] += 1e-30j
                 d = f(o, *args).imag / 1e-30
                 assert np.abs(d - J[:, k]).max() <= 1e-9 * max(1.0, np.abs(d).max())
+
+
+def test_model_a_pinned_independently_of_the_cpp_oracle(oracle):
+    """Model A (Test1_BundleAdjustment/bundle_adjustmenter.cpp:122-141) pinned without the C++ oracle's own arithmetic:
+    the projection by cv2.projectPoints, the Jacobian by a numpy complex-step twin of the functor, and the whole
+    trust-region loop by a dense numpy restatement of Ceres' LM (Jacobi scaling, D = sqrt(clamp(diag) / radius), the
+    cubic radius update) on Common/Correspondence/two_cam_data.txt.  The C++ oracle (Schur path) must reproduce all three."""
+    cv2 = pytest.importorskip("cv2")
+    pa, intr = H.two_cam()
+    K = np.array([[intr[0], 0, intr[2]], [0, intr[1], intr[3]], [0, 0, 1.0]])
+    n_cam, n_pt, nobs = pa.n_cam, pa.n_pt, len(pa.cam_idx)
+    obs = np.asarray(pa.obs_xy, np.float64).reshape(-1, 2)
+
+    def rot(w, p):
+        t2 = w @ w
+        if t2.real > np.finfo(float).eps:
+            t = np.sqrt(t2); k = w / t
+            return p * np.cos(t) + np.cross(k, p) * np.sin(t) + k * (k @ p) * (1 - np.cos(t))
+        return p + np.cross(w, p)
+
+    def residuals(x):
+        out = np.zeros(2 * nobs, dtype=x.dtype)
+        for o in range(nobs):
+            cam = x[6 * pa.cam_idx[o]:][:6]
+            X = x[6 * n_cam + 3 * pa.pt_idx[o]:][:3]
+            p = rot(cam[:3], X) + cam[3:]
+            out[2 * o] = intr[0] * p[0] / p[2] + intr[2] - obs[o, 0]
+            out[2 * o + 1] = intr[1] * p[1] / p[2] + intr[3] - obs[o, 1]
+        return out
+
+    def jacobian(x):
+        J = np.zeros((2 * nobs, x.size))
+        for k in range(x.size):
+            xc = x.astype(complex); xc[k] += 1e-30j
+            J[:, k] = residuals(xc).imag / 1e-30
+        return J
+
+    x0 = np.asarray(pa.params, np.float64)
+    # (1) the projection: OpenCV's pinhole model, no distortion
+    cost_o, res_o, jac_o = oracle.eval_model_a(n_cam, n_pt, pa.cam_idx, pa.pt_idx, pa.obs_xy, intr, x0)
+    for o in range(nobs):
+        cam = x0[6 * pa.cam_idx[o]:][:6]
+        X = x0[6 * n_cam + 3 * pa.pt_idx[o]:][:3]
+        uv, _ = cv2.projectPoints(X.reshape(1, 1, 3), cam[:3].copy(), cam[3:].copy(), K, None)
+        assert np.abs(uv.ravel() - obs[o] - res_o[o]).max() < 1e-9
+    # (2) the Jacobian: complex step against the oracle's dual numbers
+    J0 = jacobian(x0)
+    assert np.abs(residuals(x0) - res_o.ravel()).max() < 1e-10
+    for o in range(nobs):
+        jc = J0[2 * o:2 * o + 2, 6 * pa.cam_idx[o]:][:, :6]
+        jp = J0[2 * o:2 * o + 2, 6 * n_cam + 3 * pa.pt_idx[o]:][:, :3]
+        mine = np.concatenate([jc.ravel(), jp.ravel()])
+        assert np.abs(mine - jac_o[o]).max() <= 1e-9 * max(1.0, np.abs(mine).max()), o
+    # (3) the trust-region loop, dense normal equations in numpy
+    opt = oracle.default_options()
+    x = x0.copy()
+    radius, decrease = opt.initial_trust_region_radius, 2.0
+    r, J = residuals(x), J0
+    scale = 1.0 / (1.0 + np.sqrt((J * J).sum(axis=0)))
+    cost = 0.5 * r @ r
+    costs, reason = [cost], None
+    for it in range(opt.max_num_iterations):
+        Js = J * scale
+        H_ = Js.T @ Js
+        D2 = np.clip(np.diag(H_), opt.min_lm_diagonal, opt.max_lm_diagonal) / radius
+        delta = np.linalg.solve(H_ + np.diag(D2), -(Js.T @ r))
+        Jd = Js @ delta
+        model_change = -(Jd @ (r + Jd / 2))
+        assert model_change > 0
+        xn = x + scale * delta
+        if np.linalg.norm(scale * delta) <= opt.parameter_tolerance * (np.linalg.norm(x) + opt.parameter_tolerance):
+            reason = abi.REASON_PARAMETER_TOLERANCE
+            break
+        rn = residuals(xn)
+        cost_n = 0.5 * rn @ rn
+        if abs(cost - cost_n) <= opt.function_tolerance * cost:
+            reason = abi.REASON_FUNCTION_TOLERANCE
+            break
+        rho = (cost - cost_n) / model_change
+        if rho > opt.min_relative_decrease:
+            x, r, cost = xn, rn, cost_n
+            J = jacobian(x)
+            radius = min(opt.max_trust_region_radius, radius / max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3))
+            decrease = 2.0
+            costs.append(cost)
+        else:
+            radius /= decrease; decrease *= 2.0
+            costs.append(cost_n)
+    xo, so, rows_o = oracle.solve_model_a(n_cam, n_pt, pa.cam_idx, pa.pt_idx, pa.obs_xy, intr, pa.params)
+    assert reason == so.termination_reason == abi.REASON_PARAMETER_TOLERANCE
+    assert len(costs) == so.num_iterations == 3
+    assert H.rel(costs[0], rows_o[0]["cost"]) < 1e-12 and H.rel(costs[0], H.TWO_CAM_COSTS[0]) < 1e-11
+    assert H.rel(costs[1], rows_o[1]["cost"]) < 1e-7 and H.rel(costs[1], H.TWO_CAM_COSTS[1]) < 1e-7
+    assert costs[2] < 1e-10 and rows_o[2]["cost"] < 1e-10
+    assert np.abs(x - xo).max() < 1e-6
