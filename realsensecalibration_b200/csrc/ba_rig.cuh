@@ -249,10 +249,11 @@ __device__ __forceinline__ void rig_gradient(const RigParams& P, double* red, do
 }
 
 // S = L' D^-1 L'^T in place in shared memory (lower triangle; L' keeps the pivots d_k on its diagonal, invd[k] = 1 / d_k),
-// blocked by panels of 8 columns: (a) warp 0 factorises the 8 x 8 diagonal block in registers (lane = row, shuffles for the
-// pivot rows); (b) one thread per row below solves its 8 panel entries against that block; (c) rank-8 update of the
-// trailing triangle, a warp per row, a lane per column.  Three barriers per 8 columns.  Then S y = rhs by one warp.
-// Returns false (uniformly) when a pivot is not positive.
+// blocked by panels of 8 columns: (a) ONE thread factorises the 8 x 8 diagonal block in its registers; (b) one thread per row
+// below solves its 8 panel entries against that block; (c) rank-8 update of the trailing triangle, a warp per row, a lane
+// per column.  Three barriers per 8 columns.  The right-hand side is row n of S and rides through (b) and (c): that is the
+// forward substitution.  The backward substitution runs by panels too (8 dependent steps in warp 0, then one thread per row
+// above).  Returns false (uniformly) when a pivot is not positive.
 __device__ __forceinline__ bool rig_ldlt_solve(double* S, int n, int ld, double* rhs, double* invd, double* tacc, double* blk /* 64 + 1 */,
                                                double* __restrict__ y_out, long long* sclk, int dbg = 0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -263,10 +264,18 @@ __device__ __forceinline__ bool rig_ldlt_solve(double* S, int n, int ld, double*
     if (threadIdx.x == 0) {   // (a): a lone warp runs ~6 cycles per instruction, so the fewest instructions win: one thread, the
                               // whole 8 x 8 block in registers, no shuffles, no predicates
       double a[NB][NB];
+      double* blk0 = S + k0 * ld + k0;
+      if (w == NB) {
 #pragma unroll
-      for (int r = 0; r < NB; ++r)
+        for (int r = 0; r < NB; ++r)
 #pragma unroll
-        for (int c = 0; c <= r; ++c) a[r][c] = r < w ? S[(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
+          for (int c = 0; c <= r; ++c) a[r][c] = blk0[r * ld + c];
+      } else {   // the last, partial panel: identity below its w rows
+#pragma unroll
+        for (int r = 0; r < NB; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) a[r][c] = r < w ? blk0[r * ld + c] : (r == c ? 1.0 : 0.0);
+      }
       bool ok = true;
 #pragma unroll
       for (int kk = 0; kk < NB; ++kk) {
@@ -282,43 +291,56 @@ __device__ __forceinline__ bool rig_ldlt_solve(double* S, int n, int ld, double*
           for (int c = kk + 1; c <= r; ++c) a[r][c] = fma(-lrk, a[c][kk], a[r][c]);
         }
       }
+      if (w == NB) {
 #pragma unroll
-      for (int r = 1; r < NB; ++r)
+        for (int r = 1; r < NB; ++r)
 #pragma unroll
-        for (int c = 1; c <= r; ++c)
-          if (r < w) S[(k0 + r) * ld + k0 + c] = a[r][c];
+          for (int c = 1; c <= r; ++c) blk0[r * ld + c] = a[r][c];
+      } else {
+#pragma unroll
+        for (int r = 1; r < NB; ++r)
+#pragma unroll
+          for (int c = 1; c <= r; ++c)
+            if (r < w) blk0[r * ld + c] = a[r][c];
+      }
       blk[NB * NB] = ok ? 1.0 : 0.0;
     }
     __syncthreads();
     if (blk[NB * NB] == 0.0) return false;
-    const int m = n - k0 - w;   // rows below the panel (w == NB whenever m > 0)
-    if (m > 0) {
-      for (int r = threadIdx.x; r < m; r += RIG_THREADS) {   // (b)
-        double* row = S + (k0 + NB + r) * ld + k0;
-        double x[NB];
+    // rows below the panel, and the right-hand side as one more row (row n of S): its panel solve and trailing update ARE the
+    // forward substitution, so after the last panel row n holds v_k = d_k u_k of L' u = rhs at no extra dependent step
+    const int i0 = k0 + w;
+    const int m = n + 1 - i0;
+    for (int r = threadIdx.x; r < m; r += RIG_THREADS) {   // (b)
+      double* row = S + (i0 + r) * ld + k0;
+      double x[NB];
 #pragma unroll
-        for (int c = 0; c < NB; ++c) x[c] = row[c];
+      for (int c = 0; c < NB; ++c) x[c] = c < w ? row[c] : 0.0;
 #pragma unroll
-        for (int kk = 1; kk < NB; ++kk) {
+      for (int kk = 1; kk < NB; ++kk) {
 #pragma unroll
-          for (int q = 0; q < kk; ++q) x[kk] = fma(-x[q], blk[kk * NB + q], x[kk]);
-        }
-#pragma unroll
-        for (int c = 1; c < NB; ++c) row[c] = x[c];
+        for (int q = 0; q < kk; ++q) x[kk] = fma(-x[q], blk[kk * NB + q], x[kk]);
       }
-      __syncthreads();
+#pragma unroll
+      for (int c = 1; c < NB; ++c)
+        if (c < w) row[c] = x[c];
+    }
+    __syncthreads();
+    if (i0 < n) {   // (c); w == NB here
       double iv[NB];
 #pragma unroll
       for (int kk = 0; kk < NB; ++kk) iv[kk] = invd[k0 + kk];
+      const int cols = n - i0;   // trailing columns
 #pragma unroll 1
-      for (int r = warp; r < m; r += NW) {   // (c)
-        double* row = S + (k0 + NB + r) * ld + k0;
+      for (int r = warp; r < m; r += NW) {
+        double* row = S + (i0 + r) * ld + k0;
         double li[NB];
 #pragma unroll
         for (int kk = 0; kk < NB; ++kk) li[kk] = row[kk] * iv[kk];
+        const int cmax = min(r, cols - 1);
 #pragma unroll 1
-        for (int c = lane; c <= r; c += 32) {
-          const double* rj = S + (k0 + NB + c) * ld + k0;
+        for (int c = lane; c <= cmax; c += 32) {
+          const double* rj = S + (i0 + c) * ld + k0;
           double acc = row[NB + c];
 #pragma unroll
           for (int kk = 0; kk < NB; ++kk) acc = fma(-li[kk], rj[kk], acc);
@@ -331,35 +353,7 @@ __device__ __forceinline__ bool rig_ldlt_solve(double* S, int n, int ld, double*
   long long t_f = 0;
   if (sclk && threadIdx.x == 0) t_f = clock64();
   if (!(dbg & 4)) {
-    // forward, L' u = rhs  (u_k = (b_k - sum_{j<k} L'[k][j] u_j) / d_k), by panels of 8: warp 0 finishes the panel's 8
-    // unknowns (lane = row, one broadcast per unknown), then one thread per row below subtracts the panel's contribution
-    for (int k0 = 0; k0 < n; k0 += NB) {
-      const int w = min(NB, n - k0);
-      if (warp == 0) {   // everything the 8 dependent steps need is loaded first: a step is a broadcast, a product, an fma
-        const int rl = lane < w ? lane : 0;
-        const double* lrow = S + (k0 + rl) * ld + k0;
-        double bv = lane < w ? rhs[k0 + lane] : 0.0;
-        double lv[NB], iv[NB];
-#pragma unroll
-        for (int kk = 0; kk < NB; ++kk) { lv[kk] = (kk < lane && lane < w) ? lrow[kk] : 0.0; iv[kk] = kk < w ? invd[k0 + kk] : 0.0; }
-#pragma unroll
-        for (int kk = 0; kk < NB; ++kk) {
-          const double uk = __shfl_sync(0xffffffffu, bv, kk) * iv[kk];
-          bv = lane == kk ? uk : fma(-lv[kk], uk, bv);   // lv is zero for the rows already finished
-        }
-        if (lane < w) rhs[k0 + lane] = bv;
-      }
-      __syncthreads();
-      for (int i = k0 + NB + threadIdx.x; i < n; i += RIG_THREADS) {
-        const double* row = S + i * ld + k0;
-        double bv = rhs[i];
-#pragma unroll
-        for (int kk = 0; kk < NB; ++kk) bv = fma(-row[kk], rhs[k0 + kk], bv);
-        rhs[i] = bv;
-      }
-      __syncthreads();
-    }
-    // backward, L'^T x = D u  (x_k = u_k - (sum_{i>k} L'[i][k] x_i) / d_k), panels from the last: tacc[k] collects the sum over
+    // backward, L'^T x = v  (x_k = (v_k - sum_{i>k} L'[i][k] x_i) / d_k; v = row n of S), panels from the last: tacc[k] collects the sum over
     // the rows already solved; warp 0 finishes the panel, then one thread per row above adds the panel's contribution
     for (int i = threadIdx.x; i < n; i += RIG_THREADS) tacc[i] = 0.0;
     __syncthreads();
@@ -375,7 +369,7 @@ __device__ __forceinline__ bool rig_ldlt_solve(double* S, int n, int ld, double*
         double xv = 0.0;
 #pragma unroll
         for (int kk = NB - 1; kk >= 0; --kk) {
-          const double mine = fma(-av, iv, uv);   // meaningful in lane kk once the rows below it are in av
+          const double mine = (uv - av) * iv;   // meaningful in lane kk once the rows below it are in av
           const double xk = __shfl_sync(0xffffffffu, mine, kk);
           if (lane == kk) xv = xk;
           av = fma(lv[kk], xk, av);
@@ -405,8 +399,8 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
   constexpr int NU = DE * (DE + 1) / 2;
   extern __shared__ __align__(16) double dsm[];
   double* S = dsm;                          // n x ld
-  double* rhs = S + (size_t)P.n * P.ld;     // n
-  double* invd = rhs + P.n;                 // n
+  double* rhs = S + (size_t)P.n * P.ld;     // row n of S: the right-hand side rides through the factorisation
+  double* invd = rhs + P.ld;                // n
   double* tacc = invd + P.n;                // n: the backward solve's running sums
   double* blk = tacc + P.n;                 // 65: the scaled diagonal block of the current panel, and its verdict
   __shared__ double red[34];
@@ -654,6 +648,6 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
   if (P.clk && tid == 0) for (int k = 0; k < 16; ++k) P.clk[k] = sclk[k];
 }
 
-inline size_t rig_smem_bytes(int n) { return sizeof(double) * ((size_t)n * (n | 1) + 3 * (size_t)n + 66); }
+inline size_t rig_smem_bytes(int n) { return sizeof(double) * (((size_t)n + 1) * (n | 1) + 2 * (size_t)n + 66); }
 
 }  // namespace ba
