@@ -280,6 +280,14 @@ int allreduce_with_grad_tail(ba_cuda_problem* p, double* buf, size_t n) {
 int dense_solve(ba_cuda_problem* p, int64_t n) {
   // measured on B200: n = 132 (cfg2) 0.18 ms blocked vs 0.24 ms single CTA; below ~96 the single CTA wins (one launch, no grid barrier)
   static const int smem_max_n = env_int("BA_DENSE_SMEM_MAX_N", 0, CHOL_SMEM_MAX_N, 96);
+  static const bool ldlt = env_int("BA_DENSE_LDLT", 0, 1, 1) != 0;
+  if (ldlt && n <= RIG_MAX_N) {   // the panel LDL^T of the rig kernel, one CTA, matrix in shared memory (ba_rig.cuh)
+    const size_t smem = rig_smem_bytes((int)n);
+    if (smem > 48 * 1024) BA_CUDA_TRY(cudaFuncSetAttribute(k_ldlt_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rig_smem_bytes(RIG_MAX_N)));
+    k_ldlt_small<<<1, RIG_THREADS, smem, p->st>>>((int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p);
+    BA_CUDA_TRY(cudaGetLastError());
+    return BA_OK;
+  }
   if (n <= smem_max_n) return launch_chol_solve((int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p, p->st);
   return launch_chol_blocked(p->cholb, (int)n, p->Sd.p, p->rhs.p, p->yf.p, p->status.p, p->device, p->st);
 }

@@ -648,6 +648,30 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
   if (P.clk && tid == 0) for (int k = 0; k < 16; ++k) P.clk[k] = sclk[k];
 }
 
+// The same factorisation as a kernel of its own: the dense reduced-system solve of the multi-kernel pipeline for n <= RIG_MAX_N
+// (S row-major n x n in HBM, not modified).  status bit 1 is raised when a pivot is not positive.
+__global__ void __launch_bounds__(RIG_THREADS, 1)
+k_ldlt_small(int n, const double* __restrict__ Sg, const double* __restrict__ rhs_g, double* __restrict__ y, int* status) {
+  extern __shared__ __align__(16) double dsm[];
+  const int ld = n | 1;
+  double* S = dsm;
+  double* rhs = S + (size_t)n * ld;
+  double* invd = rhs + ld;
+  double* tacc = invd + n;
+  double* blk = tacc + n;
+  for (int idx = threadIdx.x; idx < n * n; idx += RIG_THREADS) {
+    const int i = idx / n, j = idx - i * n;
+    S[i * ld + j] = Sg[idx];
+  }
+  for (int i = threadIdx.x; i < n; i += RIG_THREADS) rhs[i] = rhs_g[i];
+  __syncthreads();
+  if (!rig_ldlt_solve(S, n, ld, rhs, invd, tacc, blk, y, nullptr)) {
+    for (int i = threadIdx.x; i < n; i += RIG_THREADS) y[i] = 0.0;
+    if (threadIdx.x == 0) atomicOr(status, 2);
+  }
+}
+
 inline size_t rig_smem_bytes(int n) { return sizeof(double) * (((size_t)n + 1) * (n | 1) + 2 * (size_t)n + 66); }
 
 }  // namespace ba
+
