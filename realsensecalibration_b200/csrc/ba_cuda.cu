@@ -1792,8 +1792,15 @@ int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32
   p->n_params = 6 * ((int64_t)n_cam + n_time + n_marker);
   p->half_side = marker_side / 2;
   const int64_t nf = (int64_t)n_cam + n_marker;
-  BA_TRY(build_structure(p->S, n_mobs, n_time, nf, time_idx, f0.data(), f1.data(), p->st,
-                         [](const int32_t*, const int32_t*) { return (int)BA_OK; }));  // validated above, on the host
+  PhaseTimer T;
+  // rig sizes: the lists are made on the host and uploaded in one copy (ba_structure.cuh, build_structure_host_b)
+  const int64_t host_build_max = env_int("BA_HOST_BUILD_MAX", 0, 1 << 20, 4096);
+  if (n_mobs > 0 && n_mobs <= host_build_max && p->world == 1)
+    BA_TRY(build_structure_host_b(p->S, n_mobs, n_time, nf, time_idx, f0.data(), f1.data(), p->st));
+  else
+    BA_TRY(build_structure(p->S, n_mobs, n_time, nf, time_idx, f0.data(), f1.data(), p->st,
+                           [](const int32_t*, const int32_t*) { return (int)BA_OK; }));  // validated above, on the host
+  T.lap("build_structure");
   p->model = 1;
   {
     DVec<double> tmp;
@@ -1810,11 +1817,16 @@ int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32
     BA_TRY(p->intr_f.upload(K.data(), K.size(), p->st));
     BA_CUDA_TRY(cudaStreamSynchronize(p->st));
   }
+  T.lap("observations upload");
   p->h_perm.clear();
   BA_TRY(alloc_workspace(p, 8, 6));
+  T.lap("alloc_workspace");
   p->use_fused = false;
   BA_TRY(ensure_generic_workspace(p));
-  return build_activity(p);
+  T.lap("generic workspace");
+  const int rc_act = build_activity(p);
+  T.lap("build_activity");
+  return rc_act;
 }
 
 int64_t ba_cuda_num_parameters(const ba_cuda_problem* p) { return p ? p->n_params : 0; }

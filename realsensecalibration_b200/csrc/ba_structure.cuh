@@ -10,6 +10,8 @@
 // Replaces what ceres::Problem::AddResidualBlock + Program/ParameterBlockOrdering build on
 // the host (reference call sites: bundle_adjustment_manager.cpp:37,50,67,81).
 #pragma once
+#include <algorithm>
+
 #include "ba_util.cuh"
 
 namespace ba {
@@ -53,6 +55,7 @@ struct Structure {
   DVec<int64_t> dobs_ptr;  // nslots == 2 only: dest -> obs having (f0,f1) == (fa,fb)
   DVec<int32_t> dobs;
   Chunks ch_fobs, ch_finc, ch_pairs, ch_dobs;
+  DVec<unsigned char> arena;   // host-built structures (build_structure_host_b): the one allocation every list is a view into
 };
 
 // ---- small setup kernels ---------------------------------------------------------------
@@ -502,6 +505,189 @@ inline int build_structure(Structure& S, int64_t nb, int64_t ne, int64_t nf, con
   if (S.nslots == 2) BA_TRY(build_chunks(S.ch_dobs, S.dobs_ptr.p, S.ndest, 128, st));
   BA_CUDA_TRY(cudaStreamSynchronize(st));
   BA_CUDA_TRY(cudaGetLastError());
+  return BA_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// The same structure built on the HOST, for rig-size two-slot problems (the reference's own: tens to a few thousand marker
+// observations).  build_structure() above is made for 30 M observations: a dozen radix sorts and scans, each a launch or
+// three, and ten stream synchronisations to read counts back -- 0.46 ms for hongo's 68 observations, as long as the whole
+// solve.  Here every list is made by the same rules (stable sorts by the same keys, so the orders -- and with them the
+// summation orders of every kernel -- are identical to the device build's, bit for bit), laid out in ONE host buffer,
+// uploaded with ONE copy into ONE allocation (S.arena); the DVecs of the structure are views into it.
+// ---------------------------------------------------------------------------------------
+struct HostArena {
+  std::vector<unsigned char> buf;
+  template <typename T>
+  size_t put(const std::vector<T>& v) {   // returns the offset
+    const size_t off = (buf.size() + 255) / 256 * 256;
+    buf.resize(off + std::max<size_t>(v.size(), 1) * sizeof(T), 0);
+    if (!v.empty()) std::memcpy(buf.data() + off, v.data(), v.size() * sizeof(T));
+    return off;
+  }
+};
+
+inline void host_csr(const std::vector<int32_t>& sorted_keys, int64_t nseg, std::vector<int64_t>& ptr) {   // k_seg_ptr
+  ptr.assign(nseg + 1, 0);
+  size_t pos = 0;
+  for (int64_t s2 = 0; s2 <= nseg; ++s2) {
+    while (pos < sorted_keys.size() && (int64_t)sorted_keys[pos] < s2) ++pos;
+    ptr[s2] = (int64_t)pos;
+  }
+}
+// sort_to_csr on the host: stable by key, invalid entries (INT32_MAX) at the tail
+inline void host_sort_to_csr(const std::vector<int32_t>& keys, const std::vector<int32_t>& vals, int64_t nseg, std::vector<int64_t>& ptr,
+                             std::vector<int32_t>& vals_out) {
+  std::vector<int32_t> order(keys.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return keys[a] < keys[b]; });
+  std::vector<int32_t> ks(keys.size());
+  vals_out.resize(keys.size());
+  for (size_t i = 0; i < order.size(); ++i) { ks[i] = keys[order[i]]; vals_out[i] = vals[order[i]]; }
+  host_csr(ks, nseg, ptr);
+}
+struct HostChunks { int n = 0; std::vector<int32_t> seg, seg_first; std::vector<int64_t> begin; };
+inline void host_chunks(const std::vector<int64_t>& ptr, int nseg, int ch, HostChunks& C) {   // build_chunks
+  C.seg_first.assign(nseg + 1, 0);
+  for (int s2 = 0; s2 < nseg; ++s2) C.seg_first[s2 + 1] = C.seg_first[s2] + (int32_t)((ptr[s2 + 1] - ptr[s2] + ch - 1) / ch);
+  C.n = C.seg_first[nseg];
+  C.seg.resize(C.n); C.begin.resize(C.n);
+  for (int s2 = 0; s2 < nseg; ++s2) {
+    int64_t b = ptr[s2];
+    for (int c = C.seg_first[s2]; c < C.seg_first[s2 + 1]; ++c, b += ch) { C.seg[c] = s2; C.begin[c] = b; }
+  }
+}
+
+inline int build_structure_host_b(Structure& S, int64_t nb, int64_t ne, int64_t nf, const int32_t* h_e, const int32_t* h_f0,
+                                  const int32_t* h_f1, cudaStream_t st) {
+  S.nb = nb; S.ne = ne; S.nf = nf; S.nslots = 2;
+  // 1. observations sorted by e (stable)
+  std::vector<int32_t> perm(nb), ob_e(nb), ob_f0(nb), ob_f1(nb);
+  for (int64_t i = 0; i < nb; ++i) perm[i] = (int32_t)i;
+  std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return h_e[a] < h_e[b]; });
+  for (int64_t i = 0; i < nb; ++i) { ob_e[i] = h_e[perm[i]]; ob_f0[i] = h_f0[perm[i]]; ob_f1[i] = h_f1[perm[i]]; }
+  std::vector<int64_t> e_ptr;
+  host_csr(ob_e, ne, e_ptr);
+  // 2. incidences: the distinct (e, f) of the two slots, ascending
+  std::vector<uint64_t> uniq;
+  uniq.reserve(2 * nb);
+  for (int64_t i = 0; i < nb; ++i) {
+    if (ob_f0[i] >= 0) uniq.push_back((uint64_t)ob_e[i] * nf + ob_f0[i]);
+    if (ob_f1[i] >= 0) uniq.push_back((uint64_t)ob_e[i] * nf + ob_f1[i]);
+  }
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  const int64_t ninc = (int64_t)uniq.size();
+  S.ninc = ninc;
+  std::vector<int32_t> inc_e(ninc), inc_f(ninc), ob_inc0(nb), ob_inc1(nb), ik(2 * nb), iv(2 * nb);
+  for (int64_t i = 0; i < ninc; ++i) { inc_e[i] = (int32_t)(uniq[i] / nf); inc_f[i] = (int32_t)(uniq[i] % nf); }
+  auto find_inc = [&](uint64_t key) { return (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), key) - uniq.begin()); };
+  for (int64_t i = 0; i < nb; ++i) {
+    const int32_t a = ob_f0[i] >= 0 ? find_inc((uint64_t)ob_e[i] * nf + ob_f0[i]) : -1;
+    const int32_t b = ob_f1[i] >= 0 ? find_inc((uint64_t)ob_e[i] * nf + ob_f1[i]) : -1;
+    ob_inc0[i] = a; ob_inc1[i] = b;
+    ik[2 * i] = a >= 0 ? a : INT32_MAX; iv[2 * i] = (int32_t)(i << 1);
+    ik[2 * i + 1] = b >= 0 ? b : INT32_MAX; iv[2 * i + 1] = (int32_t)(i << 1) | 1;
+  }
+  std::vector<int64_t> incobs_ptr, einc_ptr;
+  std::vector<int32_t> incobs;
+  host_sort_to_csr(ik, iv, ninc, incobs_ptr, incobs);
+  host_csr(inc_e, ne, einc_ptr);
+  // 3. f -> incidences, f -> observations
+  std::vector<int32_t> inc_iota(ninc), finc, fobs, fk(2 * nb), fv(2 * nb);
+  for (int64_t i = 0; i < ninc; ++i) inc_iota[i] = (int32_t)i;
+  std::vector<int64_t> finc_ptr, fobs_ptr;
+  host_sort_to_csr(inc_f, inc_iota, nf, finc_ptr, finc);
+  for (int64_t i = 0; i < nb; ++i) {
+    fk[2 * i] = ob_f0[i] >= 0 ? ob_f0[i] : INT32_MAX; fv[2 * i] = (int32_t)(i << 1);
+    fk[2 * i + 1] = ob_f1[i] >= 0 ? ob_f1[i] : INT32_MAX; fv[2 * i + 1] = (int32_t)(i << 1) | 1;
+  }
+  host_sort_to_csr(fk, fv, nf, fobs_ptr, fobs);
+  // 4. destination blocks with their incidence-pair lists (build_pair_lists)
+  std::vector<uint64_t> pk, pv;
+  for (int64_t e = 0; e < ne; ++e)
+    for (int64_t i = einc_ptr[e]; i < einc_ptr[e + 1]; ++i)
+      for (int64_t j = einc_ptr[e]; j < einc_ptr[e + 1]; ++j)
+        if (inc_f[i] <= inc_f[j]) {
+          pk.push_back((uint64_t)inc_f[i] * nf + inc_f[j]);
+          pv.push_back((uint64_t)(uint32_t)i | ((uint64_t)(uint32_t)j << 32));
+        }
+  for (int64_t f = 0; f < nf; ++f) { pk.push_back((uint64_t)f * nf + f); pv.push_back(~0ull); }
+  const int64_t npairs = (int64_t)pk.size();
+  S.npairs = npairs;
+  std::vector<int64_t> order(npairs);
+  for (int64_t i = 0; i < npairs; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return pk[a] < pk[b]; });
+  std::vector<uint64_t> dest_keys;
+  std::vector<int64_t> dpair_ptr;
+  std::vector<int2> pairs(npairs);
+  for (int64_t i = 0; i < npairs; ++i) {
+    const uint64_t k = pk[order[i]], v = pv[order[i]];
+    if (dest_keys.empty() || dest_keys.back() != k) { dest_keys.push_back(k); dpair_ptr.push_back(i); }
+    pairs[i] = make_int2((int32_t)(uint32_t)(v & 0xffffffffu), (int32_t)(uint32_t)(v >> 32));
+  }
+  dpair_ptr.push_back(npairs);
+  const int ndest = (int)dest_keys.size();
+  S.ndest = ndest;
+  std::vector<int32_t> dest_fa(ndest), dest_fb(ndest), diag_dest(nf, 0);
+  for (int d = 0; d < ndest; ++d) {
+    dest_fa[d] = (int32_t)(dest_keys[d] / nf); dest_fb[d] = (int32_t)(dest_keys[d] % nf);
+    if (dest_fa[d] == dest_fb[d]) diag_dest[dest_fa[d]] = d;
+  }
+  // 5. observations whose (f0, f1) is a destination block
+  std::vector<uint64_t> ffk(nb);
+  std::vector<int32_t> dobs(nb);
+  for (int64_t i = 0; i < nb; ++i) { ffk[i] = (ob_f0[i] >= 0 && ob_f1[i] >= 0) ? (uint64_t)ob_f0[i] * nf + ob_f1[i] : ~0ull; dobs[i] = (int32_t)i; }
+  std::stable_sort(dobs.begin(), dobs.end(), [&](int32_t a, int32_t b) { return ffk[a] < ffk[b]; });
+  std::vector<uint64_t> ffs(nb);
+  for (int64_t i = 0; i < nb; ++i) ffs[i] = ffk[dobs[i]];
+  std::vector<int64_t> dobs_ptr(ndest + 1);
+  for (int d = 0; d <= ndest; ++d)
+    dobs_ptr[d] = (int64_t)(std::lower_bound(ffs.begin(), ffs.end(), d < ndest ? dest_keys[d] : ~0ull) - ffs.begin());
+  // 6. chunk tables
+  HostChunks c_fobs, c_finc, c_pairs, c_dobs;
+  host_chunks(fobs_ptr, (int)nf, 256, c_fobs);
+  host_chunks(finc_ptr, (int)nf, 512, c_finc);
+  host_chunks(dpair_ptr, ndest, 256, c_pairs);
+  host_chunks(dobs_ptr, ndest, 128, c_dobs);
+
+  // one buffer, one allocation, one copy
+  HostArena A;
+  const size_t o_perm = A.put(perm), o_ob_e = A.put(ob_e), o_ob_f0 = A.put(ob_f0), o_ob_f1 = A.put(ob_f1), o_e_ptr = A.put(e_ptr);
+  const size_t o_inc_e = A.put(inc_e), o_inc_f = A.put(inc_f), o_inc0 = A.put(ob_inc0), o_inc1 = A.put(ob_inc1), o_einc = A.put(einc_ptr);
+  const size_t o_iop = A.put(incobs_ptr), o_io = A.put(incobs), o_fip = A.put(finc_ptr), o_fi = A.put(finc), o_fop = A.put(fobs_ptr), o_fo = A.put(fobs);
+  const size_t o_dfa = A.put(dest_fa), o_dfb = A.put(dest_fb), o_dd = A.put(diag_dest), o_dk = A.put(dest_keys);
+  const size_t o_dpp = A.put(dpair_ptr), o_pairs = A.put(pairs), o_dop = A.put(dobs_ptr), o_do = A.put(dobs);
+  struct CO { size_t seg, begin, first; };
+  auto put_chunks = [&](const HostChunks& C) { return CO{A.put(C.seg), A.put(C.begin), A.put(C.seg_first)}; };
+  const CO k_fobs = put_chunks(c_fobs), k_finc = put_chunks(c_finc), k_pairs = put_chunks(c_pairs), k_dobs = put_chunks(c_dobs);
+  BA_TRY(S.arena.upload(A.buf.data(), A.buf.size(), st));
+  unsigned char* base = S.arena.p;
+  S.perm.borrow((int32_t*)(base + o_perm), nb); S.ob_e.borrow((int32_t*)(base + o_ob_e), nb);
+  S.ob_f0.borrow((int32_t*)(base + o_ob_f0), nb); S.ob_f1.borrow((int32_t*)(base + o_ob_f1), nb);
+  S.e_ptr.borrow((int64_t*)(base + o_e_ptr), ne + 1);
+  S.own_inc_e.borrow((int32_t*)(base + o_inc_e), ninc); S.own_inc_f.borrow((int32_t*)(base + o_inc_f), ninc);
+  S.own_ob_inc0.borrow((int32_t*)(base + o_inc0), nb); S.ob_inc1.borrow((int32_t*)(base + o_inc1), nb);
+  S.own_einc_ptr.borrow((int64_t*)(base + o_einc), ne + 1);
+  S.inc_e = S.own_inc_e.p; S.inc_f = S.own_inc_f.p; S.ob_inc0 = S.own_ob_inc0.p; S.einc_ptr = S.own_einc_ptr.p;
+  S.incobs_ptr.borrow((int64_t*)(base + o_iop), ninc + 1); S.incobs.borrow((int32_t*)(base + o_io), 2 * nb);
+  S.finc_ptr.borrow((int64_t*)(base + o_fip), nf + 1); S.finc.borrow((int32_t*)(base + o_fi), ninc);
+  S.fobs_ptr.borrow((int64_t*)(base + o_fop), nf + 1); S.fobs.borrow((int32_t*)(base + o_fo), 2 * nb);
+  S.dest_fa.borrow((int32_t*)(base + o_dfa), ndest); S.dest_fb.borrow((int32_t*)(base + o_dfb), ndest);
+  S.diag_dest.borrow((int32_t*)(base + o_dd), nf); S.dest_keys.borrow((uint64_t*)(base + o_dk), ndest);
+  S.dpair_ptr.borrow((int64_t*)(base + o_dpp), ndest + 1); S.pairs.borrow((int2*)(base + o_pairs), npairs);
+  S.dobs_ptr.borrow((int64_t*)(base + o_dop), ndest + 1); S.dobs.borrow((int32_t*)(base + o_do), nb);
+  S.pair_lists = true;
+  auto view_chunks = [&](Chunks& C, const HostChunks& H, const CO& o, int nseg, int ch) {
+    C.n = H.n; C.nseg = nseg; C.ch = ch;
+    C.seg.borrow((int32_t*)(base + o.seg), H.n); C.begin.borrow((int64_t*)(base + o.begin), H.n);
+    C.seg_first.borrow((int32_t*)(base + o.first), nseg + 1);
+  };
+  view_chunks(S.ch_fobs, c_fobs, k_fobs, (int)nf, 256);
+  view_chunks(S.ch_finc, c_finc, k_finc, (int)nf, 512);
+  view_chunks(S.ch_pairs, c_pairs, k_pairs, ndest, 256);
+  view_chunks(S.ch_dobs, c_dobs, k_dobs, ndest, 128);
+  BA_CUDA_TRY(cudaStreamSynchronize(st));   // A.buf goes out of scope
   return BA_OK;
 }
 

@@ -119,14 +119,20 @@ template <typename T>
 struct DVec {
   T* p = nullptr;
   size_t n = 0;
+  bool borrowed = false;   // a view into someone else's allocation (the host-built structure arena): never freed here
   DVec() = default;
   DVec(const DVec&) = delete;
   DVec& operator=(const DVec&) = delete;
   ~DVec() { release(); }
   void release() {
-    if (p) DevCache::get().free(p);
+    if (p && !borrowed) DevCache::get().free(p);
     p = nullptr;
     n = 0;
+    borrowed = false;
+  }
+  void borrow(T* ptr, size_t count) {
+    release();
+    p = ptr; n = count; borrowed = true;
   }
   int alloc(size_t count) {
     release();
@@ -148,6 +154,7 @@ struct DVec {
   void swap(DVec& o) {
     T* tp = p; p = o.p; o.p = tp;
     size_t tn = n; n = o.n; o.n = tn;
+    bool tb = borrowed; borrowed = o.borrowed; o.borrowed = tb;
   }
   size_t bytes() const { return n * sizeof(T); }
 };

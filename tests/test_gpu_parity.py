@@ -708,3 +708,30 @@ def test_rig_path_with_a_robust_loss_and_without_jacobi_scaling(gpu, oracle):
         for a, b in zip(rows1, rows0):
             assert H.rel(a["cost"], b["cost"]) <= 1e-9 and a["step_is_successful"] == b["step_is_successful"]
         assert np.abs(x1 - x0).max() < POSE_ATOL
+
+
+@pytest.mark.parametrize("rig", [1, 0])
+def test_structure_built_on_the_host_is_the_device_built_one(gpu, oracle, rig):
+    # rig-size Model B problems get their lists (sorted observations, incidences, destination blocks, pair lists, chunk tables)
+    # from the host in one upload (ba_structure.cuh, build_structure_host_b); the orders are the device build's, so every
+    # sum runs in the same order: the two solves agree bit for bit, through the one-CTA kernel and through the multi-kernel pipeline
+    cases = [H.hongo(), H.test2()]
+    pr = S.marker_rig_b(4, 8, 15, 24, perturb=(0.25, 0.07))
+    cases.append((F.ModelBFile(pr.n_time, pr.n_cam, pr.n_marker, pr.counts, pr.time_idx, pr.cam_idx, pr.marker_idx, pr.obs8, pr.params),
+                  pr.intr, pr.marker_side, 1))
+    pr = S.marker_rig_b(3, 5, 40, 7, visibility=0.6)   # ragged: frames that miss cameras / markers
+    cases.append((F.ModelBFile(pr.n_time, pr.n_cam, pr.n_marker, pr.counts, pr.time_idx, pr.cam_idx, pr.marker_idx, pr.obs8, pr.params),
+                  pr.intr, pr.marker_side, 1))
+    for pb, intr, side, fix0 in cases:
+        out = []
+        for host_max in (4096, 0):
+            with _Env(BA_HOST_BUILD_MAX=host_max, BA_RIG=rig):
+                _set_b(gpu, pb, intr, side, fix0)
+                s, rows = gpu.solve()
+                out.append((s, rows, gpu.get_parameters(), gpu.eval()))
+        (s1, rows1, x1, ev1), (s0, rows0, x0, ev0) = out
+        assert s1.num_iterations == s0.num_iterations and s1.path_used == s0.path_used
+        assert [r["cost"] for r in rows1] == [r["cost"] for r in rows0]
+        assert [r["trust_region_radius"] for r in rows1] == [r["trust_region_radius"] for r in rows0]
+        assert np.array_equal(x1, x0)
+        assert ev1[0] == ev0[0] and np.array_equal(ev1[1], ev0[1]) and np.array_equal(ev1[2], ev0[2])
