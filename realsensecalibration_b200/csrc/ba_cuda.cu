@@ -1304,6 +1304,13 @@ __global__ void k_widen(const int32_t* __restrict__ a, int64_t n, int64_t* __res
 // rank's shard); the eliminated blocks are owned by exactly one rank, so only their count is summed.
 int build_activity(ba_cuda_problem* p) {
   const Structure& S = p->S;
+  if (S.host_f_act_ptr && p->world == 1) {   // host-built structure: the scan and the counts came with it
+    p->f_act_ptr.borrow(const_cast<int64_t*>(S.host_f_act_ptr), S.nf + 1);
+    p->n_active_f_global = S.host_n_active_f;
+    p->n_active_e_global = S.host_n_active_e;
+    p->nb_global = S.nb;
+    return BA_OK;
+  }
   DVec<int32_t> flag;
   DVec<int64_t> wide;
   BA_TRY(flag.alloc(S.nf + 1)); BA_TRY(wide.alloc(S.nf + 1)); BA_TRY(p->f_act_ptr.alloc(S.nf + 1));

@@ -56,6 +56,8 @@ struct Structure {
   DVec<int32_t> dobs;
   Chunks ch_fobs, ch_finc, ch_pairs, ch_dobs;
   DVec<unsigned char> arena;   // host-built structures (build_structure_host_b): the one allocation every list is a view into
+  const int64_t* host_f_act_ptr = nullptr;   // host build: exclusive scan of "f has an observation" (nf + 1), inside the arena
+  int64_t host_n_active_e = -1, host_n_active_f = -1;
 };
 
 // ---- small setup kernels ---------------------------------------------------------------
@@ -651,8 +653,15 @@ inline int build_structure_host_b(Structure& S, int64_t nb, int64_t ne, int64_t 
   host_chunks(dpair_ptr, ndest, 256, c_pairs);
   host_chunks(dobs_ptr, ndest, 128, c_dobs);
 
+  // which blocks take part (build_activity of ba_cuda.cu, one rank): known here for free
+  std::vector<int64_t> f_act(nf + 1, 0);
+  for (int64_t f = 0; f < nf; ++f) f_act[f + 1] = f_act[f] + (fobs_ptr[f + 1] > fobs_ptr[f] ? 1 : 0);
+  S.host_n_active_f = f_act[nf];
+  S.host_n_active_e = 0;
+  for (int64_t e = 0; e < ne; ++e) S.host_n_active_e += e_ptr[e + 1] > e_ptr[e] ? 1 : 0;
   // one buffer, one allocation, one copy
   HostArena A;
+  const size_t o_fact = A.put(f_act);
   const size_t o_perm = A.put(perm), o_ob_e = A.put(ob_e), o_ob_f0 = A.put(ob_f0), o_ob_f1 = A.put(ob_f1), o_e_ptr = A.put(e_ptr);
   const size_t o_inc_e = A.put(inc_e), o_inc_f = A.put(inc_f), o_inc0 = A.put(ob_inc0), o_inc1 = A.put(ob_inc1), o_einc = A.put(einc_ptr);
   const size_t o_iop = A.put(incobs_ptr), o_io = A.put(incobs), o_fip = A.put(finc_ptr), o_fi = A.put(finc), o_fop = A.put(fobs_ptr), o_fo = A.put(fobs);
@@ -663,6 +672,7 @@ inline int build_structure_host_b(Structure& S, int64_t nb, int64_t ne, int64_t 
   const CO k_fobs = put_chunks(c_fobs), k_finc = put_chunks(c_finc), k_pairs = put_chunks(c_pairs), k_dobs = put_chunks(c_dobs);
   BA_TRY(S.arena.upload(A.buf.data(), A.buf.size(), st));
   unsigned char* base = S.arena.p;
+  S.host_f_act_ptr = (const int64_t*)(base + o_fact);
   S.perm.borrow((int32_t*)(base + o_perm), nb); S.ob_e.borrow((int32_t*)(base + o_ob_e), nb);
   S.ob_f0.borrow((int32_t*)(base + o_ob_f0), nb); S.ob_f1.borrow((int32_t*)(base + o_ob_f1), nb);
   S.e_ptr.borrow((int64_t*)(base + o_e_ptr), ne + 1);
