@@ -1702,6 +1702,36 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
   T.lap("reset");
   p->n_cam = n_cam; p->n_pt = n_pt; p->n_time = 0; p->n_marker = 0;
   p->n_params = 6 * (int64_t)n_cam + 3 * n_pt;
+  // Rig sizes (Test1 / Test2 of the reference: 16..200 observations, one or two cameras): the solve will run in the one-CTA
+  // kernel (ba_rig.cuh) or, if the caller asks otherwise, in the generic pipeline; neither needs the tile / strip structures
+  // of the fused passes.  The lists are made on the host and uploaded in one copy (ba_structure.cuh, build_structure_host).
+  const int64_t host_build_max = env_int("BA_HOST_BUILD_MAX", 0, 1 << 20, 4096);
+  if (n_obs > 0 && n_obs <= host_build_max && 2 * n_obs <= RIG_MAX_ROWS && 6 * (int64_t)n_cam <= RIG_MAX_N && p->world == 1 &&
+      env_int("BA_RIG", 0, 1, 1) != 0) {
+    for (int64_t i = 0; i < n_obs; ++i)
+      if (cam_idx[i] < 0 || cam_idx[i] >= n_cam || pt_idx[i] < 0 || pt_idx[i] >= n_pt)
+        return fail(BA_ERR_INVALID_ARGUMENT, "observation %lld references camera %d / point %d out of range", (long long)i, cam_idx[i], pt_idx[i]);
+    BA_TRY(build_structure_host(p->S, n_obs, n_pt, n_cam, pt_idx, cam_idx, nullptr, p->st));
+    T.lap("host build_structure");
+    p->model = 0;
+    {
+      DVec<double> tmp;
+      BA_TRY(tmp.upload(obs_xy, 2 * (size_t)n_obs, p->st));
+      BA_TRY(p->uv.alloc(n_obs));
+      k_gather_uv<<<grid_for(2 * n_obs, 256), 256, 0, p->st>>>(tmp.p, p->S.perm.p, n_obs, 2, reinterpret_cast<double*>(p->uv.p));
+      std::vector<double> K(4 * (size_t)n_cam);
+      for (int32_t c = 0; c < n_cam; ++c)
+        for (int q = 0; q < 4; ++q) K[4 * c + q] = intr[(size_t)intr_stride * c + q];
+      BA_TRY(p->intr_f.upload(K.data(), K.size(), p->st));
+      BA_CUDA_TRY(cudaStreamSynchronize(p->st));
+    }
+    p->h_perm.clear();
+    BA_TRY(alloc_workspace(p, 2, 3));
+    p->use_fused = false; p->use_strip = false;
+    BA_TRY(ensure_generic_workspace(p));
+    T.lap("uploads + workspace");
+    return build_activity(p);
+  }
   // The image points (16 B per observation, two thirds of the upload) travel on a second stream while the index
   // structure is built from the indices: the copy is queued behind the index uploads (so those reach the device
   // first) and joined again just before the gather into sorted order.
@@ -1800,10 +1830,10 @@ int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32
   p->half_side = marker_side / 2;
   const int64_t nf = (int64_t)n_cam + n_marker;
   PhaseTimer T;
-  // rig sizes: the lists are made on the host and uploaded in one copy (ba_structure.cuh, build_structure_host_b)
+  // rig sizes: the lists are made on the host and uploaded in one copy (ba_structure.cuh, build_structure_host)
   const int64_t host_build_max = env_int("BA_HOST_BUILD_MAX", 0, 1 << 20, 4096);
   if (n_mobs > 0 && n_mobs <= host_build_max && p->world == 1)
-    BA_TRY(build_structure_host_b(p->S, n_mobs, n_time, nf, time_idx, f0.data(), f1.data(), p->st));
+    BA_TRY(build_structure_host(p->S, n_mobs, n_time, nf, time_idx, f0.data(), f1.data(), p->st));
   else
     BA_TRY(build_structure(p->S, n_mobs, n_time, nf, time_idx, f0.data(), f1.data(), p->st,
                            [](const int32_t*, const int32_t*) { return (int)BA_OK; }));  // validated above, on the host

@@ -55,7 +55,7 @@ struct Structure {
   DVec<int64_t> dobs_ptr;  // nslots == 2 only: dest -> obs having (f0,f1) == (fa,fb)
   DVec<int32_t> dobs;
   Chunks ch_fobs, ch_finc, ch_pairs, ch_dobs;
-  DVec<unsigned char> arena;   // host-built structures (build_structure_host_b): the one allocation every list is a view into
+  DVec<unsigned char> arena;   // host-built structures (build_structure_host): the one allocation every list is a view into
   const int64_t* host_f_act_ptr = nullptr;   // host build: exclusive scan of "f has an observation" (nf + 1), inside the arena
   int64_t host_n_active_e = -1, host_n_active_f = -1;
 };
@@ -560,51 +560,67 @@ inline void host_chunks(const std::vector<int64_t>& ptr, int nseg, int ch, HostC
   }
 }
 
-inline int build_structure_host_b(Structure& S, int64_t nb, int64_t ne, int64_t nf, const int32_t* h_e, const int32_t* h_f0,
-                                  const int32_t* h_f1, cudaStream_t st) {
-  S.nb = nb; S.ne = ne; S.nf = nf; S.nslots = 2;
+// h_f1 == NULL: one f slot per observation (Model A); the incidences then alias the observations and the pair lists of the
+// generic pipeline (built on demand by the device path) come with the structure.
+inline int build_structure_host(Structure& S, int64_t nb, int64_t ne, int64_t nf, const int32_t* h_e, const int32_t* h_f0,
+                                const int32_t* h_f1, cudaStream_t st) {
+  const bool two = h_f1 != nullptr;
+  S.nb = nb; S.ne = ne; S.nf = nf; S.nslots = two ? 2 : 1;
   // 1. observations sorted by e (stable)
   std::vector<int32_t> perm(nb), ob_e(nb), ob_f0(nb), ob_f1(nb);
   for (int64_t i = 0; i < nb; ++i) perm[i] = (int32_t)i;
   std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return h_e[a] < h_e[b]; });
-  for (int64_t i = 0; i < nb; ++i) { ob_e[i] = h_e[perm[i]]; ob_f0[i] = h_f0[perm[i]]; ob_f1[i] = h_f1[perm[i]]; }
+  for (int64_t i = 0; i < nb; ++i) { ob_e[i] = h_e[perm[i]]; ob_f0[i] = h_f0[perm[i]]; ob_f1[i] = two ? h_f1[perm[i]] : -1; }
   std::vector<int64_t> e_ptr;
   host_csr(ob_e, ne, e_ptr);
   // 2. incidences: the distinct (e, f) of the two slots, ascending
   std::vector<uint64_t> uniq;
-  uniq.reserve(2 * nb);
-  for (int64_t i = 0; i < nb; ++i) {
-    if (ob_f0[i] >= 0) uniq.push_back((uint64_t)ob_e[i] * nf + ob_f0[i]);
-    if (ob_f1[i] >= 0) uniq.push_back((uint64_t)ob_e[i] * nf + ob_f1[i]);
-  }
-  std::sort(uniq.begin(), uniq.end());
-  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-  const int64_t ninc = (int64_t)uniq.size();
-  S.ninc = ninc;
-  std::vector<int32_t> inc_e(ninc), inc_f(ninc), ob_inc0(nb), ob_inc1(nb), ik(2 * nb), iv(2 * nb);
-  for (int64_t i = 0; i < ninc; ++i) { inc_e[i] = (int32_t)(uniq[i] / nf); inc_f[i] = (int32_t)(uniq[i] % nf); }
-  auto find_inc = [&](uint64_t key) { return (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), key) - uniq.begin()); };
-  for (int64_t i = 0; i < nb; ++i) {
-    const int32_t a = ob_f0[i] >= 0 ? find_inc((uint64_t)ob_e[i] * nf + ob_f0[i]) : -1;
-    const int32_t b = ob_f1[i] >= 0 ? find_inc((uint64_t)ob_e[i] * nf + ob_f1[i]) : -1;
-    ob_inc0[i] = a; ob_inc1[i] = b;
-    ik[2 * i] = a >= 0 ? a : INT32_MAX; iv[2 * i] = (int32_t)(i << 1);
-    ik[2 * i + 1] = b >= 0 ? b : INT32_MAX; iv[2 * i + 1] = (int32_t)(i << 1) | 1;
-  }
+  std::vector<int32_t> inc_e, inc_f, ob_inc0, ob_inc1, incobs;
   std::vector<int64_t> incobs_ptr, einc_ptr;
-  std::vector<int32_t> incobs;
-  host_sort_to_csr(ik, iv, ninc, incobs_ptr, incobs);
-  host_csr(inc_e, ne, einc_ptr);
+  int64_t ninc = nb;
+  if (two) {
+    uniq.reserve(2 * nb);
+    for (int64_t i = 0; i < nb; ++i) {
+      if (ob_f0[i] >= 0) uniq.push_back((uint64_t)ob_e[i] * nf + ob_f0[i]);
+      if (ob_f1[i] >= 0) uniq.push_back((uint64_t)ob_e[i] * nf + ob_f1[i]);
+    }
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    ninc = (int64_t)uniq.size();
+    inc_e.resize(ninc); inc_f.resize(ninc); ob_inc0.resize(nb); ob_inc1.resize(nb);
+    std::vector<int32_t> ik(2 * nb), iv(2 * nb);
+    for (int64_t i = 0; i < ninc; ++i) { inc_e[i] = (int32_t)(uniq[i] / nf); inc_f[i] = (int32_t)(uniq[i] % nf); }
+    auto find_inc = [&](uint64_t key) { return (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), key) - uniq.begin()); };
+    for (int64_t i = 0; i < nb; ++i) {
+      const int32_t a = ob_f0[i] >= 0 ? find_inc((uint64_t)ob_e[i] * nf + ob_f0[i]) : -1;
+      const int32_t b = ob_f1[i] >= 0 ? find_inc((uint64_t)ob_e[i] * nf + ob_f1[i]) : -1;
+      ob_inc0[i] = a; ob_inc1[i] = b;
+      ik[2 * i] = a >= 0 ? a : INT32_MAX; iv[2 * i] = (int32_t)(i << 1);
+      ik[2 * i + 1] = b >= 0 ? b : INT32_MAX; iv[2 * i + 1] = (int32_t)(i << 1) | 1;
+    }
+    host_sort_to_csr(ik, iv, ninc, incobs_ptr, incobs);
+    host_csr(inc_e, ne, einc_ptr);
+  } else {   // the incidences ARE the observations
+    inc_e = ob_e; inc_f = ob_f0; einc_ptr = e_ptr;
+  }
+  S.ninc = ninc;
   // 3. f -> incidences, f -> observations
-  std::vector<int32_t> inc_iota(ninc), finc, fobs, fk(2 * nb), fv(2 * nb);
+  std::vector<int32_t> inc_iota(ninc), finc, fobs;
   for (int64_t i = 0; i < ninc; ++i) inc_iota[i] = (int32_t)i;
   std::vector<int64_t> finc_ptr, fobs_ptr;
   host_sort_to_csr(inc_f, inc_iota, nf, finc_ptr, finc);
-  for (int64_t i = 0; i < nb; ++i) {
-    fk[2 * i] = ob_f0[i] >= 0 ? ob_f0[i] : INT32_MAX; fv[2 * i] = (int32_t)(i << 1);
-    fk[2 * i + 1] = ob_f1[i] >= 0 ? ob_f1[i] : INT32_MAX; fv[2 * i + 1] = (int32_t)(i << 1) | 1;
+  if (two) {
+    std::vector<int32_t> fk(2 * nb), fv(2 * nb);
+    for (int64_t i = 0; i < nb; ++i) {
+      fk[2 * i] = ob_f0[i] >= 0 ? ob_f0[i] : INT32_MAX; fv[2 * i] = (int32_t)(i << 1);
+      fk[2 * i + 1] = ob_f1[i] >= 0 ? ob_f1[i] : INT32_MAX; fv[2 * i + 1] = (int32_t)(i << 1) | 1;
+    }
+    host_sort_to_csr(fk, fv, nf, fobs_ptr, fobs);
+  } else {
+    std::vector<int32_t> fv(nb);
+    for (int64_t i = 0; i < nb; ++i) fv[i] = (int32_t)(i << 1);
+    host_sort_to_csr(ob_f0, fv, nf, fobs_ptr, fobs);
   }
-  host_sort_to_csr(fk, fv, nf, fobs_ptr, fobs);
   // 4. destination blocks with their incidence-pair lists (build_pair_lists)
   std::vector<uint64_t> pk, pv;
   for (int64_t e = 0; e < ne; ++e)
@@ -637,21 +653,24 @@ inline int build_structure_host_b(Structure& S, int64_t nb, int64_t ne, int64_t 
     if (dest_fa[d] == dest_fb[d]) diag_dest[dest_fa[d]] = d;
   }
   // 5. observations whose (f0, f1) is a destination block
-  std::vector<uint64_t> ffk(nb);
-  std::vector<int32_t> dobs(nb);
-  for (int64_t i = 0; i < nb; ++i) { ffk[i] = (ob_f0[i] >= 0 && ob_f1[i] >= 0) ? (uint64_t)ob_f0[i] * nf + ob_f1[i] : ~0ull; dobs[i] = (int32_t)i; }
-  std::stable_sort(dobs.begin(), dobs.end(), [&](int32_t a, int32_t b) { return ffk[a] < ffk[b]; });
-  std::vector<uint64_t> ffs(nb);
-  for (int64_t i = 0; i < nb; ++i) ffs[i] = ffk[dobs[i]];
-  std::vector<int64_t> dobs_ptr(ndest + 1);
-  for (int d = 0; d <= ndest; ++d)
-    dobs_ptr[d] = (int64_t)(std::lower_bound(ffs.begin(), ffs.end(), d < ndest ? dest_keys[d] : ~0ull) - ffs.begin());
+  std::vector<int32_t> dobs;
+  std::vector<int64_t> dobs_ptr;
+  if (two) {
+    std::vector<uint64_t> ffk(nb), ffs(nb);
+    dobs.resize(nb);
+    for (int64_t i = 0; i < nb; ++i) { ffk[i] = (ob_f0[i] >= 0 && ob_f1[i] >= 0) ? (uint64_t)ob_f0[i] * nf + ob_f1[i] : ~0ull; dobs[i] = (int32_t)i; }
+    std::stable_sort(dobs.begin(), dobs.end(), [&](int32_t a, int32_t b) { return ffk[a] < ffk[b]; });
+    for (int64_t i = 0; i < nb; ++i) ffs[i] = ffk[dobs[i]];
+    dobs_ptr.resize(ndest + 1);
+    for (int d = 0; d <= ndest; ++d)
+      dobs_ptr[d] = (int64_t)(std::lower_bound(ffs.begin(), ffs.end(), d < ndest ? dest_keys[d] : ~0ull) - ffs.begin());
+  }
   // 6. chunk tables
   HostChunks c_fobs, c_finc, c_pairs, c_dobs;
   host_chunks(fobs_ptr, (int)nf, 256, c_fobs);
   host_chunks(finc_ptr, (int)nf, 512, c_finc);
   host_chunks(dpair_ptr, ndest, 256, c_pairs);
-  host_chunks(dobs_ptr, ndest, 128, c_dobs);
+  if (two) host_chunks(dobs_ptr, ndest, 128, c_dobs);
 
   // which blocks take part (build_activity of ba_cuda.cu, one rank): known here for free
   std::vector<int64_t> f_act(nf + 1, 0);
@@ -676,17 +695,22 @@ inline int build_structure_host_b(Structure& S, int64_t nb, int64_t ne, int64_t 
   S.perm.borrow((int32_t*)(base + o_perm), nb); S.ob_e.borrow((int32_t*)(base + o_ob_e), nb);
   S.ob_f0.borrow((int32_t*)(base + o_ob_f0), nb); S.ob_f1.borrow((int32_t*)(base + o_ob_f1), nb);
   S.e_ptr.borrow((int64_t*)(base + o_e_ptr), ne + 1);
-  S.own_inc_e.borrow((int32_t*)(base + o_inc_e), ninc); S.own_inc_f.borrow((int32_t*)(base + o_inc_f), ninc);
-  S.own_ob_inc0.borrow((int32_t*)(base + o_inc0), nb); S.ob_inc1.borrow((int32_t*)(base + o_inc1), nb);
-  S.own_einc_ptr.borrow((int64_t*)(base + o_einc), ne + 1);
-  S.inc_e = S.own_inc_e.p; S.inc_f = S.own_inc_f.p; S.ob_inc0 = S.own_ob_inc0.p; S.einc_ptr = S.own_einc_ptr.p;
-  S.incobs_ptr.borrow((int64_t*)(base + o_iop), ninc + 1); S.incobs.borrow((int32_t*)(base + o_io), 2 * nb);
+  if (two) {
+    S.own_inc_e.borrow((int32_t*)(base + o_inc_e), ninc); S.own_inc_f.borrow((int32_t*)(base + o_inc_f), ninc);
+    S.own_ob_inc0.borrow((int32_t*)(base + o_inc0), nb); S.ob_inc1.borrow((int32_t*)(base + o_inc1), nb);
+    S.own_einc_ptr.borrow((int64_t*)(base + o_einc), ne + 1);
+    S.inc_e = S.own_inc_e.p; S.inc_f = S.own_inc_f.p; S.ob_inc0 = S.own_ob_inc0.p; S.einc_ptr = S.own_einc_ptr.p;
+    S.incobs_ptr.borrow((int64_t*)(base + o_iop), ninc + 1); S.incobs.borrow((int32_t*)(base + o_io), 2 * nb);
+  } else {
+    S.inc_e = S.ob_e.p; S.inc_f = S.ob_f0.p; S.ob_inc0 = nullptr; S.einc_ptr = S.e_ptr.p;
+    S.ob_inc1.borrow((int32_t*)(base + o_inc1), 0);
+  }
   S.finc_ptr.borrow((int64_t*)(base + o_fip), nf + 1); S.finc.borrow((int32_t*)(base + o_fi), ninc);
   S.fobs_ptr.borrow((int64_t*)(base + o_fop), nf + 1); S.fobs.borrow((int32_t*)(base + o_fo), 2 * nb);
   S.dest_fa.borrow((int32_t*)(base + o_dfa), ndest); S.dest_fb.borrow((int32_t*)(base + o_dfb), ndest);
   S.diag_dest.borrow((int32_t*)(base + o_dd), nf); S.dest_keys.borrow((uint64_t*)(base + o_dk), ndest);
   S.dpair_ptr.borrow((int64_t*)(base + o_dpp), ndest + 1); S.pairs.borrow((int2*)(base + o_pairs), npairs);
-  S.dobs_ptr.borrow((int64_t*)(base + o_dop), ndest + 1); S.dobs.borrow((int32_t*)(base + o_do), nb);
+  if (two) { S.dobs_ptr.borrow((int64_t*)(base + o_dop), ndest + 1); S.dobs.borrow((int32_t*)(base + o_do), nb); }
   S.pair_lists = true;
   auto view_chunks = [&](Chunks& C, const HostChunks& H, const CO& o, int nseg, int ch) {
     C.n = H.n; C.nseg = nseg; C.ch = ch;
@@ -696,7 +720,7 @@ inline int build_structure_host_b(Structure& S, int64_t nb, int64_t ne, int64_t 
   view_chunks(S.ch_fobs, c_fobs, k_fobs, (int)nf, 256);
   view_chunks(S.ch_finc, c_finc, k_finc, (int)nf, 512);
   view_chunks(S.ch_pairs, c_pairs, k_pairs, ndest, 256);
-  view_chunks(S.ch_dobs, c_dobs, k_dobs, ndest, 128);
+  if (two) view_chunks(S.ch_dobs, c_dobs, k_dobs, ndest, 128);
   BA_CUDA_TRY(cudaStreamSynchronize(st));   // A.buf goes out of scope
   return BA_OK;
 }

@@ -713,7 +713,7 @@ def test_rig_path_with_a_robust_loss_and_without_jacobi_scaling(gpu, oracle):
 @pytest.mark.parametrize("rig", [1, 0])
 def test_structure_built_on_the_host_is_the_device_built_one(gpu, oracle, rig):
     # rig-size Model B problems get their lists (sorted observations, incidences, destination blocks, pair lists, chunk tables)
-    # from the host in one upload (ba_structure.cuh, build_structure_host_b); the orders are the device build's, so every
+    # from the host in one upload (ba_structure.cuh, build_structure_host); the orders are the device build's, so every
     # sum runs in the same order: the two solves agree bit for bit, through the one-CTA kernel and through the multi-kernel pipeline
     cases = [H.hongo(), H.test2()]
     pr = S.marker_rig_b(4, 8, 15, 24, perturb=(0.25, 0.07))
@@ -735,3 +735,37 @@ def test_structure_built_on_the_host_is_the_device_built_one(gpu, oracle, rig):
         assert [r["trust_region_radius"] for r in rows1] == [r["trust_region_radius"] for r in rows0]
         assert np.array_equal(x1, x0)
         assert ev1[0] == ev0[0] and np.array_equal(ev1[1], ev0[1]) and np.array_equal(ev1[2], ev0[2])
+
+
+def test_model_a_structure_built_on_the_host(gpu, oracle):
+    # Test1 / Test2 sizes of Model A: lists from the host, no tile / strip structures; the one-CTA kernel gives bit for bit
+    # the rows it gives on the device-built structure, and with BA_RIG=0 the generic pipeline takes over (same oracle rows)
+    pa, intr = H.two_cam()
+    cases = [(pa.n_cam, pa.n_pt, pa.cam_idx, pa.pt_idx, pa.obs_xy, intr, pa.params)]
+    pr = S.bal_like(8, 600, 4, 6, 3)
+    cases.append((pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params))
+    pr = S.marker_rig_a(4, 3, 20, 5)
+    cases.append((pr.n_cam, pr.n_pt, pr.cam_idx, pr.pt_idx, pr.obs_xy, pr.intr, pr.params))
+    for k, (n_cam, n_pt, ci, pi, ob, K, x0) in enumerate(cases):
+        out = []
+        for host_max in (4096, 0):
+            with _Env(BA_HOST_BUILD_MAX=host_max):
+                gpu.set_model_a(n_cam, n_pt, ci, pi, ob, K)
+                gpu.set_parameters(x0)
+                s, rows = gpu.solve()
+                out.append((s, rows, gpu.get_parameters(), gpu.eval()))
+        (s1, rows1, x1, ev1), (s0, rows0, x0_, ev0) = out
+        assert s1.path_used == s0.path_used == abi.PATH_RIG
+        assert [r["cost"] for r in rows1] == [r["cost"] for r in rows0]
+        assert np.array_equal(x1, x0_)
+        assert ev1[0] == ev0[0] or H.rel(ev1[0], ev0[0]) < 1e-12   # ba_cuda_eval: k_jac_a on the host-built one, k_fa_jac on the other
+        if k == 0:
+            continue   # the two-camera fixture ends in an exact fit (costs ~1e-12): covered by test_rig_path_*
+        xo, so, rows_o = oracle.solve_model_a(n_cam, n_pt, ci, pi, ob, K, x0)
+        _check_rows(rows1, rows_o)
+        with _Env(BA_RIG=0):   # host-built and not on the rig kernel: the generic pipeline
+            gpu.set_model_a(n_cam, n_pt, ci, pi, ob, K)
+            gpu.set_parameters(x0)
+            s2, rows2 = gpu.solve()
+        assert s2.path_used != abi.PATH_RIG
+        _check_rows(rows2, rows_o)
