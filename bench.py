@@ -483,6 +483,10 @@ def main():
                "final_cost": float(osum.final_cost),
                "sample": "full workload, one solve of %d LM iterations (problem construction + initial evaluation included), "
                          "oracle/ba_oracle.cpp with OpenMP" % kc}
+        if WORKLOADS[a.workload]["kind"] in ("hongo", "two_cam") and threads > 1:
+            # at the reference's own problem sizes OpenMP's fork / join can cost more than it buys: best of three solves on ONE thread too
+            best = min(oracle_steps(job, kc, 1)[0] for _ in range(3))
+            cpu["single_thread_value"] = kc / best
         if kc == ITERS_PER_SOLVE and K >= ITERS_PER_SOLVE:
             # relative to the final cost, but never below 1e-12 of the initial cost: a zero-residual problem (cfg1) ends at round-off
             scale = max(abs(float(osum.final_cost)), 1e-12 * abs(float(osum.initial_cost)), 1e-300)

@@ -127,6 +127,7 @@ struct ba_cuda_problem {
   bool smem_attr_set = false;   // the opt-in shared-memory sizes are per device: set once per problem
   bool rig_attr_set = false;
   bool one_shot = false;        // inside ba_cuda_solve: nobody looks at row 0 before the loop runs
+  bool building = false;        // inside ba_cuda_set_model_*: a failure from here on leaves no half-built model behind
   DVec<unsigned char> rig_buf;  // RigState | rows of one launch
   unsigned char* h_rig = nullptr;   // pinned mirror
   SparseExchange SX;            // multi-GPU, fused Model A + PCG: all-gather of the ranks' own blocks instead of an all-reduce of all
@@ -1612,17 +1613,21 @@ int ba_cuda_create(ba_cuda_problem** out, int device_id) {
   BA_CUDA_TRY(cudaSetDevice(device_id));
   ba_cuda_problem* p = new ba_cuda_problem();
   p->device = device_id;
-  BA_CUDA_TRY(cudaStreamCreateWithFlags(&p->own_st, cudaStreamNonBlocking));
-  p->st = p->own_st;
-  for (int f = 0; f < F_COUNT; ++f) { BA_CUDA_TRY(cudaEventCreate(&p->ev[f][0])); BA_CUDA_TRY(cudaEventCreate(&p->ev[f][1])); }
-  BA_CUDA_TRY(cudaEventCreate(&p->k0)); BA_CUDA_TRY(cudaEventCreate(&p->k1));
-  BA_CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_st, cudaStreamNonBlocking));
-  BA_CUDA_TRY(cudaEventCreateWithFlags(&p->copy_go, cudaEventDisableTiming));
-  BA_CUDA_TRY(cudaEventCreateWithFlags(&p->copy_done, cudaEventDisableTiming));
-  BA_CUDA_TRY(cudaMallocHost((void**)&p->h_scal, sizeof(double) * S_COUNT));
-  BA_CUDA_TRY(cudaMallocHost((void**)&p->h_status, sizeof(int)));
+  ++g_live_problems;   // ba_cuda_destroy counts it down again
+  const int rc = [&]() -> int {
+    BA_CUDA_TRY(cudaStreamCreateWithFlags(&p->own_st, cudaStreamNonBlocking));
+    p->st = p->own_st;
+    for (int f = 0; f < F_COUNT; ++f) { BA_CUDA_TRY(cudaEventCreate(&p->ev[f][0])); BA_CUDA_TRY(cudaEventCreate(&p->ev[f][1])); }
+    BA_CUDA_TRY(cudaEventCreate(&p->k0)); BA_CUDA_TRY(cudaEventCreate(&p->k1));
+    BA_CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_st, cudaStreamNonBlocking));
+    BA_CUDA_TRY(cudaEventCreateWithFlags(&p->copy_go, cudaEventDisableTiming));
+    BA_CUDA_TRY(cudaEventCreateWithFlags(&p->copy_done, cudaEventDisableTiming));
+    BA_CUDA_TRY(cudaMallocHost((void**)&p->h_scal, sizeof(double) * S_COUNT));
+    BA_CUDA_TRY(cudaMallocHost((void**)&p->h_status, sizeof(int)));
+    return BA_OK;
+  }();
+  if (rc != BA_OK) { ba_cuda_destroy(p); return rc; }   // destroy copes with whatever was created so far
   *out = p;
-  ++g_live_problems;
   return BA_OK;
 }
 
@@ -1690,8 +1695,8 @@ int ba_cuda_shard_blocks(int64_t n_blocks, const int64_t* weight, int world_size
   return BA_OK;
 }
 
-int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t n_obs, const int32_t* cam_idx,
-                        const int32_t* pt_idx, const double* obs_xy, const double* intr, int32_t intr_stride) {
+static int set_model_a_impl(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t n_obs, const int32_t* cam_idx,
+                            const int32_t* pt_idx, const double* obs_xy, const double* intr, int32_t intr_stride) {
   if (!p || n_cam < 1 || n_pt < 0 || n_obs < 0 || (n_obs > 0 && (!cam_idx || !pt_idx || !obs_xy)) || !intr ||
       (intr_stride != 0 && intr_stride != 4))
     return fail(BA_ERR_INVALID_ARGUMENT, "ba_cuda_set_model_a: bad arguments");
@@ -1699,6 +1704,7 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
   PhaseTimer T;
   BA_TRY(use_device(p));
   reset_problem(p);
+  p->building = true;
   T.lap("reset");
   p->n_cam = n_cam; p->n_pt = n_pt; p->n_time = 0; p->n_marker = 0;
   p->n_params = 6 * (int64_t)n_cam + 3 * n_pt;
@@ -1809,9 +1815,9 @@ int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t
   return rc;
 }
 
-int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32_t n_marker, int64_t n_mobs,
-                        const int32_t* time_idx, const int32_t* cam_idx, const int32_t* marker_idx, const double* obs8,
-                        const double* intr4_per_cam, double marker_side, int32_t fix_cam0, int32_t fix_marker0) {
+static int set_model_b_impl(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32_t n_marker, int64_t n_mobs,
+                            const int32_t* time_idx, const int32_t* cam_idx, const int32_t* marker_idx, const double* obs8,
+                            const double* intr4_per_cam, double marker_side, int32_t fix_cam0, int32_t fix_marker0) {
   if (!p || n_cam < 1 || n_time < 0 || n_marker < 1 || n_mobs < 0 || (n_mobs > 0 && (!time_idx || !cam_idx || !marker_idx || !obs8)) ||
       !intr4_per_cam)
     return fail(BA_ERR_INVALID_ARGUMENT, "ba_cuda_set_model_b: bad arguments");
@@ -1825,6 +1831,7 @@ int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32
   }
   BA_TRY(use_device(p));
   reset_problem(p);
+  p->building = true;
   p->n_cam = n_cam; p->n_time = n_time; p->n_marker = n_marker; p->n_pt = 0;
   p->n_params = 6 * ((int64_t)n_cam + n_time + n_marker);
   p->half_side = marker_side / 2;
@@ -1864,6 +1871,30 @@ int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32
   const int rc_act = build_activity(p);
   T.lap("build_activity");
   return rc_act;
+}
+
+// A failure after the old model was dropped (allocation, NCCL, an index out of range found on the device) must not leave
+// p->model set over unallocated buffers: the problem goes back to "no model".
+static int finish_set_model(ba_cuda_problem* p, int rc) {
+  if (!p) return rc;
+  if (rc != BA_OK && p->building) {
+    if (p->st) cudaStreamSynchronize(p->st);
+    if (p->copy_st) cudaStreamSynchronize(p->copy_st);
+    cudaGetLastError();
+    reset_problem(p);
+  }
+  p->building = false;
+  return rc;
+}
+int ba_cuda_set_model_a(ba_cuda_problem* p, int32_t n_cam, int64_t n_pt, int64_t n_obs, const int32_t* cam_idx,
+                        const int32_t* pt_idx, const double* obs_xy, const double* intr, int32_t intr_stride) {
+  return finish_set_model(p, set_model_a_impl(p, n_cam, n_pt, n_obs, cam_idx, pt_idx, obs_xy, intr, intr_stride));
+}
+int ba_cuda_set_model_b(ba_cuda_problem* p, int32_t n_cam, int32_t n_time, int32_t n_marker, int64_t n_mobs,
+                        const int32_t* time_idx, const int32_t* cam_idx, const int32_t* marker_idx, const double* obs8,
+                        const double* intr4_per_cam, double marker_side, int32_t fix_cam0, int32_t fix_marker0) {
+  return finish_set_model(p, set_model_b_impl(p, n_cam, n_time, n_marker, n_mobs, time_idx, cam_idx, marker_idx, obs8, intr4_per_cam,
+                                              marker_side, fix_cam0, fix_marker0));
 }
 
 int64_t ba_cuda_num_parameters(const ba_cuda_problem* p) { return p ? p->n_params : 0; }
@@ -2052,6 +2083,8 @@ int ba_cuda_get_iterations(ba_cuda_problem* p, ba_cuda_iteration* rows, int cap)
 int ba_cuda_eval(ba_cuda_problem* p, double* cost, double* residuals, double* jac) {
   if (!p) return fail(BA_ERR_INVALID_ARGUMENT, "NULL problem");
   if (p->model < 0 || !p->params_set) return fail(BA_ERR_STATE, "set_model_* and set_parameters must be called before eval");
+  // eval resets the Jacobi scaling and overwrites the residual / Jacobian buffers the open solve works on
+  if (p->lm.began && p->lm.go) return fail(BA_ERR_STATE, "ba_cuda_eval between ba_cuda_solve_begin and the end of the solve");
   BA_TRY(use_device(p));
   const Structure& S = p->S;
   const int RD = p->model == 0 ? 2 : 8, DE = p->model == 0 ? 3 : 6;
@@ -2113,7 +2146,7 @@ int ba_cuda_reprojection_error(ba_cuda_problem* p, double* sum_half_sq, double* 
   const double err = 0.5 * p->h_scal[S_CAND];
   const double n_points = (double)(p->model == 0 ? p->nb_global : 4 * p->nb_global);
   if (sum_half_sq) *sum_half_sq = err;
-  if (rms_per_coord) *rms_per_coord = std::pow((err * 2.0) / (n_points * 2.0), 0.5);
+  if (rms_per_coord) *rms_per_coord = n_points > 0 ? std::pow((err * 2.0) / (n_points * 2.0), 0.5) : 0.0;   // no point: no error, not NaN
   return BA_OK;
 }
 
@@ -2157,7 +2190,7 @@ static int project_points_impl(ba_cuda_problem* p, int64_t n_points, const doubl
   BA_CUDA_TRY(cudaEventElapsedTime(&p->last_kernel_ms, p->k0, p->k1));
   if (n_points == 0) err = 0.0;
   if (sum_half_sq) *sum_half_sq = err;
-  if (rms_per_coord) *rms_per_coord = std::pow((err * 2.0) / (n_points * 2.0), 0.5);
+  if (rms_per_coord) *rms_per_coord = n_points > 0 ? std::pow((err * 2.0) / (n_points * 2.0), 0.5) : 0.0;   // no point: no error, not NaN
   return BA_OK;
 }
 
