@@ -6,6 +6,9 @@ python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_o
 B="python bench.py --steps 5 --warmup 0 --no-cpu-baseline --no-e2e --no-jacobian"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_sa_pass1|k_fa_pass2|k_reduce_items|k_pcg" -s 6 -c 8 -o gpurun_out/r02f_prof_cfg5 -f $B --workload cfg5 > gpurun_out/ncu_cfg5.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_jac_b|k_inc_W|k_pairs_partial|k_model_cost|k_fobs_partial|k_dobs_partial|k_e_M|k_chol_blocked" -s 10 -c 10 -o gpurun_out/r02f_prof_cfg3 -f $B --workload cfg3 > gpurun_out/ncu_cfg3.log 2>&1
+python profiles/tools/ncu_summary.py gpurun_out/r02f_prof_cfg5.ncu-rep > gpurun_out/r02f_ncu_full_cfg5.txt 2>/dev/null
+python profiles/tools/ncu_summary.py gpurun_out/r02f_prof_cfg3.ncu-rep > gpurun_out/r02f_ncu_full_cfg3.txt 2>/dev/null
+rm -f gpurun_out/r02f_prof_cfg5.ncu-rep gpurun_out/r02f_prof_cfg3.ncu-rep   # gpurun brings back at most 64 MiB
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r02f_launches_cfg5.csv python bench.py --steps 5 --warmup 0 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r02f_launches_hongo.csv python bench.py --workload hongo --steps 10 --warmup 0 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 for w in cfg5 hongo cfg1 cfg2 cfg3 cfg3a cfg4; do
