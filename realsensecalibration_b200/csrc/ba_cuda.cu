@@ -1084,10 +1084,11 @@ int rig_run(ba_cuda_problem* p, bool begin, int32_t max_new) {
     if (clocks) {
       long long h[16];
       BA_CUDA_TRY(cudaMemcpy(h, clk.p, sizeof(h), cudaMemcpyDeviceToHost));
-      static const char* const nm[13] = {"jacobian", "normal_parts", "gradient", "e_chol+inc_Y", "vsum+pairs", "assemble+diag", "ldlt+solve",
-                                         "backsub+model_cost", "candidate", "cost_candidate", "decision", "other", "of_which_triangular_solves"};
+      static const char* const nm[16] = {"jacobian", "normal_parts", "gradient", "e_chol+inc_Y", "vsum+pairs", "assemble+diag", "ldlt+solve",
+                                         "backsub+model_cost", "candidate", "cost_candidate", "decision", "other", "of_which_triangular_solves",
+                                         "factor:(b)", "factor:barrier_after_b", "factor:diag_block"};
       std::fprintf(stderr, "[ba_cuda rig clocks] rows=%d", st.n_rows);
-      for (int k = 0; k < 13; ++k) std::fprintf(stderr, " %s=%lld", nm[k], h[k]);
+      for (int k = 0; k < 16; ++k) std::fprintf(stderr, " %s=%lld", nm[k], h[k]);
       std::fprintf(stderr, "\n");
     }
   }

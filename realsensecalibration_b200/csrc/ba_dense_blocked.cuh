@@ -57,28 +57,42 @@ k_chol_blocked(int n, double* __restrict__ A, const double* __restrict__ rhs, do
       Ld[r * (CB_NB + 1) + c] = v;
     }
     __syncthreads();
-    if (warp == 0) {  // 32x32 Cholesky by one warp: lane = row, the row lives in registers, columns go through shared memory
-      double row[CB_NB];
-#pragma unroll
-      for (int c = 0; c < CB_NB; ++c) row[c] = Ld[lane * (CB_NB + 1) + c];
+    {  // 32 x 32 Cholesky by the whole CTA (a lone warp ran it in 16 us: one warp advances ~6 cycles per instruction).  Right-looking
+       // on the unscaled columns (a_rc -= a_rj a_cj / d_j: one barrier per column, no scaling pass in between), the reciprocal of
+       // the next pivot left in shared memory by the thread that finished it; scaled to L = L' D^-1/2 at the end.
+      const int r = tid >> 3, g = tid & 7;   // thread = (row, column class): columns g, g + 8, g + 16, g + 24
+      if (tid == 0) { const double d0 = Ld[0]; colj[0] = (d0 > 0.0 && isfinite(d0)) ? 1.0 / d0 : 0.0; }
+      __syncthreads();
       bool ok = true;
-#pragma unroll
       for (int j = 0; j < CB_NB; ++j) {
-        const double d = __shfl_sync(0xffffffffu, row[j], j);
-        if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }     // uniform
-        const double l = sqrt(d), inv = 1.0 / l;
-        if (lane == j) { row[j] = l; Linv[j] = inv; }
-        if (lane > j) row[j] *= inv;
-        colj[lane] = row[j];
-        __syncwarp();
+        const double inv = colj[j];   // 1 / d_j, 0 = not positive (every thread reads the same value: uniform)
+        if (inv == 0.0) { ok = false; break; }
+        if (r > j) {
+          const double lrj = Ld[r * (CB_NB + 1) + j] * inv;
 #pragma unroll
-        for (int c = j + 1; c < CB_NB; ++c)
-          if (lane >= c) row[c] -= row[j] * colj[c];
-        __syncwarp();
+          for (int q = 0; q < CB_NB / 8; ++q) {
+            const int c = g + 8 * q;
+            if (c > j && c <= r) {
+              const double v = Ld[r * (CB_NB + 1) + c] - lrj * Ld[c * (CB_NB + 1) + j];
+              Ld[r * (CB_NB + 1) + c] = v;
+              if (r == j + 1 && c == j + 1) colj[j + 1] = (v > 0.0 && isfinite(v)) ? 1.0 / v : 0.0;
+            }
+          }
+        }
+        __syncthreads();
       }
-      if (!ok && lane == 0) s_bad = 1;
+      if (!ok) {
+        if (tid == 0) s_bad = 1;
+      } else {
+        if (tid < CB_NB) Linv[tid] = sqrt(colj[tid]);   // 1 / L_jj
+        __syncthreads();
 #pragma unroll
-      for (int c = 0; c < CB_NB; ++c) Ld[lane * (CB_NB + 1) + c] = row[c];
+        for (int q = 0; q < CB_NB / 8; ++q) {
+          const int c = g + 8 * q;
+          if (c < r) Ld[r * (CB_NB + 1) + c] *= Linv[c];
+          else if (c == r) Ld[r * (CB_NB + 1) + c] = sqrt(Ld[r * (CB_NB + 1) + c]);
+        }
+      }
     }
     __syncthreads();
     if (s_bad) {

@@ -3,7 +3,7 @@
 // The reference's own problems (Common/Correspondence/hongo: 68 marker observations; Test1/Test2_BundleAdjustment: 16..200
 // observations; Main_Calibration/bundle_adjustment_manager.cpp:16-96) are three orders of magnitude below what fills a
 // B200: on the multi-kernel pipeline one LM iteration is ~40 launches and two host round trips, all latency.  Here one
-// CTA of 1024 threads walks the same phases (the item functions d_* of ba_kernels.cuh, so the arithmetic per observation,
+// CTA of 256 threads walks the same phases (the item functions d_* of ba_kernels.cuh, so the arithmetic per observation,
 // per block and per incidence is the generic pipeline's) separated by __syncthreads instead of launches; the reduced camera
 // system lives in shared memory and is factorised there (LDL^T, one barrier per column; the two triangular solves run in
 // one warp's registers); TrustRegionMinimizer's loop variables and its decisions (lm_begin / lm_iterate of ba_cuda.cu,
@@ -14,7 +14,9 @@
 
 namespace ba {
 
-constexpr int RIG_THREADS = 512;        // 128 registers per thread: the item functions keep whole tables and 36 accumulators
+constexpr int RIG_THREADS = 256;        // 255 registers per thread: measured on B200 against 320 / 384 / 512 threads (168 / 168 / 128 registers):
+                                        // hongo 8300 vs 6530 / 6840 / 6970 LM it/s.  At the register cap ptxas puts every shared-memory load right
+                                        // in front of its use and the dependent chains of the dense solve run 3-5x longer
 constexpr int RIG_ROWS_CAP = 256;       // iteration rows one launch can record
 constexpr int RIG_MAX_N = 160;       // reduced camera system dimension that fits shared memory (n * (n | 1) doubles)
 constexpr int64_t RIG_MAX_ROWS = 8192;    // residual rows (nb * RD); measured crossover with the multi-kernel pipeline ~9k rows (profiles/r02_rig_crossover.txt)
@@ -208,7 +210,7 @@ __device__ __forceinline__ void rig_normal_parts(const RigParams& P) {
       for (int k = 0; k < 36; ++k) acc[k] = 0.0;
       if (live) {
         const int64_t end = P.dobs_ptr[d + 1];
-#pragma unroll 2
+#pragma unroll 4
         for (int64_t idx = P.dobs_ptr[d]; idx < end; ++idx) {
           const int64_t row = (int64_t)RD * P.dobs[idx] + r;
           double ra[6], rb[6];
@@ -259,92 +261,111 @@ __device__ __forceinline__ bool rig_ldlt_solve(double* S, int n, int ld, double*
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = RIG_THREADS / 32;
   constexpr int NB = 8;
-  for (int k0 = 0; k0 < n; k0 += NB) {
+  // (a) the 8 x 8 diagonal block at k0 in warp 0's registers: lane = (row r = lane >> 2, column pair g = lane & 3) holds
+  // A[r][2g], A[r][2g+1]; a pivot step is four broadcasts (pivot, the lane's row factor, its two column factors), one
+  // reciprocal, two fmas.  When `upd` the block first takes the rank-8 update of the previous panel (columns kp..kp+7), so
+  // the factorisation of panel p + 1 starts while the other warps are still in the trailing update of panel p (look-ahead).
+  auto diag_block = [&](int k0, bool upd, int kp) {
     const int w = min(NB, n - k0);
-    if (threadIdx.x == 0) {   // (a): a lone warp runs ~6 cycles per instruction, so the fewest instructions win: one thread, the
-                              // whole 8 x 8 block in registers, no shuffles, no predicates
-      double a[NB][NB];
-      double* blk0 = S + k0 * ld + k0;
-      if (w == NB) {
+    const int r = lane >> 2, g = lane & 3, c0 = 2 * g, c1 = 2 * g + 1;
+    const bool in0 = r < w && c0 <= r, in1 = r < w && c1 <= r;
+    double* row = S + (k0 + (r < w ? r : 0)) * ld;
+    double a0 = in0 ? row[k0 + c0] : (r == c0 ? 1.0 : 0.0);   // identity below a partial last panel
+    double a1 = in1 ? row[k0 + c1] : (r == c1 ? 1.0 : 0.0);
+    if (upd) {
+      const double* rc0 = S + (k0 + (c0 < w ? c0 : 0)) * ld + kp;
+      const double* rc1 = S + (k0 + (c1 < w ? c1 : 0)) * ld + kp;
+      double li[NB], v0[NB], v1[NB];
 #pragma unroll
-        for (int r = 0; r < NB; ++r)
+      for (int kk = 0; kk < NB; ++kk) { li[kk] = row[kp + kk] * invd[kp + kk]; v0[kk] = rc0[kk]; v1[kk] = rc1[kk]; }
+      double u0 = 0.0, u1 = 0.0;
 #pragma unroll
-          for (int c = 0; c <= r; ++c) a[r][c] = blk0[r * ld + c];
-      } else {   // the last, partial panel: identity below its w rows
-#pragma unroll
-        for (int r = 0; r < NB; ++r)
-#pragma unroll
-          for (int c = 0; c <= r; ++c) a[r][c] = r < w ? blk0[r * ld + c] : (r == c ? 1.0 : 0.0);
-      }
-      bool ok = true;
-#pragma unroll
-      for (int kk = 0; kk < NB; ++kk) {
-        const double d = a[kk][kk];
-        const double inv = (d > 0.0 && isfinite(d)) ? __drcp_rn(d) : 0.0;   // = 1.0 / d, correctly rounded
-        ok = ok && inv != 0.0;
-        if (kk < w) invd[k0 + kk] = inv;
-#pragma unroll
-        for (int r = kk + 1; r < NB; ++r) {
-          const double lrk = a[r][kk] * inv;   // L'[r][kk] / d_kk
-          blk[r * NB + kk] = lrk;              // the block scaled by D^-1, for (b)
-#pragma unroll
-          for (int c = kk + 1; c <= r; ++c) a[r][c] = fma(-lrk, a[c][kk], a[r][c]);
-        }
-      }
-      if (w == NB) {
-#pragma unroll
-        for (int r = 1; r < NB; ++r)
-#pragma unroll
-          for (int c = 1; c <= r; ++c) blk0[r * ld + c] = a[r][c];
-      } else {
-#pragma unroll
-        for (int r = 1; r < NB; ++r)
-#pragma unroll
-          for (int c = 1; c <= r; ++c)
-            if (r < w) blk0[r * ld + c] = a[r][c];
-      }
-      blk[NB * NB] = ok ? 1.0 : 0.0;
+      for (int kk = 0; kk < NB; ++kk) { u0 = fma(li[kk], v0[kk], u0); u1 = fma(li[kk], v1[kk], u1); }
+      if (in0) a0 -= u0;
+      if (in1) a1 -= u1;
     }
-    __syncthreads();
-    if (blk[NB * NB] == 0.0) return false;
+    bool ok = true;
+#pragma unroll
+    for (int kk = 0; kk < NB; ++kk) {
+      const double mine = (kk & 1) ? a1 : a0;   // this lane's entry of column kk if g == kk / 2
+      const double d = __shfl_sync(0xffffffffu, mine, 4 * kk + (kk >> 1));
+      const double inv = (d > 0.0 && isfinite(d)) ? __drcp_rn(d) : 0.0;   // = 1.0 / d, correctly rounded
+      ok = ok && inv != 0.0;
+      const double lrk = __shfl_sync(0xffffffffu, mine, (lane & 28) | (kk >> 1)) * inv;   // A[r][kk] / d_kk
+      const double l0 = __shfl_sync(0xffffffffu, mine, 4 * c0 + (kk >> 1));               // A[c0][kk]
+      const double l1 = __shfl_sync(0xffffffffu, mine, 4 * c1 + (kk >> 1));               // A[c1][kk]
+      if (r > kk) {
+        if (c0 > kk && c0 <= r) a0 = fma(-lrk, l0, a0);
+        if (c1 > kk && c1 <= r) a1 = fma(-lrk, l1, a1);
+        if (g == 0) blk[r * NB + kk] = lrk;   // the block scaled by D^-1, for (b)
+      }
+      if (lane == 0 && kk < w) invd[k0 + kk] = inv;
+    }
+    if (in0) row[k0 + c0] = a0;
+    if (in1) row[k0 + c1] = a1;
+    if (lane == 0) blk[NB * NB] = ok ? 1.0 : 0.0;
+  };
+  if (warp == 0) diag_block(0, false, 0);
+  __syncthreads();
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    if (blk[NB * NB] == 0.0) return false;   // a pivot of this panel is not positive (uniform: read after a barrier)
+    const int w = min(NB, n - k0);
     // rows below the panel, and the right-hand side as one more row (row n of S): its panel solve and trailing update ARE the
     // forward substitution, so after the last panel row n holds v_k = d_k u_k of L' u = rhs at no extra dependent step
     const int i0 = k0 + w;
     const int m = n + 1 - i0;
+    long long tq = 0;
+    if (sclk && threadIdx.x == 0) tq = clock64();
     for (int r = threadIdx.x; r < m; r += RIG_THREADS) {   // (b)
       double* row = S + (i0 + r) * ld + k0;
       double x[NB];
 #pragma unroll
       for (int c = 0; c < NB; ++c) x[c] = c < w ? row[c] : 0.0;
+      // column by column: once x[q] is final its NB - 1 - q updates are independent, and their block entries are loaded together
+      // (row by row the compiler put every shared-memory load right in front of the fma that waits for it: 28 round trips)
 #pragma unroll
-      for (int kk = 1; kk < NB; ++kk) {
+      for (int q = 0; q < NB - 1; ++q) {
+        double bq[NB];
 #pragma unroll
-        for (int q = 0; q < kk; ++q) x[kk] = fma(-x[q], blk[kk * NB + q], x[kk]);
+        for (int kk = q + 1; kk < NB; ++kk) bq[kk] = blk[kk * NB + q];
+#pragma unroll
+        for (int kk = q + 1; kk < NB; ++kk) x[kk] = fma(-x[q], bq[kk], x[kk]);
       }
 #pragma unroll
       for (int c = 1; c < NB; ++c)
         if (c < w) row[c] = x[c];
     }
+    if (sclk && threadIdx.x == 0) { const long long q = clock64(); sclk[13] += q - tq; tq = q; }
     __syncthreads();
-    if (i0 < n) {   // (c); w == NB here
-      double iv[NB];
+    if (sclk && threadIdx.x == 0) { const long long q = clock64(); sclk[14] += q - tq; tq = q; }
+    if (i0 < n) {   // (c), w == NB here: warp 0 takes the next diagonal block (and factorises it), the others the rows below it
+      const int nd = min(NB, n - i0);
+      if (warp == 0) {
+        diag_block(i0, true, k0);
+        if (sclk && threadIdx.x == 0) { const long long q = clock64(); sclk[15] += q - tq; tq = q; }
+      } else {
+        double iv[NB];
 #pragma unroll
-      for (int kk = 0; kk < NB; ++kk) iv[kk] = invd[k0 + kk];
-      const int cols = n - i0;   // trailing columns
+        for (int kk = 0; kk < NB; ++kk) iv[kk] = invd[k0 + kk];
+        const int cols = n - i0;   // trailing columns
 #pragma unroll 1
-      for (int r = warp; r < m; r += NW) {
-        double* row = S + (i0 + r) * ld + k0;
-        double li[NB];
+        for (int r = nd + warp - 1; r < m; r += NW - 1) {
+          double* row = S + (i0 + r) * ld + k0;
+          double li[NB];
 #pragma unroll
-        for (int kk = 0; kk < NB; ++kk) li[kk] = row[kk] * iv[kk];
-        const int cmax = min(r, cols - 1);
+          for (int kk = 0; kk < NB; ++kk) li[kk] = row[kk] * iv[kk];
+          const int cmax = min(r, cols - 1);
 #pragma unroll 1
-        for (int c = lane; c <= cmax; c += 32) {
-          const double* rj = S + (i0 + c) * ld + k0;
-          double acc = row[NB + c];
+          for (int c = lane; c <= cmax; c += 32) {
+            const double* rj = S + (i0 + c) * ld + k0;
+            double rv[NB];
 #pragma unroll
-          for (int kk = 0; kk < NB; ++kk) acc = fma(-li[kk], rj[kk], acc);
-          row[NB + c] = acc;
+            for (int kk = 0; kk < NB; ++kk) rv[kk] = rj[kk];
+            double acc0 = row[NB + c], acc1 = 0.0;   // two chains of four
+#pragma unroll
+            for (int kk = 0; kk < NB; kk += 2) { acc0 = fma(-li[kk], rv[kk], acc0); acc1 = fma(-li[kk + 1], rv[kk + 1], acc1); }
+            row[NB + c] = acc0 + acc1;
+          }
         }
       }
       __syncthreads();
@@ -378,10 +399,12 @@ __device__ __forceinline__ bool rig_ldlt_solve(double* S, int n, int ld, double*
       }
       __syncthreads();
       for (int i = threadIdx.x; i < k0; i += RIG_THREADS) {
+        double sv[NB], xv[NB];
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) { sv[kk] = kk < w ? S[(k0 + kk) * ld + i] : 0.0; xv[kk] = kk < w ? rhs[k0 + kk] : 0.0; }
         double av = tacc[i];
 #pragma unroll
-        for (int kk = 0; kk < NB; ++kk)
-          if (kk < w) av = fma(S[(k0 + kk) * ld + i], rhs[k0 + kk], av);
+        for (int kk = 0; kk < NB; ++kk) av = fma(sv[kk], xv[kk], av);
         tacc[i] = av;
       }
       __syncthreads();
@@ -523,7 +546,7 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
         for (int q = 0; q < 36; ++q) acc[q] = 0.0;
         if (live && r < DE) {
           const int64_t end = P.dpair_ptr[d + 1];
-#pragma unroll 2
+#pragma unroll 4
           for (int64_t idx = P.dpair_ptr[d]; idx < end; ++idx) {
             const int2 pr = P.pairs[idx];
             if (pr.x < 0) continue;
