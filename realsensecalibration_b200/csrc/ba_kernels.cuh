@@ -477,11 +477,7 @@ k_fobs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const
   const int64_t end = min(begin + ch, fobs_ptr[chunk_seg[c] + 1]);
   double acc[NV_F];
   d_fobs_seg<RD>(lane, begin, end, fobs, RES, JF0, JF1, acc);
-#pragma unroll
-  for (int k = 0; k < NV_F; ++k) {
-    const double s = warp_sum(acc[k]);
-    if (lane == 0) partial[(int64_t)c * NV_F + k] = s;
-  }
+  group_sum_store<NV_F, 32>(acc, lane, partial + (int64_t)c * NV_F, true);
 }
 
 // out[seg][NV] = sum of the chunk partials of the segment, fixed order.  One warp per segment.
@@ -550,16 +546,7 @@ __device__ __forceinline__ void d_e_M(int64_t t, int64_t ne, const int64_t* __re
       }
     }
   }
-  if (G > 1) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k)
-#pragma unroll
-      for (int off = G / 2; off > 0; off >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], off, G);
-  }
-  if (live && g == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) ME[e * NV + k] = acc[k];
-  }
+  group_sum_store<NV, G>(acc, g, ME + (live ? e : 0) * NV, live);
 }
 template <int RD, int DE, int G>
 __global__ void __launch_bounds__(128)
@@ -597,14 +584,7 @@ __device__ __forceinline__ void d_inc_W(int64_t t, int64_t ninc, const int64_t* 
         for (int a = 0; a < 6; ++a) acc[k * 6 + a] = fma(re[k], rf[a], acc[k * 6 + a]);
     }
   }
-#pragma unroll
-  for (int k = 0; k < 36; ++k)
-#pragma unroll
-    for (int off = G / 2; off > 0; off >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], off, G);
-  if (live && g == 0) {
-#pragma unroll
-    for (int k = 0; k < 36; ++k) Wt[i * 36 + k] = acc[k];
-  }
+  group_sum_store<36, G>(acc, g, Wt + (live ? i : 0) * 36, live);
 }
 template <int RD>
 __global__ void __launch_bounds__(128)
@@ -731,11 +711,7 @@ k_finc_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const
   const int64_t end = min(begin + ch, finc_ptr[chunk_seg[c] + 1]);
   double acc[6];
   d_finc_seg(lane, begin, end, finc, vb, acc);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const double s = warp_sum(acc[k]);
-    if (lane == 0) partial[(int64_t)c * 6 + k] = s;
-  }
+  group_sum_store<6, 32>(acc, lane, partial + (int64_t)c * 6, true);
 }
 
 // sum over incidence pairs (i,j) of Y_i Y_j^T = Yt_i^T Yt_j for one destination block, chunk partials (36 values).
@@ -775,11 +751,7 @@ k_pairs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, cons
   const int64_t end = min(begin + ch, dpair_ptr[chunk_seg[c] + 1]);
   double acc[36];
   d_pairs_seg<DE>(lane, begin, end, pairs, Yt, acc);
-#pragma unroll
-  for (int q = 0; q < 36; ++q) {
-    const double s = warp_sum(acc[q]);
-    if (lane == 0) partial[(int64_t)c * 36 + q] = s;
-  }
+  group_sum_store<36, 32>(acc, lane, partial + (int64_t)c * 36, true);
 }
 
 // Model B: sum over observations with (f0,f1) == (fa,fb) of JF0^T JF1, chunk partials (36 values).  One warp per chunk,
@@ -816,11 +788,7 @@ k_dobs_partial(int nchunks, int ch, const int32_t* __restrict__ chunk_seg, const
   const int64_t end = min(begin + ch, dobs_ptr[chunk_seg[c] + 1]);
   double acc[36];
   d_dobs_seg<RD>(lane, begin, end, dobs, JF0, JF1, acc);
-#pragma unroll
-  for (int k = 0; k < 36; ++k) {
-    const double s = warp_sum(acc[k]);
-    if (lane == 0) partial[(int64_t)c * 36 + k] = s;
-  }
+  group_sum_store<36, 32>(acc, lane, partial + (int64_t)c * 36, true);
 }
 
 // Dense RCS: S[fa,fb] = Q - P (and its transpose).  One thread per (dest, entry).

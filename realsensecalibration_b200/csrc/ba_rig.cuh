@@ -81,35 +81,6 @@ __device__ __forceinline__ double rig_now_s() {
   return 1e-9 * (double)t;
 }
 
-// Sum of 36 values over a group of 8 lanes by halving: after three exchanges every lane holds 5 (or 4) of the 36 sums and
-// stores them (32 shuffles instead of the 108 of a butterfly per value).  Whole warps call this; fixed order.
-__device__ __forceinline__ void group8_sum36_store(const double* acc, int lane, double* __restrict__ dst, bool live) {
-  const bool b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
-  double v1[18], v2[9], v3[5];
-#pragma unroll
-  for (int q = 0; q < 18; ++q) {
-    const double send = b2 ? acc[q] : acc[18 + q], keep = b2 ? acc[18 + q] : acc[q];
-    v1[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int q = 0; q < 9; ++q) {
-    const double send = b1 ? v1[q] : v1[9 + q], keep = b1 ? v1[9 + q] : v1[q];
-    v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-#pragma unroll
-  for (int q = 0; q < 5; ++q) {   // bit 0 clear keeps [0, 5), set keeps [5, 9)
-    const double hi = q < 4 ? v2[5 + q] : 0.0;
-    const double send = b0 ? v2[q] : hi, keep = b0 ? hi : v2[q];
-    v3[q] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-  }
-  if (live) {
-    const int base = (b2 ? 18 : 0) + (b1 ? 9 : 0) + (b0 ? 5 : 0), cnt = b0 ? 4 : 5;
-#pragma unroll
-    for (int q = 0; q < 5; ++q)
-      if (q < cnt) dst[base + q] = v3[q];
-  }
-}
-
 // tables at x (candidate = false) or at the candidate point
 template <int MODEL>
 __device__ __forceinline__ void rig_tables(const RigParams& P, bool candidate) {
@@ -191,11 +162,7 @@ __device__ __forceinline__ void rig_normal_parts(const RigParams& P) {
   for (int64_t f = warp; f < P.nf; f += NW) {
     double acc[NV_F];
     d_fobs_seg<RD>(lane, P.fobs_ptr[f], P.fobs_ptr[f + 1], P.fobs, P.RES, P.JF0, P.JF1, acc);
-#pragma unroll
-    for (int k = 0; k < NV_F; ++k) {
-      const double s = warp_sum(acc[k]);
-      if (lane == 0) P.HG[f * NV_F + k] = s;
-    }
+    group_sum_store<NV_F, 32>(acc, lane, P.HG + f * NV_F, true);
   }
   for (int64_t base = 0; base < P.ne * GE; base += RIG_THREADS) d_e_M<RD, DE, GE>(base + threadIdx.x, P.ne, P.e_ptr, P.RES, P.JE, P.ME);
   if (RD == 8) {   // Model B
@@ -222,7 +189,7 @@ __device__ __forceinline__ void rig_normal_parts(const RigParams& P) {
             for (int b = 0; b < 6; ++b) acc[a * 6 + b] = fma(ra[a], rb[b], acc[a * 6 + b]);
         }
       }
-      group8_sum36_store(acc, lane, P.Qacc + (int64_t)(live ? d : 0) * 36, live);
+      group_sum_store<36, 8>(acc, lane, P.Qacc + (int64_t)(live ? d : 0) * 36, live);
     }
   }
   __syncthreads();
@@ -531,11 +498,7 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
     for (int64_t f = warp; f < P.nf; f += NW) {
       double acc[6];
       d_finc_seg(lane, P.finc_ptr[f], P.finc_ptr[f + 1], P.finc, P.vb, acc);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const double s = warp_sum(acc[k]);
-        if (lane == 0) P.vsum[f * 6 + k] = s;
-      }
+      group_sum_store<6, 32>(acc, lane, P.vsum + f * 6, true);
     }
     if (P.ndest >= 2 * NW) {   // many destinations with short pair lists (a rig): 8 lanes (= rows of Yt) per destination
       for (int base = 0; base < P.ndest; base += RIG_THREADS / 8) {
@@ -559,17 +522,13 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
               for (int b = 0; b < 6; ++b) acc[a * 6 + b] = fma(yi[a], yj[b], acc[a * 6 + b]);
           }
         }
-        group8_sum36_store(acc, lane, P.Pacc + (int64_t)(live ? d : 0) * 36, live);
+        group_sum_store<36, 8>(acc, lane, P.Pacc + (int64_t)(live ? d : 0) * 36, live);
       }
     } else {
       for (int d = warp; d < P.ndest; d += NW) {
         double acc[36];
         d_pairs_seg<DE>(lane, P.dpair_ptr[d], P.dpair_ptr[d + 1], P.pairs, P.Yt, acc);
-#pragma unroll
-        for (int q = 0; q < 36; ++q) {
-          const double s = warp_sum(acc[q]);
-          if (lane == 0) P.Pacc[(int64_t)d * 36 + q] = s;
-        }
+        group_sum_store<36, 32>(acc, lane, P.Pacc + (int64_t)d * 36, true);
       }
     }
     __syncthreads();

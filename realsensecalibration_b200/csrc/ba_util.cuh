@@ -185,6 +185,41 @@ __device__ __forceinline__ double warp_max(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
   return v;
 }
+// Sum of N values over a group of G lanes (G a power of two, the group aligned in the warp) by recursive halving: at every
+// step a lane keeps one half of its values and sends the other half to its partner, so the whole reduction costs about N
+// shuffles instead of N log2(G) and ends with the N sums spread over the lanes, which store them to dst[0..N).  Whole warps
+// call this; the order of the additions is fixed.
+template <int N, int G>
+struct HalvingSum {
+  static __device__ __forceinline__ void run(const double* v, int lane, int base, int cnt, double* __restrict__ dst, bool live) {
+    if constexpr (G == 1) {
+#pragma unroll
+      for (int q = 0; q < N; ++q)
+        if (live && q < cnt) dst[base + q] = v[q];
+    } else {
+      constexpr int LO = (N + 1) / 2, HI = N - LO, H = G / 2;
+      const bool up = (lane & H) != 0;
+      double w[LO > 0 ? LO : 1];
+#pragma unroll
+      for (int q = 0; q < LO; ++q) {
+        const double hi = q < HI ? v[LO + q] : 0.0;
+        const double send = up ? v[q] : hi, keep = up ? hi : v[q];
+        w[q] = keep + __shfl_xor_sync(0xffffffffu, send, H);
+      }
+      const int c2 = up ? max(cnt - LO, 0) : min(cnt, LO);
+      HalvingSum<LO, H>::run(w, lane, base + (up ? LO : 0), c2, dst, live);
+    }
+  }
+};
+template <int G>
+struct HalvingSum<0, G> {
+  static __device__ __forceinline__ void run(const double*, int, int, int, double* __restrict__, bool) {}
+};
+template <int N, int G>
+__device__ __forceinline__ void group_sum_store(const double* v, int lane, double* __restrict__ dst, bool live) {
+  HalvingSum<N, G>::run(v, lane, 0, N, dst, live);
+}
+
 // Sum over a CTA in a fixed tree order; result valid in thread 0.  blockDim.x multiple of 32, <= 1024.
 __device__ __forceinline__ double block_sum(double v, double* smem32) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
