@@ -75,6 +75,34 @@ __device__ __forceinline__ double rig_max(double v, double* red) {
   __syncthreads();
   return red[32];
 }
+// N values at once (sum, or maximum where is_max): one pair of barriers for all of them; every thread gets the results in v
+template <int N>
+__device__ __forceinline__ void rig_reduce(double* v, const bool* is_max, double* red /* N * 8 + N */) {
+  constexpr int NW = RIG_THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double y = __shfl_down_sync(0xffffffffu, x, o);
+      x = is_max[k] ? fmax(x, y) : x + y;
+    }
+    if (lane == 0) red[k * NW + warp] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    const int k = threadIdx.x;
+    double x = red[k * NW];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) x = is_max[k] ? fmax(x, red[k * NW + w]) : x + red[k * NW + w];
+    red[N * NW + k] = x;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = red[N * NW + k];
+  __syncthreads();   // red may be reused right away
+}
 __device__ __forceinline__ double rig_now_s() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -199,21 +227,22 @@ __device__ __forceinline__ void rig_normal_parts(const RigParams& P) {
 template <int DE>
 __device__ __forceinline__ void rig_gradient(const RigParams& P, double* red, double& gmax, double& gnorm) {
   constexpr int NU = DE * (DE + 1) / 2;
-  double mx = 0.0, sq = 0.0;
+  double mx = 0.0, sqe = 0.0, sqf = 0.0;
   for (int64_t t = threadIdx.x; t < P.ne * DE; t += RIG_THREADS) {
     double m = 0.0, s = 0.0;
     d_gradient_norm<DE, NU + DE, NU>(t, P.e_ptr, P.xe, P.se, P.ME, m, s);
-    mx = fmax(mx, m); sq += s;
+    mx = fmax(mx, m); sqe += s;
   }
-  const double g2e = rig_sum(sq, red);
-  sq = 0.0;
   for (int64_t t = threadIdx.x; t < P.nf * 6; t += RIG_THREADS) {
     double m = 0.0, s = 0.0;
     d_gradient_norm<6, NV_F, 21>(t, P.f_act_ptr, P.xf, P.sf, P.HG, m, s);
-    mx = fmax(mx, m); sq += s;
+    mx = fmax(mx, m); sqf += s;
   }
-  const double g2f = rig_sum(sq, red);
-  gmax = rig_max(mx, red);
+  double v[3] = {sqe, sqf, mx};
+  const bool is_max[3] = {false, false, true};
+  rig_reduce<3>(v, is_max, red);
+  const double g2e = v[0], g2f = v[1];
+  gmax = v[2];
   gnorm = sqrt(g2e + g2f);
 }
 
@@ -393,7 +422,7 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
   double* invd = rhs + P.ld;                // n
   double* tacc = invd + P.n;                // n: the backward solve's running sums
   double* blk = tacc + P.n;                 // 65: the scaled diagonal block of the current panel, and its verdict
-  __shared__ double red[34];
+  __shared__ double red[48];   // rig_reduce<5>: 5 * 8 warps + 5; rig_sum: 32 + 1
   __shared__ RigState st;
   __shared__ int status;
   __shared__ double sh_radius;
@@ -554,13 +583,13 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
     for (int64_t rr = tid; rr < P.nb * RD; rr += RIG_THREADS)
       acc += d_model_cost_row<RD, DE, NSLOT>(rr, P.ob_e, P.ob_f0, P.ob_f1, P.RES, P.JE, P.JF0, P.JF1, P.ye, P.yf);
     lap(7);
-    const double mcc = rig_sum(acc, red);
-    double x2 = 0.0, d2 = 0.0;
-    for (int64_t t = tid; t < P.ne * DE; t += RIG_THREADS) { double a = 0.0, b = 0.0; d_candidate<DE>(t, P.e_ptr, P.xe, P.se, P.ye, P.xe_c, a, b); x2 += a; d2 += b; }
-    const double xe2 = rig_sum(x2, red), de2 = rig_sum(d2, red);
-    x2 = 0.0; d2 = 0.0;
-    for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS) { double a = 0.0, b = 0.0; d_candidate<6>(t, P.f_act_ptr, P.xf, P.sf, P.yf, P.xf_c, a, b); x2 += a; d2 += b; }
-    const double xf2 = rig_sum(x2, red), df2 = rig_sum(d2, red);
+    double x2e = 0.0, d2e = 0.0, x2f = 0.0, d2f = 0.0;
+    for (int64_t t = tid; t < P.ne * DE; t += RIG_THREADS) { double a = 0.0, b = 0.0; d_candidate<DE>(t, P.e_ptr, P.xe, P.se, P.ye, P.xe_c, a, b); x2e += a; d2e += b; }
+    for (int64_t t = tid; t < P.nf * 6; t += RIG_THREADS) { double a = 0.0, b = 0.0; d_candidate<6>(t, P.f_act_ptr, P.xf, P.sf, P.yf, P.xf_c, a, b); x2f += a; d2f += b; }
+    double sv[5] = {acc, x2e, d2e, x2f, d2f};
+    const bool no_max[5] = {false, false, false, false, false};
+    rig_reduce<5>(sv, no_max, red);
+    const double mcc = sv[0], xe2 = sv[1], de2 = sv[2], xf2 = sv[3], df2 = sv[4];
     lap(8);
     const double cand = rig_cost_candidate<MODEL>(P, red);
     lap(9);

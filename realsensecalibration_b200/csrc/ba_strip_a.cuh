@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(512) k_sa_tile_entries(SaEntParams P) {
   int* start = count + P.segw;       // [segw + 1]
   int* stage = start + P.segw + 1;   // [stage_cap]
   __shared__ int nfl_s;
+  __shared__ int wtot[32];
   const int t = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
   const SaTile T = P.tiles[t];
   const SaStrip S = P.strips[t / P.L];
@@ -582,10 +583,33 @@ __global__ void __launch_bounds__(512) k_sa_tile_entries(SaEntParams P) {
     }
     __syncthreads();
     if (pass == 0) {
-      if (tid == 0) {   // exclusive scan over <= 1536 + 1 owner slots
-        int a = 0;
-        for (int v = 0; v < P.segw; ++v) { start[v] = a; a += count[v]; }
-        start[P.segw] = a;
+      {   // exclusive scan over <= 1536 + 1 owner slots: a run of consecutive slots per thread, warp scans, the warp totals by warp 0
+        const int per = (P.segw + nthr - 1) / nthr;
+        const int v0 = tid * per, v1 = min(v0 + per, P.segw);
+        int mine = 0;
+        for (int v = v0; v < v1; ++v) mine += count[v];
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, incl, o);
+          if ((tid & 31) >= o) incl += y;
+        }
+        if ((tid & 31) == 31) wtot[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+          const int nw = nthr >> 5;
+          int t = tid < nw ? wtot[tid] : 0;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, t, o);
+            if (tid >= o) t += y;
+          }
+          if (tid < nw) wtot[tid] = t;   // inclusive totals of the warps
+        }
+        __syncthreads();
+        int a = incl - mine + ((tid >> 5) > 0 ? wtot[(tid >> 5) - 1] : 0);
+        for (int v = v0; v < v1; ++v) { start[v] = a; a += count[v]; }
+        if (tid == nthr - 1) start[P.segw] = wtot[(nthr >> 5) - 1];
       }
       __syncthreads();
       for (int v = tid; v < P.segw; v += nthr) {
