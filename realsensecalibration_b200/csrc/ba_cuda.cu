@@ -1041,7 +1041,6 @@ int rig_run(ba_cuda_problem* p, bool begin, int32_t max_new) {
   P.rows = reinterpret_cast<ba_cuda_iteration*>(p->rig_buf.p + sizeof(RigState));
   P.opt = L.opt; P.loss = p->loss;
   static const bool clocks = env_int("BA_RIG_CLOCKS", 0, 1, 0) != 0;
-  P.dbg = env_int("BA_RIG_DBG", 0, 255, 0);
   DVec<long long> clk;
   if (clocks) { BA_TRY(clk.alloc_zero(16, p->st)); P.clk = clk.p; }
   int64_t left = max_new;

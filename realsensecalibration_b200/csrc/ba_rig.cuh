@@ -5,10 +5,10 @@
 // B200: on the multi-kernel pipeline one LM iteration is ~40 launches and two host round trips, all latency.  Here one
 // CTA of 256 threads walks the same phases (the item functions d_* of ba_kernels.cuh, so the arithmetic per observation,
 // per block and per incidence is the generic pipeline's) separated by __syncthreads instead of launches; the reduced camera
-// system lives in shared memory and is factorised there (LDL^T, one barrier per column; the two triangular solves run in
-// one warp's registers); TrustRegionMinimizer's loop variables and its decisions (lm_begin / lm_iterate of ba_cuda.cu,
-// statement for statement) are taken by thread 0 between barriers, and the iteration rows are written to HBM for the host
-// to read after the launch.  Every sum is a fixed tree: results are bitwise reproducible.
+// system lives in shared memory and is factorised there (L D L^T by panels of 8 columns with look-ahead, the right-hand side
+// riding along as one more row; rig_ldlt_solve below); TrustRegionMinimizer's loop variables and its decisions (lm_begin /
+// lm_iterate of ba_cuda.cu, statement for statement) are taken by thread 0 between barriers, and the iteration rows are
+// written to HBM for the host to read after the launch.  Every sum is a fixed tree: results are bitwise reproducible.
 #pragma once
 #include "ba_kernels.cuh"
 
@@ -54,7 +54,6 @@ struct RigParams {
   int32_t begin;      // 1: start from `init` and run iteration zero first (TrustRegionMinimizer::IterationZero)
   int32_t max_new;    // at most this many loop iterations in this launch (begin + max_new <= RIG_ROWS_CAP)
   RigState init;
-  int dbg;            // BA_RIG_DBG: timing experiments only (results are wrong)
   long long* clk;     // BA_RIG_CLOCKS=1: SM cycles per phase (16 slots), thread 0's view
   ba_cuda_options opt;
   LossSpec loss;
@@ -253,7 +252,7 @@ __device__ __forceinline__ void rig_gradient(const RigParams& P, double* red, do
 // forward substitution.  The backward substitution runs by panels too (8 dependent steps in warp 0, then one thread per row
 // above).  Returns false (uniformly) when a pivot is not positive.
 __device__ __forceinline__ bool rig_ldlt_solve(double* S, int n, int ld, double* rhs, double* invd, double* tacc, double* blk /* 64 + 1 */,
-                                               double* __restrict__ y_out, long long* sclk, int dbg = 0) {
+                                               double* __restrict__ y_out, long long* sclk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = RIG_THREADS / 32;
   constexpr int NB = 8;
@@ -369,7 +368,7 @@ __device__ __forceinline__ bool rig_ldlt_solve(double* S, int n, int ld, double*
   }
   long long t_f = 0;
   if (sclk && threadIdx.x == 0) t_f = clock64();
-  if (!(dbg & 4)) {
+  {
     // backward, L'^T x = v  (x_k = (v_k - sum_{i>k} L'[i][k] x_i) / d_k; v = row n of S), panels from the last: tacc[k] collects the sum over
     // the rows already solved; warp 0 finishes the panel, then one thread per row above adds the panel's contribution
     for (int i = threadIdx.x; i < n; i += RIG_THREADS) tacc[i] = 0.0;
@@ -569,7 +568,7 @@ __global__ void __launch_bounds__(RIG_THREADS, 1) k_rig_lm(const RigParams P) {
       d_diag_rhs_dense(t, P.HG, NV_F, P.vsum, 6, &sh_radius, opt.min_lm_diagonal, opt.max_lm_diagonal, P.ld, S, rhs);
     __syncthreads();
     lap(5);
-    const bool pd = rig_ldlt_solve(S, P.n, P.ld, rhs, invd, tacc, blk, P.yf, P.clk ? sclk : nullptr, P.dbg);
+    const bool pd = rig_ldlt_solve(S, P.n, P.ld, rhs, invd, tacc, blk, P.yf, P.clk ? sclk : nullptr);
     lap(6);
     if (!pd) {
       for (int t = tid; t < P.n; t += RIG_THREADS) P.yf[t] = 0.0;
