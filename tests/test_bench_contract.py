@@ -52,3 +52,15 @@ def test_both_arms_print_the_same_config_keys():
     ours = bench.config_of(job, "small", 1, 2, 300)
     assert sorted(ref) == sorted(ours)
     assert all(ref[k] == ours[k] for k in ref if k not in ("rcs_solver", "rcs_dim"))
+
+
+def test_committed_traffic_numbers_belong_to_this_tree():
+    """roofline.traffic comes from profiles/traffic.json; bench.py only uses an entry whose kernel_source_hash is the hash of
+    the csrc/ files it runs.  The committed entries of the default workload must be the ones of the committed kernels."""
+    import json
+    import bench
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+        t = json.load(f)
+    h = bench.kernel_source_hash()
+    entries = t[bench.DEFAULT_WORKLOAD]
+    assert entries and all(e.get("kernel_source_hash") == h for e in entries.values()), (h, entries)
